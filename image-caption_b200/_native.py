@@ -1,0 +1,78 @@
+"""ctypes binding of libicap.so (include/icap.h).  There is deliberately NO fallback: if the
+library is missing or the device is not sm_100 every call raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_uint64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libicap.so")
+
+F32, BF16 = 0, 1
+EPI_NONE, EPI_RELU, EPI_RELU_MASK = 0, 1, 2
+
+P, I, L, F, U = c_void_p, c_int, c_int64, c_float, c_uint64
+
+# name -> argtypes, in the order of include/icap.h
+SIGNATURES = {
+    "icap_version": [],
+    "icap_sm_check": [I],
+    "icap_gemm": [I, I, I, L, L, L, P, L, P, L, P, L, I, P, I, P, L, I, I, P],
+    "icap_mha_fwd": [I, L, L, L, L, L, L, P, L, P, L, P, L, P, L, P, I, F, U, P, P, P],
+    "icap_mha_bwd": [I, L, L, L, L, L, L, P, L, P, L, P, L, P, L, P, L, P, L, P, L, P, I, F, U, P, P],
+    "icap_add_ln_fwd": [I, I, L, L, P, P, L, P, P, P, P, P, P, I, F, U, P, F, P],
+    "icap_add_ln_bwd": [I, L, L, P, P, P, P, P, P, P, P, P, P, P, P, F, U, P, P],
+    "icap_xent": [I, L, L, P, L, P, I, P, P, I, P],
+    "icap_xent_finalize": [L, P, P, I, P, P],
+    "icap_argmax": [I, L, L, P, L, P, L, P, P],
+    "icap_beam_select": [I, L, L, L, P, L, P, L, P, P, P, P, I, P],
+    "icap_beam_reorder": [L, L, L, L, P, P, P, P, P, P, P],
+    "icap_mha_decode": [I, L, L, L, L, L, P, L, P, L, P, L, L, P, L, P, L, P, L, I, P, L, P, P],
+    "icap_copy2d": [P, I, L, P, I, L, L, L, I, P],
+    "icap_region_valid": [P, L, L, P, P, P],
+    "icap_caption_prep": [P, I, L, L, I, P, P, P, P, P, P, P],
+    "icap_embed_fwd": [I, I, P, L, L, L, P, P, P, I, P],
+    "icap_embed_bwd": [I, P, L, L, I, P, P, P],
+    "icap_colsum": [I, L, L, P, L, P, P],
+    "icap_adam_step": [L, P, P, P, P, P, F, F, F, F, P, I, P, F, P],
+    "icap_scale": [P, L, P, F, P],
+}
+
+
+class IcapError(RuntimeError):
+    pass
+
+
+_lib = None
+launch_count = 0          # number of C-ABI kernel-launching calls made by this process (bench: gpu_launches)
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise IcapError(f"{LIB_PATH} is missing: run `python __graft_entry__.py build` "
+                            "(image-caption_b200 has no CPU / PyTorch fallback)")
+        l = ctypes.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.argtypes = args
+            fn.restype = c_int
+        l.icap_last_error.argtypes = []
+        l.icap_last_error.restype = c_char_p
+        _lib = l
+    return _lib
+
+
+def last_error() -> str:
+    return lib().icap_last_error().decode("utf-8", "replace")
+
+
+def call(name: str, *args) -> None:
+    """Invoke an entry point; raise IcapError on a non-zero return code."""
+    global launch_count
+    rc = getattr(lib(), name)(*args)
+    if rc != 0:
+        raise IcapError(f"{name} failed (rc={rc}): {last_error()}")
+    launch_count += 1

@@ -1,0 +1,430 @@
+// Fused multi-head attention, forward and backward, one CTA per (batch, head).
+//
+//   S = (Q / sqrt(dk)) K^T ; masked_fill(-inf) ; P = softmax(S) ; P = dropout(P) ; O = P V
+//
+// Follows ScaledDotProductAttention.forward + the head split/merge of MultiHeadAttention.forward
+// (modules.py:16-27, 72-84): q is scaled BEFORE QK^T, masks are True = masked, dropout is applied
+// to the probabilities.  Masks are generated in-kernel: key j of batch b is masked iff
+// kvalid[b*Lk+j] == 0 (kvalid may be null) or (causal and j > i)  (model.py:202-209,311-319,421-430).
+// Heads are addressed in the packed projection outputs ([rows, H*dh] with a row stride), so no
+// transpose / contiguous copies exist.  The whole (b, h) problem (L <= ~128) lives in shared memory;
+// softmax uses warp shuffles.  Backward recomputes P (nothing but Q, K, V, dO is read).
+#include "icap_common.cuh"
+
+namespace {
+
+constexpr int NT = 128;
+
+struct AttnDims {
+  int Lq, Lk, LkP, dk, dv, H;
+};
+
+template <typename T>
+__device__ __forceinline__ void load_rows(float* dst, int dst_ld, const T* src, int64_t src_ld, int rows, int cols,
+                                          float scale) {
+  const int cq = cols >> 2;
+  for (int u = threadIdx.x; u < rows * cq; u += NT) {
+    const int r = u / cq, c = (u % cq) * 4;
+    float v[4];
+    load4(src + (int64_t)r * src_ld + c, v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dst[r * dst_ld + c + j] = v[j] * scale;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void load_rows_t(float* dst, int dst_ld, const T* src, int64_t src_ld, int rows, int cols) {
+  // dst[c][r] = src[r][c]; columns beyond `rows` up to dst_ld are zeroed by the caller
+  const int cq = cols >> 2;
+  for (int u = threadIdx.x; u < rows * cq; u += NT) {
+    const int r = u % rows, c = (u / rows) * 4;
+    float v[4];
+    load4(src + (int64_t)r * src_ld + c, v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dst[(c + j) * dst_ld + r] = v[j];
+  }
+}
+
+// P[i][j] for all i, j (softmax with masks, then dropout); P has row stride LkP, padded cols = 0
+__device__ __forceinline__ void scores_softmax(float* P, float* Praw, const float* Qs, const float* Kt,
+                                               const uint8_t* kvalid_b, const AttnDims& D, int causal, float p_drop,
+                                               uint32_t thresh, uint64_t seed, uint64_t bh) {
+  const int jq = D.LkP >> 2;
+  for (int u = threadIdx.x; u < D.Lq * jq; u += NT) {
+    const int i = u / jq, j0 = (u % jq) * 4;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const float* q = Qs + i * D.dk;
+    for (int c = 0; c < D.dk; ++c) {
+      const float qc = q[c];
+      const float4 k = *reinterpret_cast<const float4*>(Kt + c * D.LkP + j0);
+      a0 = fmaf(qc, k.x, a0); a1 = fmaf(qc, k.y, a1); a2 = fmaf(qc, k.z, a2); a3 = fmaf(qc, k.w, a3);
+    }
+    *reinterpret_cast<float4*>(P + i * D.LkP + j0) = make_float4(a0, a1, a2, a3);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  for (int i = warp; i < D.Lq; i += NT / 32) {
+    float* row = P + i * D.LkP;
+    float mx = -INFINITY;
+    for (int j = lane; j < D.LkP; j += 32) {
+      const bool masked = (j >= D.Lk) || (kvalid_b && !kvalid_b[j]) || (causal && j > i);
+      const float s = masked ? -INFINITY : row[j];
+      row[j] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < D.LkP; j += 32) {
+      const float e = (row[j] == -INFINITY) ? 0.f : expf(row[j] - mx);
+      row[j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;   // all-masked row -> inf/NaN exactly like the reference's softmax
+    for (int j = lane; j < D.LkP; j += 32) {
+      float p = row[j] * inv;
+      if (j >= D.Lk) p = 0.f;
+      if (Praw) Praw[i * D.LkP + j] = p;
+      if (p_drop > 0.f) {
+        const uint64_t e = (bh * D.Lq + i) * (uint64_t)D.LkP + j;
+        const uint4 r = philox4x32(seed, e >> 2);
+        const uint32_t rv = (e & 3) == 0 ? r.x : (e & 3) == 1 ? r.y : (e & 3) == 2 ? r.z : r.w;
+        p = rv >= thresh ? p * keep_scale : 0.f;
+      }
+      row[j] = p;
+    }
+  }
+  __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NT)
+mha_fwd_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, int64_t ldk, const T* __restrict__ v,
+               int64_t ldv, T* __restrict__ o, int64_t ldo, const uint8_t* __restrict__ kvalid, AttnDims D, int causal,
+               float p_drop, uint32_t thresh, uint64_t seed, const int* __restrict__ seed_dev,
+               float* __restrict__ attn_mean) {
+  if (seed_dev) seed += (uint64_t)(*seed_dev) * 0x9E3779B97F4A7C15ull;
+  extern __shared__ __align__(16) float sm[];
+  const int b = blockIdx.x / D.H, h = blockIdx.x % D.H;
+  float* Qs = sm;                         // [Lq][dk]
+  float* Kt = Qs + D.Lq * D.dk;           // [dk][LkP]
+  float* Vs = Kt + D.dk * D.LkP;          // [Lk][dv]
+  float* P = Vs + D.Lk * D.dv;            // [Lq][LkP]
+  for (int u = threadIdx.x; u < D.dk * D.LkP; u += NT) Kt[u] = 0.f;
+  __syncthreads();
+  load_rows(Qs, D.dk, q + (int64_t)b * D.Lq * ldq + h * D.dk, ldq, D.Lq, D.dk, (1.f / sqrtf((float)D.dk)));
+  load_rows_t(Kt, D.LkP, k + (int64_t)b * D.Lk * ldk + h * D.dk, ldk, D.Lk, D.dk);
+  load_rows(Vs, D.dv, v + (int64_t)b * D.Lk * ldv + h * D.dv, ldv, D.Lk, D.dv, 1.f);
+  __syncthreads();
+  scores_softmax(P, nullptr, Qs, Kt, kvalid ? kvalid + (int64_t)b * D.Lk : nullptr, D, causal, p_drop, thresh, seed,
+                 (uint64_t)blockIdx.x);
+  if (attn_mean) {   // mean over heads of the probabilities (greedy visualisation, model.py:123)
+    for (int u = threadIdx.x; u < D.Lq * D.Lk; u += NT) {
+      const int i = u / D.Lk, j = u % D.Lk;
+      atomicAdd(attn_mean + ((int64_t)b * D.Lq + i) * D.Lk + j, P[i * D.LkP + j] / (float)D.H);
+    }
+  }
+  const int cq = D.dv >> 2;
+  for (int u = threadIdx.x; u < D.Lq * cq; u += NT) {
+    const int i = u / cq, c0 = (u % cq) * 4;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* prow = P + i * D.LkP;
+    for (int j = 0; j < D.Lk; ++j) {
+      const float p = prow[j];
+      const float4 vv = *reinterpret_cast<const float4*>(Vs + j * D.dv + c0);
+      acc[0] = fmaf(p, vv.x, acc[0]); acc[1] = fmaf(p, vv.y, acc[1]);
+      acc[2] = fmaf(p, vv.z, acc[2]); acc[3] = fmaf(p, vv.w, acc[3]);
+    }
+    store4(o + ((int64_t)b * D.Lq + i) * ldo + h * D.dv + c0, acc);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NT)
+mha_bwd_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, int64_t ldk, const T* __restrict__ v,
+               int64_t ldv, const T* __restrict__ dout, int64_t lddo, T* __restrict__ dq, int64_t lddq,
+               T* __restrict__ dk_, int64_t lddk, T* __restrict__ dv_, int64_t lddv,
+               const uint8_t* __restrict__ kvalid, AttnDims D, int causal, float p_drop, uint32_t thresh,
+               uint64_t seed, const int* __restrict__ seed_dev) {
+  if (seed_dev) seed += (uint64_t)(*seed_dev) * 0x9E3779B97F4A7C15ull;
+  extern __shared__ __align__(16) float sm[];
+  const int b = blockIdx.x / D.H, h = blockIdx.x % D.H;
+  float* Qs = sm;                          // [Lq][dk]  (pre-scaled)
+  float* Kn = Qs + D.Lq * D.dk;            // [Lk][dk]
+  float* Kt = Kn + D.Lk * D.dk;            // [dk][LkP]
+  float* Vt = Kt + D.dk * D.LkP;           // [dv][LkP]
+  float* dO = Vt + D.dv * D.LkP;           // [Lq][dv]
+  float* Pd = dO + D.Lq * D.dv;            // [Lq][LkP]  dropped probabilities, later dS
+  float* Pr = Pd + D.Lq * D.LkP;           // [Lq][LkP]  raw probabilities
+  const float scale = (1.f / sqrtf((float)D.dk));
+  for (int u = threadIdx.x; u < (D.dk + D.dv) * D.LkP; u += NT) Kt[u] = 0.f;   // Kt and Vt are adjacent
+  __syncthreads();
+  load_rows(Qs, D.dk, q + (int64_t)b * D.Lq * ldq + h * D.dk, ldq, D.Lq, D.dk, scale);
+  load_rows(Kn, D.dk, k + (int64_t)b * D.Lk * ldk + h * D.dk, ldk, D.Lk, D.dk, 1.f);
+  load_rows_t(Kt, D.LkP, k + (int64_t)b * D.Lk * ldk + h * D.dk, ldk, D.Lk, D.dk);
+  load_rows_t(Vt, D.LkP, v + (int64_t)b * D.Lk * ldv + h * D.dv, ldv, D.Lk, D.dv);
+  load_rows(dO, D.dv, dout + (int64_t)b * D.Lq * lddo + h * D.dv, lddo, D.Lq, D.dv, 1.f);
+  __syncthreads();
+  scores_softmax(Pd, Pr, Qs, Kt, kvalid ? kvalid + (int64_t)b * D.Lk : nullptr, D, causal, p_drop, thresh, seed,
+                 (uint64_t)blockIdx.x);
+
+  // dV[j][c] = sum_i Pd[i][j] dO[i][c]
+  {
+    const int cq = D.dv >> 2;
+    for (int u = threadIdx.x; u < D.Lk * cq; u += NT) {
+      const int j = u / cq, c0 = (u % cq) * 4;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int i = 0; i < D.Lq; ++i) {
+        const float p = Pd[i * D.LkP + j];
+        const float4 g = *reinterpret_cast<const float4*>(dO + i * D.dv + c0);
+        acc[0] = fmaf(p, g.x, acc[0]); acc[1] = fmaf(p, g.y, acc[1]);
+        acc[2] = fmaf(p, g.z, acc[2]); acc[3] = fmaf(p, g.w, acc[3]);
+      }
+      store4(dv_ + ((int64_t)b * D.Lk + j) * lddv + h * D.dv + c0, acc);
+    }
+  }
+  __syncthreads();
+  // dPd[i][j] = sum_c dO[i][c] V[j][c]; then dP = dropout-mask * dPd / (1-p), recovered from Pd/Pr
+  {
+    const int jq = D.LkP >> 2;
+    for (int u = threadIdx.x; u < D.Lq * jq; u += NT) {
+      const int i = u / jq, j0 = (u % jq) * 4;
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
+      const float* g = dO + i * D.dv;
+      for (int c = 0; c < D.dv; ++c) {
+        const float gc = g[c];
+        const float4 vv = *reinterpret_cast<const float4*>(Vt + c * D.LkP + j0);
+        a[0] = fmaf(gc, vv.x, a[0]); a[1] = fmaf(gc, vv.y, a[1]);
+        a[2] = fmaf(gc, vv.z, a[2]); a[3] = fmaf(gc, vv.w, a[3]);
+      }
+      // Pd = keep ? Pr/(1-p) : 0  =>  dP = keep ? dPd/(1-p) : 0 ;  P*dP = Pd * dPd
+#pragma unroll
+      for (int t = 0; t < 4; ++t) Pd[i * D.LkP + j0 + t] *= a[t];     // now holds P * dP
+    }
+  }
+  __syncthreads();
+  // dS[i][j] = P dP - P * sum_j (P dP)
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = warp; i < D.Lq; i += NT / 32) {
+      float sum = 0.f;
+      for (int j = lane; j < D.Lk; j += 32) sum += Pd[i * D.LkP + j];
+      sum = warp_sum(sum);
+      for (int j = lane; j < D.LkP; j += 32)
+        Pd[i * D.LkP + j] = (j < D.Lk) ? Pd[i * D.LkP + j] - Pr[i * D.LkP + j] * sum : 0.f;
+    }
+  }
+  __syncthreads();
+  // dQ[i][c] = scale * sum_j dS[i][j] K[j][c]
+  {
+    const int cq = D.dk >> 2;
+    for (int u = threadIdx.x; u < D.Lq * cq; u += NT) {
+      const int i = u / cq, c0 = (u % cq) * 4;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int j = 0; j < D.Lk; ++j) {
+        const float s = Pd[i * D.LkP + j];
+        const float4 kk = *reinterpret_cast<const float4*>(Kn + j * D.dk + c0);
+        acc[0] = fmaf(s, kk.x, acc[0]); acc[1] = fmaf(s, kk.y, acc[1]);
+        acc[2] = fmaf(s, kk.z, acc[2]); acc[3] = fmaf(s, kk.w, acc[3]);
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) acc[t] *= scale;
+      store4(dq + ((int64_t)b * D.Lq + i) * lddq + h * D.dk + c0, acc);
+    }
+    // dK[j][c] = sum_i dS[i][j] Qs[i][c]
+    for (int u = threadIdx.x; u < D.Lk * cq; u += NT) {
+      const int j = u / cq, c0 = (u % cq) * 4;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int i = 0; i < D.Lq; ++i) {
+        const float s = Pd[i * D.LkP + j];
+        const float4 qq = *reinterpret_cast<const float4*>(Qs + i * D.dk + c0);
+        acc[0] = fmaf(s, qq.x, acc[0]); acc[1] = fmaf(s, qq.y, acc[1]);
+        acc[2] = fmaf(s, qq.z, acc[2]); acc[3] = fmaf(s, qq.w, acc[3]);
+      }
+      store4(dk_ + ((int64_t)b * D.Lk + j) * lddk + h * D.dk + c0, acc);
+    }
+  }
+}
+
+template <typename K>
+int ensure_smem(K kern, size_t smem, size_t* cur) {
+  if (smem > *cur) {   // one process drives one GPU, so a process-wide high-water mark is enough
+    ICAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    *cur = smem;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// KV-cached decoding attention: one query per row, one warp per (row, head).
+//   lanes own keys for the score / softmax phase, then own output columns for P.V
+template <typename T>
+__global__ void __launch_bounds__(NT)
+mha_decode_kernel(int rows, int H, int Lk, int dk, int dv, const T* __restrict__ q, int64_t ldq,
+                  const T* __restrict__ kc, int64_t ldk, const T* __restrict__ vc, int64_t ldv, int kv_rows_per_seq,
+                  T* __restrict__ o, int64_t ldo, const int* __restrict__ slot, int64_t slot_ld,
+                  const int* __restrict__ tokens, int64_t tok_ld, int pad_idx, const uint8_t* __restrict__ kvalid,
+                  int rows_per_image, float* __restrict__ attn_mean) {
+  extern __shared__ __align__(16) float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blockIdx.x * (NT / 32) + warp;
+  if (unit >= rows * H) return;
+  const int row = unit / H, h = unit % H;
+  float* qs = sm + warp * dk;
+  const float scale = 1.f / sqrtf((float)dk);
+  for (int c = lane; c < dk; c += 32) qs[c] = to_f32(q[(int64_t)row * ldq + h * dk + c]) * scale;
+  __syncwarp();
+  const bool self_mode = tokens != nullptr;             // self-attention over the KV cache
+  const int seq = row / rows_per_image;                 // cross-attention: image index
+  float p[4];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    const int j = jj * 32 + lane;
+    float s = -INFINITY;
+    if (j < Lk) {
+      bool masked;
+      int64_t krow;
+      if (self_mode) {
+        masked = tokens[(int64_t)row * tok_ld + j] == pad_idx;
+        krow = (int64_t)(slot ? slot[(int64_t)row * slot_ld + j] : row) * kv_rows_per_seq + j;
+      } else {
+        masked = kvalid && !kvalid[(int64_t)seq * Lk + j];
+        krow = (int64_t)seq * kv_rows_per_seq + j;
+      }
+      if (!masked) {
+        const T* kp = kc + krow * ldk + h * dk;
+        float acc = 0.f;
+        for (int c = 0; c < dk; c += 4) {
+          float kv4[4];
+          load4(kp + c, kv4);
+          acc = fmaf(qs[c], kv4[0], acc); acc = fmaf(qs[c + 1], kv4[1], acc);
+          acc = fmaf(qs[c + 2], kv4[2], acc); acc = fmaf(qs[c + 3], kv4[3], acc);
+        }
+        s = acc;
+      }
+    }
+    p[jj] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    p[jj] = (p[jj] == -INFINITY) ? 0.f : expf(p[jj] - mx);
+    sum += p[jj];
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    p[jj] *= inv;
+    const int j = jj * 32 + lane;
+    if (attn_mean && j < Lk) atomicAdd(attn_mean + (int64_t)row * Lk + j, p[jj] / (float)H);
+  }
+  for (int c0 = lane; c0 < dv; c0 += 32) {
+    float acc = 0.f;
+    for (int j = 0; j < Lk; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, p[j >> 5], j & 31);
+      int64_t vrow;
+      if (self_mode) vrow = (int64_t)(slot ? slot[(int64_t)row * slot_ld + j] : row) * kv_rows_per_seq + j;
+      else vrow = (int64_t)seq * kv_rows_per_seq + j;
+      if (pj != 0.f) acc = fmaf(pj, to_f32(vc[vrow * ldv + h * dv + c0]), acc);
+    }
+    o[(int64_t)row * ldo + h * dv + c0] = from_f32<T>(acc);
+  }
+}
+
+int check_dims(const char* fn, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t dk, int64_t dv) {
+  ICAP_ARG(B > 0 && H > 0 && Lq > 0 && Lk > 0, "%s: empty problem", fn);
+  ICAP_ARG(dk % 4 == 0 && dv % 4 == 0 && dk > 0 && dv > 0, "%s: head dims must be multiples of 4 (dk=%lld dv=%lld)", fn,
+           (long long)dk, (long long)dv);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int icap_mha_fwd(int dtype, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t dk, int64_t dv,
+                            const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                            void* o, int64_t ldo, const uint8_t* kvalid, int causal, float p_drop, uint64_t seed,
+                            const int* seed_dev, float* attn_mean, void* stream) {
+  if (int rc = check_dims("icap_mha_fwd", B, H, Lq, Lk, dk, dv)) return rc;
+  AttnDims D{(int)Lq, (int)Lk, (int)((Lk + 3) & ~3), (int)dk, (int)dv, (int)H};
+  const size_t smem = sizeof(float) * ((size_t)D.Lq * D.dk + (size_t)D.dk * D.LkP + (size_t)D.Lk * D.dv +
+                                       (size_t)D.Lq * D.LkP);
+  ICAP_ARG(smem <= 227 * 1024, "icap_mha_fwd: (Lq=%d, Lk=%d, dk=%d, dv=%d) needs %zu B of shared memory", D.Lq, D.Lk,
+           D.dk, D.dv, smem);
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint32_t th = dropout_threshold(p_drop);
+  if (dtype == ICAP_F32) {
+    static size_t cur = 48 * 1024;
+    if (int rc = ensure_smem(mha_fwd_kernel<float>, smem, &cur)) return rc;
+    mha_fwd_kernel<float><<<(unsigned)(B * H), NT, smem, st>>>((const float*)q, ldq, (const float*)k, ldk,
+                                                               (const float*)v, ldv, (float*)o, ldo, kvalid, D, causal,
+                                                               p_drop, th, seed, seed_dev, attn_mean);
+  } else {
+    static size_t cur = 48 * 1024;
+    if (int rc = ensure_smem(mha_fwd_kernel<bf16>, smem, &cur)) return rc;
+    mha_fwd_kernel<bf16><<<(unsigned)(B * H), NT, smem, st>>>((const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v,
+                                                              ldv, (bf16*)o, ldo, kvalid, D, causal, p_drop, th, seed,
+                                                              seed_dev, attn_mean);
+  }
+  ICAP_LAUNCH_CHECK("icap_mha_fwd");
+  return 0;
+}
+
+extern "C" int icap_mha_bwd(int dtype, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t dk, int64_t dv,
+                            const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                            const void* dout, int64_t lddo, void* dq, int64_t lddq, void* dk_out, int64_t lddk,
+                            void* dv_out, int64_t lddv, const uint8_t* kvalid, int causal, float p_drop, uint64_t seed,
+                            const int* seed_dev, void* stream) {
+  if (int rc = check_dims("icap_mha_bwd", B, H, Lq, Lk, dk, dv)) return rc;
+  AttnDims D{(int)Lq, (int)Lk, (int)((Lk + 3) & ~3), (int)dk, (int)dv, (int)H};
+  const size_t smem = sizeof(float) * ((size_t)D.Lq * D.dk + (size_t)D.Lk * D.dk + (size_t)D.dk * D.LkP +
+                                       (size_t)D.dv * D.LkP + (size_t)D.Lq * D.dv + 2 * (size_t)D.Lq * D.LkP);
+  ICAP_ARG(smem <= 227 * 1024, "icap_mha_bwd: (Lq=%d, Lk=%d, dk=%d, dv=%d) needs %zu B of shared memory", D.Lq, D.Lk,
+           D.dk, D.dv, smem);
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint32_t th = dropout_threshold(p_drop);
+  if (dtype == ICAP_F32) {
+    static size_t cur = 48 * 1024;
+    if (int rc = ensure_smem(mha_bwd_kernel<float>, smem, &cur)) return rc;
+    mha_bwd_kernel<float><<<(unsigned)(B * H), NT, smem, st>>>(
+        (const float*)q, ldq, (const float*)k, ldk, (const float*)v, ldv, (const float*)dout, lddo, (float*)dq, lddq,
+        (float*)dk_out, lddk, (float*)dv_out, lddv, kvalid, D, causal, p_drop, th, seed, seed_dev);
+  } else {
+    static size_t cur = 48 * 1024;
+    if (int rc = ensure_smem(mha_bwd_kernel<bf16>, smem, &cur)) return rc;
+    mha_bwd_kernel<bf16><<<(unsigned)(B * H), NT, smem, st>>>(
+        (const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v, ldv, (const bf16*)dout, lddo, (bf16*)dq, lddq,
+        (bf16*)dk_out, lddk, (bf16*)dv_out, lddv, kvalid, D, causal, p_drop, th, seed, seed_dev);
+  }
+  ICAP_LAUNCH_CHECK("icap_mha_bwd");
+  return 0;
+}
+
+extern "C" int icap_mha_decode(int dtype, int64_t rows, int64_t H, int64_t Lk, int64_t dk, int64_t dv, const void* q,
+                               int64_t ldq, const void* kc, int64_t ldk, const void* vc, int64_t ldv,
+                               int64_t kv_rows_per_seq, void* o, int64_t ldo, const int* slot, int64_t slot_ld,
+                               const int* tokens, int64_t tok_ld, int pad_idx, const uint8_t* kvalid,
+                               int64_t rows_per_image, float* attn_mean, void* stream) {
+  if (int rc = check_dims("icap_mha_decode", rows, H, 1, Lk, dk, dv)) return rc;
+  ICAP_ARG(Lk <= 128, "icap_mha_decode: at most 128 keys per query (got %lld)", (long long)Lk);
+  ICAP_ARG(slot == nullptr || tokens != nullptr, "icap_mha_decode: a slot table needs the token buffer (self mode)");
+  ICAP_ARG(rows_per_image >= 1, "icap_mha_decode: rows_per_image must be >= 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (NT / 32) * dk * sizeof(float);
+  const unsigned grid = (unsigned)ceil_div64(rows * H, NT / 32);
+  if (dtype == ICAP_F32)
+    mha_decode_kernel<float><<<grid, NT, smem, st>>>((int)rows, (int)H, (int)Lk, (int)dk, (int)dv, (const float*)q, ldq,
+                                                     (const float*)kc, ldk, (const float*)vc, ldv,
+                                                     (int)kv_rows_per_seq, (float*)o, ldo, slot, slot_ld, tokens,
+                                                     tok_ld, pad_idx, kvalid, (int)rows_per_image, attn_mean);
+  else
+    mha_decode_kernel<bf16><<<grid, NT, smem, st>>>((int)rows, (int)H, (int)Lk, (int)dk, (int)dv, (const bf16*)q, ldq,
+                                                    (const bf16*)kc, ldk, (const bf16*)vc, ldv, (int)kv_rows_per_seq,
+                                                    (bf16*)o, ldo, slot, slot_ld, tokens, tok_ld, pad_idx, kvalid,
+                                                    (int)rows_per_image, attn_mean);
+  ICAP_LAUNCH_CHECK("icap_mha_decode");
+  return 0;
+}

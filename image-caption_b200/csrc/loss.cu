@@ -1,0 +1,317 @@
+// Vocabulary-side kernels: fused log-softmax + NLL (+ in-place dlogits), loss finalisation
+// (mean over non-pad targets, optional focal transform), greedy argmax, and the beam-search
+// candidate selection (softmax + running score + top-k over k*V + parent/token split).
+//
+// Reference semantics:
+//   CrossEntropyLoss(ignore_index=pad, reduction='mean')                 model.py:76,93-96
+//   FocalLoss: ce scalar -> (1 - exp(-ce))^2 * ce                        loss.py:20-28
+//   greedy: argmax(Softmax(logits))                                      model.py:125-128
+//   beam  : Softmax(logits) + prev_score, cat over beams, topk(k),
+//           parent = idx // V, token = idx % V                           model.py:181-198
+//           (LogSoftmax in the PolicyNetwork variant, model_RL.py:72)
+#include "icap_common.cuh"
+
+namespace {
+
+constexpr int NT = 256;
+
+__device__ __forceinline__ float block_max(float v, float* red) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int i = 1; i < NT / 32; ++i) r = fmaxf(r, red[i]);
+  return r;
+}
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+  for (int i = 0; i < NT / 32; ++i) r += red[i];   // fixed order: deterministic
+  return r;
+}
+
+// one block per row; the row is staged once in shared memory as fp32 when it fits
+template <typename T>
+__global__ void __launch_bounds__(NT)
+xent_kernel(int V, T* __restrict__ logits, int64_t ldl, const int* __restrict__ targets, int ignore_index,
+            const float* __restrict__ inv_count, float* __restrict__ row_loss, int write_grad, int cached, int vec) {
+  extern __shared__ __align__(16) float xs[];
+  __shared__ float red[NT / 32];
+  const int row = blockIdx.x;
+  T* x = logits + (int64_t)row * ldl;
+  const int tgt = targets[row];
+  const bool valid = tgt != ignore_index;
+  if (!valid && !write_grad) {
+    if (threadIdx.x == 0) row_loss[row] = 0.f;
+    return;
+  }
+  float mx = -INFINITY;
+  const int V4 = vec ? (V & ~3) : 0;
+  for (int j = threadIdx.x * 4; j < V4; j += NT * 4) {
+    float v[4];
+    load4(x + j, v);
+    if (cached) *reinterpret_cast<float4*>(xs + j) = make_float4(v[0], v[1], v[2], v[3]);
+    mx = fmaxf(fmaxf(mx, fmaxf(v[0], v[1])), fmaxf(v[2], v[3]));
+  }
+  for (int j = V4 + threadIdx.x; j < V; j += NT) {
+    const float v = to_f32(x[j]);
+    if (cached) xs[j] = v;
+    mx = fmaxf(mx, v);
+  }
+  mx = block_max(mx, red);
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < V; j += NT) sum += expf((cached ? xs[j] : to_f32(x[j])) - mx);
+  sum = block_sum(sum, red);
+  const float lse = mx + logf(sum);
+  if (threadIdx.x == 0) row_loss[row] = valid ? lse - (cached ? xs[tgt] : to_f32(x[tgt])) : 0.f;
+  if (write_grad) {
+    const float sc = valid ? *inv_count : 0.f;
+    for (int j = threadIdx.x * 4; j < V4; j += NT * 4) {
+      float g[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float xv = cached ? xs[j + t] : to_f32(x[j + t]);
+        g[t] = (expf(xv - lse) - ((j + t) == tgt ? 1.f : 0.f)) * sc;
+      }
+      store4(x + j, g);
+    }
+    for (int j = V4 + threadIdx.x; j < V; j += NT) {
+      const float xv = cached ? xs[j] : to_f32(x[j]);
+      x[j] = from_f32<T>((expf(xv - lse) - (j == tgt ? 1.f : 0.f)) * sc);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NT)
+xent_finalize_kernel(int M, const float* __restrict__ row_loss, const float* __restrict__ inv_count, int focal,
+                     float* __restrict__ out) {
+  __shared__ float red[NT / 32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < M; i += NT) s += row_loss[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    const float ce = s * (*inv_count);
+    if (focal) {
+      const float pt = expf(-ce), om = 1.f - pt;
+      out[0] = om * om * ce;
+      out[1] = 2.f * om * pt * ce + om * om;   // d focal / d ce : scales every gradient
+    } else {
+      out[0] = ce;
+      out[1] = 1.f;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NT)
+argmax_kernel(int V, const T* __restrict__ logits, int64_t ldl, int* __restrict__ out, int64_t out_stride,
+              float* __restrict__ gap) {
+  __shared__ float sv[NT], sv2[NT];
+  __shared__ int si[NT];
+  const T* x = logits + (int64_t)blockIdx.x * ldl;
+  float best = -INFINITY, second = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int j = threadIdx.x; j < V; j += NT) {
+    const float v = to_f32(x[j]);
+    if (v > best) { second = best; best = v; bi = j; }
+    else if (v > second) second = v;
+  }
+  sv[threadIdx.x] = best; sv2[threadIdx.x] = second; si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int s = NT / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      const float a = sv[threadIdx.x], b = sv[threadIdx.x + s];
+      const int ia = si[threadIdx.x], ib = si[threadIdx.x + s];
+      const float a2 = sv2[threadIdx.x], b2 = sv2[threadIdx.x + s];
+      if (b > a || (b == a && ib < ia)) {       // lowest index wins ties (torch.argmax on CPU)
+        sv[threadIdx.x] = b; si[threadIdx.x] = ib; sv2[threadIdx.x] = fmaxf(a, b2);
+      } else {
+        sv2[threadIdx.x] = fmaxf(a2, b);
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[(int64_t)blockIdx.x * out_stride] = si[0];
+    if (gap) gap[blockIdx.x] = sv[0] - sv2[0];
+  }
+}
+
+constexpr int KMAX = 8;   // beam width limit; lists hold KMAX+1 entries so the k/(k+1) gap can be reported
+
+struct Cand { float s; int i; };
+__device__ __forceinline__ bool better(float s, int i, float s2, int i2) { return s > s2 || (s == s2 && i < i2); }
+
+template <typename T>
+__global__ void __launch_bounds__(NT)
+beam_select_kernel(int kin, int V, const T* __restrict__ logits, int64_t ldl, const float* __restrict__ prev,
+                   int kout, float* __restrict__ out_score, int* __restrict__ out_parent, int* __restrict__ out_token,
+                   float* __restrict__ gap, int log_domain) {
+  __shared__ float red[NT / 32];
+  __shared__ float s_mx[KMAX], s_den[KMAX];
+  __shared__ float h_s[NT];
+  __shared__ int h_i[NT], h_t[NT];
+  const int b = blockIdx.x;
+  for (int r = 0; r < kin; ++r) {
+    const T* x = logits + ((int64_t)b * kin + r) * ldl;
+    float mx = -INFINITY;
+    for (int j = threadIdx.x; j < V; j += NT) mx = fmaxf(mx, to_f32(x[j]));
+    mx = block_max(mx, red);
+    float sum = 0.f;
+    for (int j = threadIdx.x; j < V; j += NT) sum += expf(to_f32(x[j]) - mx);
+    sum = block_sum(sum, red);
+    if (threadIdx.x == 0) { s_mx[r] = mx; s_den[r] = log_domain ? logf(sum) : sum; }
+  }
+  __syncthreads();
+  const int L = kout + 1;
+  Cand lst[KMAX + 1];
+#pragma unroll
+  for (int t = 0; t <= KMAX; ++t) { lst[t].s = -INFINITY; lst[t].i = 0x7fffffff; }
+  for (int r = 0; r < kin; ++r) {
+    const T* x = logits + ((int64_t)b * kin + r) * ldl;
+    const float mx = s_mx[r], den = s_den[r], pv = prev ? prev[b * kin + r] : 0.f;
+    for (int j = threadIdx.x; j < V; j += NT) {
+      const float xv = to_f32(x[j]);
+      const float sc = (log_domain ? (xv - mx - den) : (expf(xv - mx) / den)) + pv;
+      const int idx = r * V + j;
+      if (better(sc, idx, lst[L - 1].s, lst[L - 1].i)) {
+        lst[L - 1].s = sc; lst[L - 1].i = idx;
+#pragma unroll
+        for (int t = KMAX; t > 0; --t) {
+          if (t < L && better(lst[t].s, lst[t].i, lst[t - 1].s, lst[t - 1].i)) {
+            Cand c = lst[t]; lst[t] = lst[t - 1]; lst[t - 1] = c;
+          }
+        }
+      }
+    }
+  }
+  // block merge: L rounds of "best remaining head"
+  int head = 0;
+  float kth = 0.f;
+  for (int round = 0; round < L; ++round) {
+    h_s[threadIdx.x] = head < L ? lst[head].s : -INFINITY;
+    h_i[threadIdx.x] = head < L ? lst[head].i : 0x7fffffff;
+    h_t[threadIdx.x] = threadIdx.x;
+    __syncthreads();
+    for (int s = NT / 2; s > 0; s >>= 1) {
+      if (threadIdx.x < s) {
+        if (better(h_s[threadIdx.x + s], h_i[threadIdx.x + s], h_s[threadIdx.x], h_i[threadIdx.x])) {
+          h_s[threadIdx.x] = h_s[threadIdx.x + s];
+          h_i[threadIdx.x] = h_i[threadIdx.x + s];
+          h_t[threadIdx.x] = h_t[threadIdx.x + s];
+        }
+      }
+      __syncthreads();
+    }
+    const int winner = h_t[0];
+    const float ws = h_s[0];
+    const int wi = h_i[0];
+    if (threadIdx.x == winner) ++head;
+    if (threadIdx.x == 0) {
+      if (round < kout) {
+        out_score[b * kout + round] = ws;
+        out_parent[b * kout + round] = wi / V;
+        out_token[b * kout + round] = wi % V;
+        kth = ws;
+      } else if (gap) {
+        gap[b] = kth - ws;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// tokens_out[b, s, 0..t] = tokens_in[b, parent[b,s], 0..t]; tokens_out[b, s, t+1] = token[b,s]
+// the same gather is applied to the KV-cache slot table (which physical row holds position t')
+__global__ void beam_reorder_kernel(int B, int k, int Tmax, int t, const int* __restrict__ parent,
+                                    const int* __restrict__ token, const int* __restrict__ tok_in,
+                                    int* __restrict__ tok_out, const int* __restrict__ slot_in,
+                                    int* __restrict__ slot_out) {
+  const int row = blockIdx.x;            // b*k + s
+  const int b = row / k;
+  const int src = b * k + parent[row];
+  for (int j = threadIdx.x; j <= t + 1 && j < Tmax; j += blockDim.x) {
+    tok_out[(int64_t)row * Tmax + j] = (j == t + 1) ? token[row] : tok_in[(int64_t)src * Tmax + j];
+    if (slot_in) slot_out[(int64_t)row * Tmax + j] = (j == t + 1) ? row : slot_in[(int64_t)src * Tmax + j];
+  }
+}
+
+}  // namespace
+
+extern "C" int icap_xent(int dtype, int64_t M, int64_t V, void* logits, int64_t ldl, const int* targets,
+                         int ignore_index, const float* inv_count, float* row_loss, int write_grad, void* stream) {
+  ICAP_ARG(M > 0 && V > 0 && logits && targets && row_loss && inv_count, "icap_xent: null/empty argument");
+  const int esz = dtype == ICAP_F32 ? 4 : 2;
+  const int vec = ((uintptr_t)logits % 16 == 0) && ((ldl * esz) % 16 == 0);
+  size_t smem = (size_t)V * 4;
+  int cached = smem <= 200 * 1024;
+  if (!cached) smem = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  static size_t cur_f = 48 * 1024, cur_b = 48 * 1024;
+  if (dtype == ICAP_F32) {
+    if (smem > cur_f) {
+      ICAP_CUDA(cudaFuncSetAttribute(xent_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cur_f = smem;
+    }
+    xent_kernel<float><<<(unsigned)M, NT, smem, st>>>((int)V, (float*)logits, ldl, targets, ignore_index, inv_count,
+                                                      row_loss, write_grad, cached, vec);
+  } else {
+    if (smem > cur_b) {
+      ICAP_CUDA(cudaFuncSetAttribute(xent_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cur_b = smem;
+    }
+    xent_kernel<bf16><<<(unsigned)M, NT, smem, st>>>((int)V, (bf16*)logits, ldl, targets, ignore_index, inv_count,
+                                                     row_loss, write_grad, cached, vec);
+  }
+  ICAP_LAUNCH_CHECK("icap_xent");
+  return 0;
+}
+
+extern "C" int icap_xent_finalize(int64_t M, const float* row_loss, const float* inv_count, int focal, float* out2,
+                                  void* stream) {
+  ICAP_ARG(M > 0 && row_loss && inv_count && out2, "icap_xent_finalize: null/empty argument");
+  xent_finalize_kernel<<<1, NT, 0, (cudaStream_t)stream>>>((int)M, row_loss, inv_count, focal, out2);
+  ICAP_LAUNCH_CHECK("icap_xent_finalize");
+  return 0;
+}
+
+extern "C" int icap_argmax(int dtype, int64_t M, int64_t V, const void* logits, int64_t ldl, int* out,
+                           int64_t out_stride, float* gap, void* stream) {
+  ICAP_ARG(M > 0 && V > 0 && logits && out, "icap_argmax: null/empty argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == ICAP_F32) argmax_kernel<float><<<(unsigned)M, NT, 0, st>>>((int)V, (const float*)logits, ldl, out, out_stride, gap);
+  else argmax_kernel<bf16><<<(unsigned)M, NT, 0, st>>>((int)V, (const bf16*)logits, ldl, out, out_stride, gap);
+  ICAP_LAUNCH_CHECK("icap_argmax");
+  return 0;
+}
+
+extern "C" int icap_beam_select(int dtype, int64_t B, int64_t kin, int64_t V, const void* logits, int64_t ldl,
+                                const float* prev_score, int64_t kout, float* out_score, int* out_parent,
+                                int* out_token, float* gap, int log_domain, void* stream) {
+  ICAP_ARG(B > 0 && V > 0 && logits && out_score && out_parent && out_token, "icap_beam_select: null/empty argument");
+  ICAP_ARG(kin >= 1 && kin <= KMAX && kout >= 1 && kout <= KMAX, "icap_beam_select: beam width must be in [1, %d]", KMAX);
+  ICAP_ARG(kin * V > kout, "icap_beam_select: fewer candidates than beams");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == ICAP_F32)
+    beam_select_kernel<float><<<(unsigned)B, NT, 0, st>>>((int)kin, (int)V, (const float*)logits, ldl, prev_score,
+                                                          (int)kout, out_score, out_parent, out_token, gap, log_domain);
+  else
+    beam_select_kernel<bf16><<<(unsigned)B, NT, 0, st>>>((int)kin, (int)V, (const bf16*)logits, ldl, prev_score,
+                                                         (int)kout, out_score, out_parent, out_token, gap, log_domain);
+  ICAP_LAUNCH_CHECK("icap_beam_select");
+  return 0;
+}
+
+extern "C" int icap_beam_reorder(int64_t B, int64_t k, int64_t Tmax, int64_t t, const int* parent, const int* token,
+                                 const int* tok_in, int* tok_out, const int* slot_in, int* slot_out, void* stream) {
+  ICAP_ARG(B > 0 && k > 0 && parent && token && tok_in && tok_out, "icap_beam_reorder: null/empty argument");
+  ICAP_ARG(tok_in != tok_out && (slot_in == nullptr || slot_in != slot_out), "icap_beam_reorder: must be out of place");
+  beam_reorder_kernel<<<(unsigned)(B * k), 32, 0, (cudaStream_t)stream>>>((int)B, (int)k, (int)Tmax, (int)t, parent,
+                                                                         token, tok_in, tok_out, slot_in, slot_out);
+  ICAP_LAUNCH_CHECK("icap_beam_reorder");
+  return 0;
+}

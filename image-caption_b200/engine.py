@@ -1,0 +1,712 @@
+"""Kernel orchestration for the caption Transformer on one B200.
+
+`CaptionEngine` owns the flat parameter / gradient / optimizer buffers and turns one call of the
+reference's hot path (core/TRANSFORMER/model.py: Transformer.forward, generate_caption_vector,
+beam_search; core/models.py:115-126 train_step) into a sequence of libicap.so launches on the
+current CUDA stream.  PyTorch is used only as the device allocator / stream owner; every FLOP and
+every byte moved on the device goes through the C ABI (include/icap.h).  There is no CPU path.
+
+Two arithmetic modes:
+  * "bf16": activations + weight shadow in bf16, tcgen05 GEMMs, fp32 statistics / softmax / loss /
+            master weights / Adam.
+  * "fp32": everything fp32 with true-fp32 SIMT GEMMs (parity mode, 1e-4 relative vs the reference).
+
+Backward is explicit (no autograd): each forward block appends a closure to a tape; gradients of
+multi-consumer activations are carried as lists and summed inside the fused LayerNorm backward.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+
+from . import _native as N
+from ._native import BF16, F32, call
+
+
+@dataclass
+class ModelConfig:
+    """Constructor arguments of the reference Transformer (model.py:10-36)."""
+    num_vocab: int
+    max_length: int
+    encode_dim_positions: int
+    encode_dim_features: int
+    output_name: str = "x"
+    encode_mask: bool = False
+    pad_idx: int = 0
+    dropout: float = 0.2
+    encode_input_size: int = 512
+    encode_q_k_dim: int = 512
+    encode_v_dim: int = 512
+    encode_hidden_size: int = 2048
+    encode_num_blocks: int = 6
+    encode_num_heads: int = 8
+    dim_word_embedding: int = 512
+    decode_input_size: int = 512
+    decode_q_k_dim: int = 512
+    decode_v_dim: int = 512
+    decode_hidden_size: int = 2048
+    decode_num_blocks: int = 6
+    decode_num_heads: int = 8
+    move_first_image_feature: bool = False
+    split_position: bool = False
+    split_image_objects: bool = False
+
+    @property
+    def focal(self) -> bool:
+        return self.output_name.find("FocalLoss") != -1      # model.py:73
+
+    @property
+    def T(self) -> int:                                        # decoder positions (model.py:383)
+        return self.max_length - 1
+
+
+ATTN_DROPOUT = 0.1      # ScaledDotProductAttention default, never overridden (modules.py:8,55-56)
+LN_EPS = 1e-6
+
+
+def param_layout(cfg: ModelConfig) -> "Dict[str, Tuple[int, ...]]":
+    """Parameter/buffer shapes in the reference's registration order (== state_dict order)."""
+    d, F_, E = cfg.encode_input_size, cfg.encode_hidden_size, cfg.dim_word_embedding
+    shapes: Dict[str, Tuple[int, ...]] = {}
+
+    def mha(p, d_in, dk, dv):
+        shapes[p + ".q_linear.weight"] = (dk, d_in)
+        shapes[p + ".k_linear.weight"] = (dk, d_in)
+        shapes[p + ".v_linear.weight"] = (dv, d_in)
+        shapes[p + ".layer_norm.weight"] = (d_in,)
+        shapes[p + ".layer_norm.bias"] = (d_in,)
+        shapes[p + ".joint_linear.weight"] = (d_in, dv)
+
+    def ffn(p, d_in, hid):
+        shapes[p + ".position_wise_1.weight"] = (hid, d_in)
+        shapes[p + ".position_wise_1.bias"] = (hid,)
+        shapes[p + ".position_wise_2.weight"] = (d_in, hid)
+        shapes[p + ".position_wise_2.bias"] = (d_in,)
+        shapes[p + ".layer_norm.weight"] = (d_in,)
+        shapes[p + ".layer_norm.bias"] = (d_in,)
+
+    if cfg.split_position:
+        shapes["encoder.object_embedding.weight"] = (d, cfg.encode_dim_positions - 4)
+        shapes["encoder.position_embedding.weight"] = (d, 4)
+    else:
+        shapes["encoder.position_embedding.weight"] = (d, cfg.encode_dim_positions)
+    if cfg.split_image_objects:
+        mha("encoder.image_encoder.multihead_attention", d, cfg.encode_q_k_dim, cfg.encode_v_dim)
+        ffn("encoder.image_encoder.feed_forward", d, F_)
+    shapes["encoder.feature_embedding.weight"] = (d, cfg.encode_dim_features)
+    shapes["encoder.norm.weight"] = (d,)
+    shapes["encoder.norm.bias"] = (d,)
+    for i in range(cfg.encode_num_blocks):
+        mha(f"encoder.encoder.{i}.multihead_attention", d, cfg.encode_q_k_dim, cfg.encode_v_dim)
+        ffn(f"encoder.encoder.{i}.feed_forward", d, F_)
+    dd, dF = cfg.decode_input_size, cfg.decode_hidden_size
+    shapes["decoder.word_embedding.weight"] = (cfg.num_vocab, E)
+    shapes["decoder.word_embedding_linear.weight"] = (dd, E)
+    shapes["decoder.position_embedding.pos_table"] = (1, cfg.max_length - 1, dd)      # buffer
+    shapes["decoder.norm.weight"] = (dd,)
+    shapes["decoder.norm.bias"] = (dd,)
+    if cfg.move_first_image_feature:
+        shapes["decoder.position_wise_1.weight"] = (dF, dd)
+        shapes["decoder.position_wise_1.bias"] = (dF,)
+        shapes["decoder.position_wise_2.weight"] = (dd, dF)
+        shapes["decoder.position_wise_2.bias"] = (dd,)
+        shapes["decoder.layer_norm.weight"] = (dd,)
+        shapes["decoder.layer_norm.bias"] = (dd,)
+    for i in range(cfg.decode_num_blocks):
+        mha(f"decoder.decoder.{i}.self_attention", dd, cfg.decode_q_k_dim, cfg.decode_v_dim)
+        mha(f"decoder.decoder.{i}.encode_attention", dd, cfg.decode_q_k_dim, cfg.decode_v_dim)
+        ffn(f"decoder.decoder.{i}.feed_forward", dd, dF)
+    shapes["classifer.weight"] = (cfg.num_vocab, dd)
+    shapes["classifer.bias"] = (cfg.num_vocab,)
+    return shapes
+
+
+BUFFER_NAMES = ("decoder.position_embedding.pos_table",)
+
+
+def flat_offsets(shapes: "Dict[str, Tuple[int, ...]]") -> "Tuple[Dict[str, int], int]":
+    """Offsets (in elements) of every PARAMETER in the flat buffers; 8-element aligned so that bf16
+    views are 16-byte aligned for TMA and fp32 views for float4."""
+    off, offsets = 0, {}
+    for name, shp in shapes.items():
+        if name in BUFFER_NAMES:
+            continue
+        offsets[name] = off
+        off += (math.prod(shp) + 7) // 8 * 8
+    return offsets, off
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class CaptionEngine:
+    def __init__(self, cfg: ModelConfig, flat_params: torch.Tensor, pos_table: torch.Tensor, precision: str = "bf16"):
+        assert flat_params.is_cuda and flat_params.dtype == torch.float32
+        assert precision in ("bf16", "fp32")
+        self.cfg = cfg
+        self.dev = flat_params.device
+        call("icap_sm_check", self.dev.index if self.dev.index is not None else torch.cuda.current_device())
+        self.precision = precision
+        self.act = BF16 if precision == "bf16" else F32
+        self.tdt = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.shapes = param_layout(cfg)
+        self.offsets, self.n_flat = flat_offsets(self.shapes)
+        assert flat_params.numel() == self.n_flat
+        self.p32 = flat_params
+        self.g32 = torch.zeros_like(flat_params)
+        self.p16 = torch.empty(self.n_flat, dtype=torch.bfloat16, device=self.dev) if precision == "bf16" else None
+        self.shadow_fresh = False
+        self.adam_m: Optional[torch.Tensor] = None
+        self.adam_v: Optional[torch.Tensor] = None
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.pos_table32 = pos_table.reshape(-1, pos_table.shape[-1]).contiguous()
+        self.pos_table_act = self.pos_table32.to(self.tdt)
+        self.base_seed = 0x1234ABCD
+        self.tape: Optional[List[Callable[[], None]]] = None
+        self.gr: Dict[int, List[torch.Tensor]] = {}
+        self.keep: List[torch.Tensor] = []
+        self.training = False
+        self._site = 0
+        self._stream = 0
+        self.bucket_hook: Optional[Callable[[str], None]] = None   # data-parallel: called as grads complete
+        for k in ("encode_q_k_dim", "encode_v_dim", "decode_q_k_dim", "decode_v_dim"):
+            assert getattr(cfg, k) % 8 == 0, f"{k} must be a multiple of 8"
+        assert cfg.encode_input_size == cfg.decode_input_size, \
+            "cross-attention reads encoder rows with decoder projections: widths must match (as in the reference)"
+
+    # ------------------------------------------------------------------ parameter views
+    def w(self, name: str, rows: Optional[int] = None, cols: Optional[int] = None):
+        """(pointer to the GEMM-dtype copy of a weight, numel offset) for kernels."""
+        base = self.p16 if self.precision == "bf16" else self.p32
+        return base.data_ptr() + self.offsets[name] * base.element_size()
+
+    def p(self, name: str) -> int:      # fp32 master pointer (LN affine, biases)
+        return self.p32.data_ptr() + self.offsets[name] * 4
+
+    def g(self, name: str) -> int:      # fp32 gradient pointer
+        return self.g32.data_ptr() + self.offsets[name] * 4
+
+    def refresh_shadow(self) -> None:
+        if self.precision == "bf16" and not self.shadow_fresh:
+            call("icap_copy2d", self.p32.data_ptr(), F32, self.n_flat, self.p16.data_ptr(), BF16, self.n_flat,
+                 1, self.n_flat, 0, self._s())
+            self.shadow_fresh = True
+
+    # ------------------------------------------------------------------ small helpers
+    def _s(self) -> int:
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def new(self, *shape, dtype=None, zero=False) -> torch.Tensor:
+        dt = self.tdt if dtype is None else dtype
+        t = (torch.zeros if zero else torch.empty)(*shape, dtype=dt, device=self.dev)
+        if self.tape is not None:
+            self.keep.append(t)
+        return t
+
+    def _seed(self) -> int:
+        self._site += 1
+        return (self.base_seed + 0x9E3779B1 * self._site) & 0xFFFFFFFFFFFFFFFF
+
+    def add_grad(self, x: torch.Tensor, g: torch.Tensor) -> None:
+        self.gr.setdefault(id(x), []).append(g)
+
+    def pop_grads(self, x: torch.Tensor) -> List[torch.Tensor]:
+        gs = self.gr.pop(id(x), [])
+        if len(gs) > 2:      # fold extras so the fused LN backward sees at most two
+            acc = gs[1]
+            for extra in gs[2:]:
+                call("icap_copy2d", extra.data_ptr(), self.act, extra.shape[-1], acc.data_ptr(), self.act,
+                     acc.shape[-1], extra.shape[0], extra.shape[-1], 1, self._s())
+            gs = gs[:2]
+        return gs
+
+    # ------------------------------------------------------------------ primitive launches
+    def gemm(self, a: torch.Tensor, a_kmajor: bool, b_ptr: int, ldb: int, b_kmajor: bool, M: int, Nn: int, K: int,
+             out: torch.Tensor, ldc: Optional[int] = None, bias: Optional[int] = None, epi: int = 0,
+             aux: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: int = 1,
+             lda: Optional[int] = None, a_ptr: Optional[int] = None, c_ptr: Optional[int] = None,
+             c_dtype: Optional[int] = None) -> None:
+        ab = BF16 if self.precision == "bf16" else F32
+        if c_dtype is None:
+            c_dtype = F32 if out.dtype == torch.float32 else BF16
+        call("icap_gemm", ab, int(a_kmajor), int(b_kmajor), M, Nn, K,
+             a.data_ptr() if a_ptr is None else a_ptr, a.shape[-1] if lda is None else lda, b_ptr, ldb,
+             out.data_ptr() if c_ptr is None else c_ptr, (out.shape[-1] if ldc is None else ldc), c_dtype,
+             bias, epi, _ptr(aux), (aux.shape[-1] if aux is not None else 0), int(accumulate), split_k, self._s())
+
+    def wgrad(self, dy: torch.Tensor, x: torch.Tensor, g_ptr: int, Nout: int, Kin: int, rows: int,
+              ld_dy: Optional[int] = None, dy_ptr: Optional[int] = None, ldg: Optional[int] = None) -> None:
+        """dW[Nout,Kin] += dy[rows,Nout]^T x[rows,Kin]  (fp32, split-K over rows so the grid fills the GPU)."""
+        tiles = ((Nout + 127) // 128) * ((Kin + 127) // 128)
+        split = max(1, min(32, (148 * 2) // max(1, tiles), (rows + 511) // 512))
+        ab = BF16 if self.precision == "bf16" else F32
+        call("icap_gemm", ab, 0, 0, Nout, Kin, rows, dy.data_ptr() if dy_ptr is None else dy_ptr,
+             dy.shape[-1] if ld_dy is None else ld_dy, x.data_ptr(), x.shape[-1], g_ptr, Kin if ldg is None else ldg,
+             F32, None, 0, None, 0, 1, split, self._s())
+
+    def add_ln(self, a: torch.Tensor, res: Optional[torch.Tensor], res_rows: int, norm: str,
+               rowscale: Optional[torch.Tensor], p_drop: float):
+        M, d = a.shape
+        y = self.new(M, d)
+        rec = self.tape is not None
+        mean = self.new(M, dtype=torch.float32) if rec else None
+        rstd = self.new(M, dtype=torch.float32) if rec else None
+        seed = self._seed()
+        p = p_drop if self.training else 0.0
+        call("icap_add_ln_fwd", F32 if a.dtype == torch.float32 else BF16, self.act, M, d, a.data_ptr(), _ptr(res),
+             res_rows, self.p(norm + ".weight"), self.p(norm + ".bias"), _ptr(rowscale), y.data_ptr(), _ptr(mean),
+             _ptr(rstd), int(rec), p, seed, self.step_dev.data_ptr(), LN_EPS, self._s())
+        return y, mean, rstd, seed, p
+
+    def ln_bwd(self, y: torch.Tensor, s: torch.Tensor, mean, rstd, norm: str, rowscale, p: float, seed: int,
+               dbias2: Optional[int] = None):
+        """Returns (ds, da): gradient for the residual input and for the GEMM-branch input."""
+        gs = self.pop_grads(y)
+        assert gs, "activation without gradient"
+        M, d = s.shape
+        ds = self.new(M, d)
+        da = self.new(M, d) if p > 0 else None
+        call("icap_add_ln_bwd", self.act, M, d, gs[0].data_ptr(), _ptr(gs[1]) if len(gs) > 1 else None, s.data_ptr(),
+             mean.data_ptr(), rstd.data_ptr(), self.p(norm + ".weight"), _ptr(rowscale), ds.data_ptr(), _ptr(da),
+             self.g(norm + ".weight"), self.g(norm + ".bias"), dbias2, p, seed, self.step_dev.data_ptr(), self._s())
+        return ds, (da if da is not None else ds)
+
+    # ------------------------------------------------------------------ blocks
+    def mha_block(self, prefix: str, xq: torch.Tensor, xkv: torch.Tensor, B: int, Lq: int, Lk: int, H: int,
+                  dk_tot: int, dv_tot: int, kvalid: Optional[torch.Tensor], causal: bool,
+                  attn_mean: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """MultiHeadAttention.forward (modules.py:67-92) with q = xq, k = v = xkv."""
+        cfg = self.cfg
+        d = xq.shape[1]
+        Mq, Mk = B * Lq, B * Lk
+        dk, dv = dk_tot // H, dv_tot // H
+        self_attn = xkv is xq
+        wq = prefix + ".q_linear.weight"
+        wk = prefix + ".k_linear.weight"
+        if self_attn:
+            nqkv = 2 * dk_tot + dv_tot
+            qkv = self.new(Mq, nqkv)
+            self.gemm(xq, True, self.w(wq), d, True, Mq, nqkv, d, qkv)      # packed [Wq;Wk;Wv]
+            q_ptr, k_ptr, v_ptr = qkv.data_ptr(), qkv.data_ptr() + dk_tot * qkv.element_size(), \
+                qkv.data_ptr() + 2 * dk_tot * qkv.element_size()
+            ldq = ldk = ldv = nqkv
+            kvb = None
+        else:
+            qkv = self.new(Mq, dk_tot)
+            self.gemm(xq, True, self.w(wq), d, True, Mq, dk_tot, d, qkv)
+            kvb = self.new(Mk, dk_tot + dv_tot)
+            self.gemm(xkv, True, self.w(wk), d, True, Mk, dk_tot + dv_tot, d, kvb)   # packed [Wk;Wv]
+            q_ptr, k_ptr, v_ptr = qkv.data_ptr(), kvb.data_ptr(), kvb.data_ptr() + dk_tot * kvb.element_size()
+            ldq, ldk, ldv = dk_tot, dk_tot + dv_tot, dk_tot + dv_tot
+        att = self.new(Mq, dv_tot)
+        seed_a = self._seed()
+        p_att = ATTN_DROPOUT if self.training else 0.0
+        call("icap_mha_fwd", self.act, B, H, Lq, Lk, dk, dv, q_ptr, ldq, k_ptr, ldk, v_ptr, ldv, att.data_ptr(), dv_tot,
+             _ptr(kvalid), int(causal), p_att, seed_a, self.step_dev.data_ptr(), _ptr(attn_mean), self._s())
+        o = self.new(Mq, d)
+        self.gemm(att, True, self.w(prefix + ".joint_linear.weight"), dv_tot, True, Mq, d, dv_tot, o)
+        y, mean, rstd, seed_l, p_l = self.add_ln(o, xq, Mq, prefix + ".layer_norm", None, cfg.dropout)
+
+        if self.tape is not None:
+            def bwd():
+                ds, da = self.ln_bwd(y, o, mean, rstd, prefix + ".layer_norm", None, p_l, seed_l)
+                self.add_grad(xq, ds)
+                self.wgrad(da, att, self.g(prefix + ".joint_linear.weight"), d, dv_tot, Mq)
+                datt = self.new(Mq, dv_tot)
+                self.gemm(da, True, self.w(prefix + ".joint_linear.weight"), dv_tot, False, Mq, dv_tot, d, datt)
+                esz = qkv.element_size()
+                if self_attn:
+                    dqkv = self.new(Mq, nqkv)
+                    call("icap_mha_bwd", self.act, B, H, Lq, Lk, dk, dv, q_ptr, ldq, k_ptr, ldk, v_ptr, ldv,
+                         datt.data_ptr(), dv_tot, dqkv.data_ptr(), nqkv, dqkv.data_ptr() + dk_tot * esz, nqkv,
+                         dqkv.data_ptr() + 2 * dk_tot * esz, nqkv, _ptr(kvalid), int(causal), p_att, seed_a,
+                         self.step_dev.data_ptr(), self._s())
+                    self.wgrad(dqkv, xq, self.g(wq), nqkv, d, Mq)
+                    dx = self.new(Mq, d)
+                    self.gemm(dqkv, True, self.w(wq), d, False, Mq, d, nqkv, dx)
+                    self.add_grad(xq, dx)
+                else:
+                    dq = self.new(Mq, dk_tot)
+                    dkv = self.new(Mk, dk_tot + dv_tot)
+                    call("icap_mha_bwd", self.act, B, H, Lq, Lk, dk, dv, q_ptr, ldq, k_ptr, ldk, v_ptr, ldv,
+                         datt.data_ptr(), dv_tot, dq.data_ptr(), dk_tot, dkv.data_ptr(), dk_tot + dv_tot,
+                         dkv.data_ptr() + dk_tot * esz, dk_tot + dv_tot, _ptr(kvalid), int(causal), p_att, seed_a,
+                         self.step_dev.data_ptr(), self._s())
+                    self.wgrad(dq, xq, self.g(wq), dk_tot, d, Mq)
+                    dx = self.new(Mq, d)
+                    self.gemm(dq, True, self.w(wq), d, False, Mq, d, dk_tot, dx)
+                    self.add_grad(xq, dx)
+                    self.wgrad(dkv, xkv, self.g(wk), dk_tot + dv_tot, d, Mk)
+                    # all decoder layers accumulate into ONE gradient buffer of the encoder output
+                    gl = self.gr.setdefault(id(xkv), [])
+                    if gl:
+                        self.gemm(dkv, True, self.w(wk), d, False, Mk, d, dk_tot + dv_tot, gl[0], accumulate=True)
+                    else:
+                        dxkv = self.new(Mk, d)
+                        self.gemm(dkv, True, self.w(wk), d, False, Mk, d, dk_tot + dv_tot, dxkv)
+                        gl.append(dxkv)
+            self.tape.append(bwd)
+        return y
+
+    def ffn_block(self, prefix: str, x: torch.Tensor, hidden: int, rowscale: Optional[torch.Tensor],
+                  norm: Optional[str] = None, x_in: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """FeedForward.forward (modules.py:110-122) [+ `*= non_pad_mask`, modules.py:154-155,203-204].
+        x_in (move_first_image_feature tail, model.py:451-457): GEMM input differs from the residual."""
+        cfg = self.cfg
+        M, d = x.shape
+        norm = norm or (prefix + ".layer_norm")
+        w1, b1 = prefix + ".position_wise_1.weight", prefix + ".position_wise_1.bias"
+        w2, b2 = prefix + ".position_wise_2.weight", prefix + ".position_wise_2.bias"
+        gin = x if x_in is None else x_in
+        h = self.new(M, hidden)
+        self.gemm(gin, True, self.w(w1), d, True, M, hidden, d, h, bias=self.p(b1), epi=N.EPI_RELU)
+        f = self.new(M, d)
+        self.gemm(h, True, self.w(w2), hidden, True, M, d, hidden, f, bias=self.p(b2))
+        y, mean, rstd, seed_l, p_l = self.add_ln(f, x, M, norm, rowscale, cfg.dropout)
+
+        if self.tape is not None:
+            def bwd():
+                ds, da = self.ln_bwd(y, f, mean, rstd, norm, rowscale, p_l, seed_l, dbias2=self.g(b2))
+                self.add_grad(x, ds)
+                self.wgrad(da, h, self.g(w2), d, hidden, M)
+                dh = self.new(M, hidden)
+                self.gemm(da, True, self.w(w2), hidden, False, M, hidden, d, dh, epi=N.EPI_RELU_MASK, aux=h)
+                call("icap_colsum", self.act, M, hidden, dh.data_ptr(), hidden, self.g(b1), self._s())
+                self.wgrad(dh, gin, self.g(w1), hidden, d, M)
+                dx = self.new(M, d)
+                self.gemm(dh, True, self.w(w1), d, False, M, d, hidden, dx)
+                self.add_grad(gin, dx)
+            self.tape.append(bwd)
+        return y
+
+    # ------------------------------------------------------------------ encoder
+    def _cat_width(self) -> int:
+        cfg = self.cfg
+        return (cfg.encode_dim_features + cfg.encode_dim_positions + 7) // 8 * 8
+
+    def _pack_embed_weights(self) -> torch.Tensor:
+        """[Wf | Wp (| Wobj) | 0] as one [d, Kc] matrix: feature_embedding + position_embedding
+        (+ object_embedding) become ONE GEMM over the concatenated input (model.py:294-307)."""
+        cfg = self.cfg
+        d, Df, Dp, Kc = cfg.encode_input_size, cfg.encode_dim_features, cfg.encode_dim_positions, self._cat_width()
+        wcat = self.new(d, Kc, zero=True)
+        src_dt = F32
+        call("icap_copy2d", self.p("encoder.feature_embedding.weight"), src_dt, Df, wcat.data_ptr(), self.act, Kc,
+             d, Df, 0, self._s())
+        esz = wcat.element_size()
+        if cfg.split_position:
+            call("icap_copy2d", self.p("encoder.position_embedding.weight"), src_dt, 4, wcat.data_ptr() + Df * esz,
+                 self.act, Kc, d, 4, 0, self._s())
+            call("icap_copy2d", self.p("encoder.object_embedding.weight"), src_dt, Dp - 4,
+                 wcat.data_ptr() + (Df + 4) * esz, self.act, Kc, d, Dp - 4, 0, self._s())
+        else:
+            call("icap_copy2d", self.p("encoder.position_embedding.weight"), src_dt, Dp, wcat.data_ptr() + Df * esz,
+                 self.act, Kc, d, Dp, 0, self._s())
+        return wcat
+
+    def _unpack_embed_grads(self, dwcat: torch.Tensor) -> None:
+        cfg = self.cfg
+        d, Df, Dp, Kc = cfg.encode_input_size, cfg.encode_dim_features, cfg.encode_dim_positions, self._cat_width()
+        call("icap_copy2d", dwcat.data_ptr(), F32, Kc, self.g("encoder.feature_embedding.weight"), F32, Df, d, Df, 1,
+             self._s())
+        if cfg.split_position:
+            call("icap_copy2d", dwcat.data_ptr() + Df * 4, F32, Kc, self.g("encoder.position_embedding.weight"), F32, 4,
+                 d, 4, 1, self._s())
+            call("icap_copy2d", dwcat.data_ptr() + (Df + 4) * 4, F32, Kc, self.g("encoder.object_embedding.weight"), F32,
+                 Dp - 4, d, Dp - 4, 1, self._s())
+        else:
+            call("icap_copy2d", dwcat.data_ptr() + Df * 4, F32, Kc, self.g("encoder.position_embedding.weight"), F32, Dp,
+                 d, Dp, 1, self._s())
+
+    def encode(self, feats: torch.Tensor, pos: torch.Tensor):
+        """Encoder.forward (model.py:257-332).  feats [B,R,Df] fp32, pos [B,R,Dp] fp32 (device)."""
+        cfg = self.cfg
+        B, R, Df = feats.shape
+        Dp = pos.shape[2]
+        assert Df == cfg.encode_dim_features and Dp == cfg.encode_dim_positions
+        M, d, Kc = B * R, cfg.encode_input_size, self._cat_width()
+        H = cfg.encode_num_heads
+        kvalid = self.new(M, dtype=torch.uint8)
+        rowscale = self.new(M, dtype=torch.float32)
+        call("icap_region_valid", pos.data_ptr(), M, Dp, kvalid.data_ptr(), rowscale.data_ptr(), self._s())
+        xcat = self.new(M, Kc, zero=(Kc != Df + Dp))
+        call("icap_copy2d", feats.data_ptr(), F32, Df, xcat.data_ptr(), self.act, Kc, M, Df, 0, self._s())
+        call("icap_copy2d", pos.data_ptr(), F32, Dp, xcat.data_ptr() + Df * xcat.element_size(), self.act, Kc, M, Dp, 0,
+             self._s())
+        wcat = self._pack_embed_weights()
+        if cfg.split_image_objects:
+            x = self._encode_split_objects(xcat, wcat, kvalid, rowscale, B, R)
+        else:
+            e = self.new(M, d)
+            self.gemm(xcat, True, wcat.data_ptr(), Kc, True, M, d, Kc, e)
+            x, mean, rstd, _, _ = self.add_ln(e, None, 1, "encoder.norm", None, 0.0)
+            if self.tape is not None:
+                def bwd():
+                    ds, _ = self.ln_bwd(x, e, mean, rstd, "encoder.norm", None, 0.0, 0)
+                    dwcat = self.new(d, Kc, dtype=torch.float32, zero=True)
+                    self.wgrad(ds, xcat, dwcat.data_ptr(), d, Kc, M)
+                    self._unpack_embed_grads(dwcat)
+                self.tape.append(bwd)
+        for i in range(cfg.encode_num_blocks):
+            pre = f"encoder.encoder.{i}"
+            if cfg.encode_mask:   # key-pad OR causal over region order, rows zeroed after the FFN (model.py:311-326)
+                x = self.mha_block(pre + ".multihead_attention", x, x, B, R, R, H, cfg.encode_q_k_dim, cfg.encode_v_dim,
+                                   kvalid, True)
+                x = self.ffn_block(pre + ".feed_forward", x, cfg.encode_hidden_size, rowscale)
+            else:                 # no mask at all (model.py:327-328)
+                x = self.mha_block(pre + ".multihead_attention", x, x, B, R, R, H, cfg.encode_q_k_dim, cfg.encode_v_dim,
+                                   None, False)
+                x = self.ffn_block(pre + ".feed_forward", x, cfg.encode_hidden_size, None)
+        return x, kvalid
+
+    def _encode_split_objects(self, xcat, wcat, kvalid, rowscale, B, R):
+        raise N.IcapError("split_image_objects=True is not built yet in the CUDA path")
+
+    # ------------------------------------------------------------------ decoder (teacher forced)
+    def decode_train(self, inp: torch.Tensor, tok_valid: torch.Tensor, rowscale: torch.Tensor, enc: torch.Tensor,
+                     kvalid_enc: torch.Tensor, B: int, T: int, R: int, ctx_mean: Optional[torch.Tensor] = None):
+        """Decoder.forward (model.py:419-459) on the full teacher-forced sequence."""
+        cfg = self.cfg
+        M, d, E, H = B * T, cfg.decode_input_size, cfg.dim_word_embedding, cfg.decode_num_heads
+        emb = self.new(M, E)
+        call("icap_embed_fwd", self.act, self.act, inp.data_ptr(), 1, M, E, self.w("decoder.word_embedding.weight"),
+             emb.data_ptr(), None, cfg.pad_idx, self._s())
+        we = self.new(M, d)
+        self.gemm(emb, True, self.w("decoder.word_embedding_linear.weight"), E, True, M, d, E, we)
+        x, mean, rstd, _, _ = self.add_ln(we, self.pos_table_act, T, "decoder.norm", None, 0.0)
+        if self.tape is not None:
+            def bwd():
+                ds, _ = self.ln_bwd(x, we, mean, rstd, "decoder.norm", None, 0.0, 0)
+                self.wgrad(ds, emb, self.g("decoder.word_embedding_linear.weight"), d, E, M)
+                demb = self.new(M, E)
+                self.gemm(ds, True, self.w("decoder.word_embedding_linear.weight"), E, False, M, E, d, demb)
+                call("icap_embed_bwd", self.act, inp.data_ptr(), M, E, cfg.pad_idx, demb.data_ptr(),
+                     self.g("decoder.word_embedding.weight"), self._s())
+            self.tape.append(bwd)
+        for i in range(cfg.decode_num_blocks):
+            pre = f"decoder.decoder.{i}"
+            last = i == cfg.decode_num_blocks - 1
+            x = self.mha_block(pre + ".self_attention", x, x, B, T, T, H, cfg.decode_q_k_dim, cfg.decode_v_dim,
+                               tok_valid, True)
+            x = self.mha_block(pre + ".encode_attention", x, enc, B, T, R, H, cfg.decode_q_k_dim, cfg.decode_v_dim,
+                               kvalid_enc, False, attn_mean=ctx_mean if last else None)
+            x = self.ffn_block(pre + ".feed_forward", x, cfg.decode_hidden_size, rowscale)
+        if cfg.move_first_image_feature:
+            x = self._move_first_tail(x, enc, B, T, R)
+        return x
+
+    def _move_first_tail(self, x, enc, B, T, R):
+        raise N.IcapError("move_first_image_feature=True is not built yet in the CUDA path")
+
+    # ------------------------------------------------------------------ full passes
+    def prepare_inputs(self, feats, pos, captions=None):
+        feats = feats.to(self.dev, torch.float32, non_blocking=True).contiguous()
+        pos = pos.to(self.dev, torch.float32, non_blocking=True).contiguous()
+        if captions is not None:
+            captions = captions.to(self.dev, non_blocking=True).contiguous()
+            assert captions.dtype in (torch.int32, torch.int64)
+        return feats, pos, captions
+
+    def forward_logits(self, feats, pos, captions, record: bool):
+        """Teacher-forced pass up to the classifier (Transformer.forward, model.py:79-93).
+        Returns (logits [B*T, ldl] in act dtype, tgt, count2, dec_out)."""
+        cfg = self.cfg
+        self.refresh_shadow()
+        self._site = 0
+        self.tape = [] if record else None
+        self.gr, self.keep = {}, []
+        B, R, _ = feats.shape
+        L = captions.shape[1]
+        T = L - 1
+        assert T <= cfg.T, f"caption length {L} exceeds max_length {cfg.max_length}"
+        M = B * T
+        inp = self.new(M, dtype=torch.int32)
+        tgt = self.new(M, dtype=torch.int32)
+        tok_valid = self.new(M, dtype=torch.uint8)
+        rowscale = self.new(M, dtype=torch.float32)
+        count_i = self.new(1, dtype=torch.int32)
+        count2 = self.new(2, dtype=torch.float32)
+        call("icap_caption_prep", captions.data_ptr(), int(captions.dtype == torch.int64), B, L, cfg.pad_idx,
+             inp.data_ptr(), tgt.data_ptr(), tok_valid.data_ptr(), rowscale.data_ptr(), count_i.data_ptr(),
+             count2.data_ptr(), self._s())
+        enc, kvalid = self.encode(feats, pos)
+        dec = self.decode_train(inp, tok_valid, rowscale, enc, kvalid, B, T, R)
+        V, d = cfg.num_vocab, cfg.decode_input_size
+        ldl = (V + 7) // 8 * 8
+        logits = self.new(M, ldl)
+        self.gemm(dec, True, self.w("classifer.weight"), d, True, M, V, d, logits, ldc=ldl, bias=self.p("classifer.bias"))
+        return logits, tgt, count2, dec
+
+    def loss_from_logits(self, logits, tgt, count2, dec, record: bool) -> torch.Tensor:
+        """CrossEntropyLoss(ignore_index, 'mean') / FocalLoss (model.py:73-76,95-96); returns out2 =
+        [loss, dloss/dce] on the device.  With record=True the logits buffer becomes dlogits."""
+        cfg = self.cfg
+        M, ldl = logits.shape
+        V, d = cfg.num_vocab, cfg.decode_input_size
+        row_loss = self.new(M, dtype=torch.float32)
+        out2 = self.new(2, dtype=torch.float32)
+        inv_count = count2[1:2]
+        call("icap_xent", self.act, M, V, logits.data_ptr(), ldl, tgt.data_ptr(), cfg.pad_idx, inv_count.data_ptr(),
+             row_loss.data_ptr(), int(record), self._s())
+        call("icap_xent_finalize", M, row_loss.data_ptr(), inv_count.data_ptr(), int(cfg.focal), out2.data_ptr(),
+             self._s())
+        if record:
+            def bwd():
+                self.wgrad(logits, dec, self.g("classifer.weight"), V, d, M, ld_dy=ldl)
+                call("icap_colsum", self.act, M, V, logits.data_ptr(), ldl, self.g("classifer.bias"), self._s())
+                dx = self.new(M, d)
+                self.gemm(logits, True, self.w("classifer.weight"), d, False, M, d, V, dx, lda=ldl)
+                self.add_grad(dec, dx)
+            self.tape.append(bwd)
+        return out2
+
+    def backward(self, zero_grads: bool = True) -> None:
+        """Run the tape in reverse: fills g32 with d(mean CE)/d(param); focal scaling is applied by
+        the caller (icap_scale / Adam gscale) from out2[1]."""
+        assert self.tape is not None, "forward was not recorded"
+        if zero_grads:
+            self.g32.zero_()
+        for fn in reversed(self.tape):
+            fn()
+            if self.bucket_hook is not None:
+                self.bucket_hook(getattr(fn, "__qualname__", ""))
+        self.tape = None
+        self.gr, self.keep = {}, []
+
+    def adam_step(self, lr: float, betas=(0.9, 0.999), eps: float = 1e-8, gscale_dev: Optional[torch.Tensor] = None,
+                  gscale: float = 1.0) -> None:
+        """torch.optim.Adam semantics over the flat buffers (core/models.py:111-113,126)."""
+        if self.adam_m is None:
+            self.adam_m = torch.zeros_like(self.p32)
+            self.adam_v = torch.zeros_like(self.p32)
+        call("icap_adam_step", self.n_flat, self.p32.data_ptr(), self.g32.data_ptr(), self.adam_m.data_ptr(),
+             self.adam_v.data_ptr(), _ptr(self.p16), lr, betas[0], betas[1], eps, self.step_dev.data_ptr(), 1,
+             _ptr(gscale_dev), gscale, self._s())
+        self.shadow_fresh = True
+
+    def train_step(self, feats, pos, captions, lr: float = 5e-4) -> torch.Tensor:
+        """zero_grad -> forward -> backward -> Adam (core/models.py:115-126), all on the current stream.
+        Returns the device tensor [loss, dloss/dce] (no host sync)."""
+        self.training = True
+        logits, tgt, count2, dec = self.forward_logits(feats, pos, captions, record=True)
+        out2 = self.loss_from_logits(logits, tgt, count2, dec, record=True)
+        self.backward(zero_grads=True)
+        self.adam_step(lr, gscale_dev=out2[1:2] if self.cfg.focal else None)
+        return out2
+
+    # ------------------------------------------------------------------ KV-cached decoding
+    def decode(self, feats: torch.Tensor, pos: torch.Tensor, beam_size: int = 1, log_domain: bool = False,
+               want_attention: bool = False, want_gaps: bool = False):
+        """Greedy (beam_size=1: Transformer.generate_caption_vector, model.py:101-132) or beam search
+        (Transformer.beam_search, model.py:135-200) with a KV cache: the reference re-runs the decoder on
+        the whole prefix every step (and once per beam); here every step computes ONE position for all
+        B*k rows, self-attention reads cached K/V through a beam slot table, cross-attention K/V of the
+        encoder output are projected once per layer.  Semantics kept: probability-domain additive beam
+        scores (log-domain for the PolicyNetwork variant), no EOS handling, pad-token (id 0) masking of
+        generated tokens, result = beam slot 0.
+
+        Returns dict(ids int32 [B, T+1] (col 0 = <START>), attention fp32 [T, B, R] | None,
+                     gaps fp32 [T, B] | None)  -- all device tensors, no host sync."""
+        cfg = self.cfg
+        assert self.tape is None
+        self.training = False
+        self.refresh_shadow()
+        self._site = 0
+        k = int(beam_size)
+        B, R, _ = feats.shape
+        T, d, V, E = cfg.T, cfg.decode_input_size, cfg.num_vocab, cfg.dim_word_embedding
+        H, dk_tot, dv_tot, hid = cfg.decode_num_heads, cfg.decode_q_k_dim, cfg.decode_v_dim, cfg.decode_hidden_size
+        dk, dv = dk_tot // H, dv_tot // H
+        nqkv, nkv = 2 * dk_tot + dv_tot, dk_tot + dv_tot
+        rows = B * k
+        Tmax = T + 1
+        esz = 2 if self.precision == "bf16" else 4
+        s = self._s
+        enc, kvalid = self.encode(feats, pos)
+        # cross-attention K/V of every decoder layer, once (the reference recomputes them per step and beam)
+        cross = []
+        for i in range(cfg.decode_num_blocks):
+            kvb = self.new(B * R, nkv)
+            self.gemm(enc, True, self.w(f"decoder.decoder.{i}.encode_attention.k_linear.weight"), d, True, B * R, nkv, d, kvb)
+            cross.append(kvb)
+        # token embedding folded with word_embedding_linear: table[v] = Emb[v] . Wwe^T  (model.py:432-433)
+        table = self.new(V, d)
+        emb_w = self.p16 if self.precision == "bf16" else self.p32
+        self.gemm(emb_w, True, self.w("decoder.word_embedding_linear.weight"), E, True, V, d, E, table,
+                  a_ptr=self.w("decoder.word_embedding.weight"), lda=E)
+        tok = [torch.zeros(rows, Tmax, dtype=torch.int32, device=self.dev) for _ in range(2)]
+        tok[0][:, 0] = 1                                  # <START> (model.py:111,144)
+        slot = None
+        if k > 1:
+            slot = [torch.zeros(rows, Tmax, dtype=torch.int32, device=self.dev) for _ in range(2)]
+            slot[0][:, 0] = torch.arange(rows, dtype=torch.int32, device=self.dev)
+            score = [torch.zeros(B, k, dtype=torch.float32, device=self.dev) for _ in range(2)]
+            parent = torch.empty(B, k, dtype=torch.int32, device=self.dev)
+            newtok = torch.empty(B, k, dtype=torch.int32, device=self.dev)
+        caches = [self.new(rows, T, nkv) for _ in range(cfg.decode_num_blocks)]
+        attn = torch.zeros(T, rows, R, dtype=torch.float32, device=self.dev) if want_attention else None
+        gaps = torch.zeros(T, B, dtype=torch.float32, device=self.dev) if want_gaps else None
+        ldl = (V + 7) // 8 * 8
+        cur = 0
+        for t in range(T):
+            tk = tok[cur]
+            x0 = self.new(rows, d)
+            rowscale = self.new(rows, dtype=torch.float32)
+            call("icap_embed_fwd", self.act, self.act, tk.data_ptr() + 4 * t, Tmax, rows, d, table.data_ptr(),
+                 x0.data_ptr(), rowscale.data_ptr(), cfg.pad_idx, s())
+            x = self.new(rows, d)
+            call("icap_add_ln_fwd", self.act, self.act, rows, d, x0.data_ptr(), self.pos_table_act.data_ptr() + t * d * esz,
+                 1, self.p("decoder.norm.weight"), self.p("decoder.norm.bias"), None, x.data_ptr(), None, None, 0, 0.0, 0,
+                 None, LN_EPS, s())
+            for i in range(cfg.decode_num_blocks):
+                pre = f"decoder.decoder.{i}"
+                last = i == cfg.decode_num_blocks - 1
+                # --- masked self-attention over the cache (modules.py:190-194)
+                qkv = self.new(rows, nqkv)
+                self.gemm(x, True, self.w(pre + ".self_attention.q_linear.weight"), d, True, rows, nqkv, d, qkv)
+                cache = caches[i]
+                call("icap_copy2d", qkv.data_ptr() + dk_tot * esz, self.act, nqkv, cache.data_ptr() + t * nkv * esz,
+                     self.act, T * nkv, rows, nkv, 0, s())
+                att = self.new(rows, dv_tot)
+                call("icap_mha_decode", self.act, rows, H, t + 1, dk, dv, qkv.data_ptr(), nqkv, cache.data_ptr(), nkv,
+                     cache.data_ptr() + dk_tot * esz, nkv, T, att.data_ptr(), dv_tot,
+                     slot[cur].data_ptr() if slot is not None else None, Tmax, tk.data_ptr(), Tmax, cfg.pad_idx,
+                     None, 1, None, s())
+                o = self.new(rows, d)
+                self.gemm(att, True, self.w(pre + ".self_attention.joint_linear.weight"), dv_tot, True, rows, d, dv_tot, o)
+                x1, *_ = self.add_ln(o, x, rows, pre + ".self_attention.layer_norm", None, 0.0)
+                # --- cross-attention over the image regions (modules.py:196-200)
+                q2 = self.new(rows, dk_tot)
+                self.gemm(x1, True, self.w(pre + ".encode_attention.q_linear.weight"), d, True, rows, dk_tot, d, q2)
+                att2 = self.new(rows, dv_tot)
+                call("icap_mha_decode", self.act, rows, H, R, dk, dv, q2.data_ptr(), dk_tot, cross[i].data_ptr(), nkv,
+                     cross[i].data_ptr() + dk_tot * esz, nkv, R, att2.data_ptr(), dv_tot, None, 0, None, 0, cfg.pad_idx,
+                     kvalid.data_ptr(), k, attn[t].data_ptr() if (attn is not None and last) else None, s())
+                o2 = self.new(rows, d)
+                self.gemm(att2, True, self.w(pre + ".encode_attention.joint_linear.weight"), dv_tot, True, rows, d, dv_tot, o2)
+                x2, *_ = self.add_ln(o2, x1, rows, pre + ".encode_attention.layer_norm", None, 0.0)
+                # --- FFN + non-pad row mask (modules.py:202-204)
+                x = self.ffn_block(pre + ".feed_forward", x2, hid, rowscale)
+            if cfg.move_first_image_feature:
+                x = self._move_first_tail(x, enc, B, 1, R)
+            logits = self.new(rows, ldl)
+            self.gemm(x, True, self.w("classifer.weight"), d, True, rows, V, d, logits, ldc=ldl, bias=self.p("classifer.bias"))
+            if k == 1:
+                call("icap_argmax", self.act, rows, V, logits.data_ptr(), ldl, tk.data_ptr() + 4 * (t + 1), Tmax,
+                     gaps[t].data_ptr() if gaps is not None else None, s())
+            else:
+                kin = 1 if t == 0 else k       # step 0: all beams hold <START>, only beam 0 competes (model.py:146-166)
+                call("icap_beam_select", self.act, B, kin, V, logits.data_ptr(), ldl * (k if t == 0 else 1),
+                     score[cur].data_ptr() if t > 0 else None, k, score[cur ^ 1].data_ptr(), parent.data_ptr(),
+                     newtok.data_ptr(), gaps[t].data_ptr() if gaps is not None else None, int(log_domain), s())
+                call("icap_beam_reorder", B, k, Tmax, t, parent.data_ptr(), newtok.data_ptr(), tk.data_ptr(),
+                     tok[cur ^ 1].data_ptr(), slot[cur].data_ptr(), slot[cur ^ 1].data_ptr(), s())
+                cur ^= 1
+        ids = tok[cur].view(B, k, Tmax)[:, 0, :]
+        if attn is not None:
+            attn = attn.view(T, B, k, R)[:, :, 0, :]
+        return {"ids": ids, "attention": attn, "gaps": gaps}

@@ -1,0 +1,323 @@
+"""Drop-in `Transformer` (same constructor / forward / generate_caption_vector / beam_search
+signatures and state_dict layout as core/TRANSFORMER/model.py:8-209 of the reference), executing on
+libicap.so.  It is an nn.Module so the reference wrapper's `.to(DEVICE)`, `.parameters()`,
+`.state_dict()`, `.load_state_dict()`, `.eval()` (core/models.py:63-68,110-113) keep working.
+
+All parameters are views into ONE flat fp32 buffer (registration order == reference order), which
+is what the fused Adam / gradient all-reduce operate on.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .engine import BUFFER_NAMES, CaptionEngine, ModelConfig, flat_offsets, param_layout
+from ._native import IcapError
+
+
+def _sinusoid_table(num_positions: int, dim: int) -> torch.Tensor:
+    """PositionalEncoding._get_sinusoid_encoding_table (model.py:502-514): float64 numpy, then float32."""
+    j = np.arange(dim)
+    pos = np.arange(num_positions, dtype=np.float64)[:, None]
+    table = pos / np.power(10000, 2 * (j // 2) / dim)[None, :]
+    table[:, 0::2] = np.sin(table[:, 0::2])
+    table[:, 1::2] = np.cos(table[:, 1::2])
+    return torch.tensor(table, dtype=torch.float32).unsqueeze(0)
+
+
+class _Namespace(nn.Module):
+    """Empty container used to reproduce the reference's dotted parameter names."""
+
+
+def _set_nested(root: nn.Module, dotted: str, value, is_buffer: bool) -> None:
+    parts = dotted.split(".")
+    mod = root
+    for p in parts[:-1]:
+        if not hasattr(mod, p):
+            mod.add_module(p, _Namespace())
+        mod = getattr(mod, p)
+    if is_buffer:
+        mod.register_buffer(parts[-1], value)
+    else:
+        mod.register_parameter(parts[-1], value)
+
+
+class _LossFn(torch.autograd.Function):
+    """Lets `loss.backward()` (core/models.py:125) drive the explicit backward of the engine."""
+
+    @staticmethod
+    def forward(ctx, model, feats, pos, captions, *params):
+        eng = model._engine()
+        eng.training = model.training
+        eng.shadow_fresh = False                       # an external optimizer may have stepped the weights
+        f, p, c = eng.prepare_inputs(feats, pos, captions)
+        record = torch.is_grad_enabled() and any(q.requires_grad for q in params)
+        logits, tgt, count2, dec = eng.forward_logits(f, p, c, record=record)
+        out2 = eng.loss_from_logits(logits, tgt, count2, dec, record=record)
+        ctx.model, ctx.out2, ctx.recorded = model, out2, record
+        return out2[0].clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        model, eng = ctx.model, ctx.model._engine()
+        if not ctx.recorded:
+            raise IcapError("backward() called on a forward that did not record (no_grad / frozen parameters)")
+        params = [q for _, q in model.named_parameters()]
+        fresh = all(q.grad is None for q in params)
+        eng.backward(zero_grads=fresh)                 # existing .grad views => accumulate like autograd does
+        from ._native import call
+        call("icap_scale", eng.g32.data_ptr(), eng.n_flat, ctx.out2[1:2].data_ptr() if eng.cfg.focal else None,
+             1.0, eng._s())
+        if not (grad_out.numel() == 1 and float(grad_out) == 1.0):
+            eng.g32.mul_(grad_out)
+        for name, q in model.named_parameters():
+            off = eng.offsets[name]
+            q.grad = eng.g32[off:off + q.numel()].view_as(q)
+        return (None,) * (4 + len(params))
+
+
+class Transformer(nn.Module):
+    """Reference signature: model.py:10-36."""
+
+    def __init__(self, num_vocab, max_length,
+                 encode_dim_positions,
+                 encode_dim_features,
+                 device,
+                 output_name,
+                 encode_mask=False,
+                 pad_idx=0,
+                 dropout=0.2,
+
+                 encode_input_size=512,
+                 encode_q_k_dim=512,
+                 encode_v_dim=512,
+                 encode_hidden_size=2048,
+                 encode_num_blocks=6,
+                 encode_num_heads=8,
+
+                 dim_word_embedding=512,
+                 decode_input_size=512,
+                 decode_q_k_dim=512,
+                 decode_v_dim=512,
+                 decode_hidden_size=2048,
+                 decode_num_blocks=6,
+                 decode_num_heads=8,
+
+                 move_first_image_feature=False,
+                 split_position=False,
+                 split_image_objects=False):
+        super().__init__()
+        self.max_length = max_length
+        self.device = device
+        self.num_vocab = num_vocab
+        self.pad_idx = pad_idx
+        self.cfg = ModelConfig(
+            num_vocab=num_vocab, max_length=max_length, encode_dim_positions=encode_dim_positions,
+            encode_dim_features=encode_dim_features, output_name=output_name, encode_mask=encode_mask,
+            pad_idx=pad_idx, dropout=dropout, encode_input_size=encode_input_size, encode_q_k_dim=encode_q_k_dim,
+            encode_v_dim=encode_v_dim, encode_hidden_size=encode_hidden_size, encode_num_blocks=encode_num_blocks,
+            encode_num_heads=encode_num_heads, dim_word_embedding=dim_word_embedding,
+            decode_input_size=decode_input_size, decode_q_k_dim=decode_q_k_dim, decode_v_dim=decode_v_dim,
+            decode_hidden_size=decode_hidden_size, decode_num_blocks=decode_num_blocks,
+            decode_num_heads=decode_num_heads, move_first_image_feature=move_first_image_feature,
+            split_position=split_position, split_image_objects=split_image_objects)
+        # "bf16" (tcgen05 GEMMs) or "fp32" (parity mode); the constructor signature is the reference's,
+        # so the switch lives in the environment / an attribute.
+        self.precision = os.environ.get("ICAP_PRECISION", "bf16")
+        self.log_domain_beam = False          # True = PolicyNetwork scoring (model_RL.py:72)
+        self.last_gaps: Optional[torch.Tensor] = None
+        self._shapes = param_layout(self.cfg)
+        self._offsets, self._n_flat = flat_offsets(self._shapes)
+        flat = torch.zeros(self._n_flat, dtype=torch.float32)
+        self._flat = flat
+        for name, shp in self._shapes.items():
+            if name in BUFFER_NAMES:
+                _set_nested(self, name, _sinusoid_table(shp[1], shp[2]), is_buffer=True)
+            else:
+                off = self._offsets[name]
+                view = flat[off:off + math.prod(shp)].view(shp)
+                _set_nested(self, name, nn.Parameter(view), is_buffer=False)
+        self._init_parameters()
+        self._eng: Optional[CaptionEngine] = None
+
+    # ------------------------------------------------------------------ init (SURVEY.md §8a "Initialisation")
+    @torch.no_grad()
+    def _init_parameters(self) -> None:
+        for name, q in self.named_parameters():
+            shp = q.shape
+            if name.endswith("norm.weight"):
+                q.fill_(1.0)
+            elif name.endswith("norm.bias"):
+                q.zero_()
+            elif name == "decoder.word_embedding.weight":           # nn.Embedding: N(0,1), padding row zero
+                q.normal_(0.0, 1.0)
+                q[self.pad_idx].zero_()
+            elif name.endswith(".bias"):                             # nn.Linear default bias
+                fan_in = self._shapes[name[:-4] + "weight"][1]
+                q.uniform_(-1.0 / math.sqrt(fan_in), 1.0 / math.sqrt(fan_in))
+            elif name.endswith(("q_linear.weight", "k_linear.weight", "v_linear.weight")):   # modules.py:45-53
+                q.normal_(0.0, math.sqrt(2.0 / (shp[0] + shp[1])))
+            elif any(s in name for s in ("joint_linear", "position_wise", "classifer")):     # xavier_normal
+                q.normal_(0.0, math.sqrt(2.0 / (shp[0] + shp[1])))
+            else:                                                    # nn.Linear default: U(+-1/sqrt(fan_in))
+                q.uniform_(-1.0 / math.sqrt(shp[1]), 1.0 / math.sqrt(shp[1]))
+
+    # ------------------------------------------------------------------ flat storage upkeep
+    def _apply(self, fn, *args, **kwargs):
+        super()._apply(fn, *args, **kwargs)            # moves every parameter separately ...
+        self._reflatten()                              # ... so re-pack them into one buffer
+        return self
+
+    @torch.no_grad()
+    def _reflatten(self) -> None:
+        params = dict(self.named_parameters())
+        any_p = next(iter(params.values()))
+        flat = torch.zeros(self._n_flat, dtype=torch.float32, device=any_p.device)
+        for name, q in params.items():
+            off = self._offsets[name]
+            flat[off:off + q.numel()].copy_(q.detach().reshape(-1).to(torch.float32))
+            q.data = flat[off:off + q.numel()].view(q.shape)
+            q.grad = None
+        self._flat = flat
+        self._eng = None
+        if any_p.is_cuda:
+            self.device = any_p.device
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        out = super().load_state_dict(state_dict, strict=strict, **kw)     # in-place copies: views stay valid
+        if self._eng is not None:
+            self._eng.shadow_fresh = False
+            self._eng.pos_table32.copy_(self.decoder.position_embedding.pos_table.reshape(self._eng.pos_table32.shape))
+            self._eng.pos_table_act.copy_(self._eng.pos_table32)
+        return out
+
+    def set_precision(self, precision: str) -> "Transformer":
+        assert precision in ("bf16", "fp32")
+        if precision != self.precision:
+            self.precision, self._eng = precision, None
+        return self
+
+    def _engine(self) -> CaptionEngine:
+        if not self._flat.is_cuda:
+            raise IcapError("image-caption_b200 runs on sm_100a GPUs only: call model.to('cuda') first "
+                            "(there is no CPU fallback)")
+        if self._eng is None:
+            self._eng = CaptionEngine(self.cfg, self._flat, self.decoder.position_embedding.pos_table, self.precision)
+        return self._eng
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, object_features, position_features, target_caption):
+        """model.py:79-98 -> {'loss': 0-d tensor}."""
+        params = [q for _, q in self.named_parameters()]
+        loss = _LossFn.apply(self, object_features, position_features, target_caption, *params)
+        return {"loss": loss}
+
+    @torch.no_grad()
+    def logits(self, object_features, position_features, target_caption) -> torch.Tensor:
+        """Teacher-forced logits [B, T, V] fp32 (== PolicyNetwork.forward, model_RL.py:75-90)."""
+        eng = self._engine()
+        eng.training = False
+        f, p, c = eng.prepare_inputs(object_features, position_features, target_caption)
+        lg, _, _, _ = eng.forward_logits(f, p, c, record=False)
+        B, T = c.shape[0], c.shape[1] - 1
+        return lg[:, :self.num_vocab].float().view(B, T, self.num_vocab)
+
+    def generate_caption_vector(self, object_features, position_features):
+        """model.py:101-132 -> (LongTensor [B, max_length+1], list of max_length-1 float32 arrays [B, R])."""
+        with torch.no_grad():
+            eng = self._engine()
+            f, p, _ = eng.prepare_inputs(object_features, position_features)
+            out = eng.decode(f, p, beam_size=1, want_attention=True, want_gaps=True)
+            B = f.shape[0]
+            ids = torch.zeros(B, self.max_length + 1, dtype=torch.long, device=f.device)
+            ids[:, :self.max_length] = out["ids"].long()
+            self.last_gaps = out["gaps"]
+            att = out["attention"].cpu().numpy()                      # ONE device->host copy (reference: one per step)
+            attention_list: List[np.ndarray] = [att[t] for t in range(att.shape[0])]
+        return ids, attention_list
+
+    def beam_search(self, object_features, position_features, beam_size=1):
+        """model.py:135-200 -> LongTensor [B, max_length] (beam slot 0)."""
+        with torch.no_grad():
+            eng = self._engine()
+            f, p, _ = eng.prepare_inputs(object_features, position_features)
+            out = eng.decode(f, p, beam_size=int(beam_size), log_domain=self.log_domain_beam, want_gaps=True)
+            self.last_gaps = out["gaps"]
+            return out["ids"].long().contiguous()
+
+    def get_attention_key_pad_mask(self, k, q):
+        """model.py:202-209 (host-visible helper kept for API parity; kernels build the mask in-register)."""
+        assert k.size(0) == q.size(0)
+        mask = torch.count_nonzero(k, dim=2).eq(0)
+        return mask.unsqueeze(1).expand(k.size(0), q.size(1), k.size(1))
+
+    # ------------------------------------------------------------------ fused training step
+    def train_step_fused(self, object_features, position_features, target_caption, lr: float = 5e-4) -> torch.Tensor:
+        """zero_grad + forward + backward + Adam in one stream-ordered launch sequence
+        (core/models.py:115-126).  Returns the device loss (0-d view, no host sync)."""
+        eng = self._engine()
+        f, p, c = eng.prepare_inputs(object_features, position_features, target_caption)
+        out2 = eng.train_step(f, p, c, lr=lr)
+        return out2[0]
+
+
+class GraphedTrainStep:
+    """One CUDA graph holding H2D-staged inputs -> zero_grad -> forward -> backward -> Adam for a fixed
+    batch shape.  Replays cost one launch; dropout masks change per replay because the kernels mix the
+    device-side step counter into their seeds."""
+
+    def __init__(self, model: Transformer, batch: int, regions: int, caption_len: int, lr: float = 5e-4,
+                 warmup: int = 2):
+        eng = model._engine()
+        cfg = model.cfg
+        dev = eng.dev
+        self.model, self.eng, self.lr = model, eng, lr
+        self.feats = torch.zeros(batch, regions, cfg.encode_dim_features, device=dev)
+        self.pos = torch.zeros(batch, regions, cfg.encode_dim_positions, device=dev)
+        self.pos[:, :, 2:4] = 1.0                      # placeholder keeps every region "valid" during capture
+        self.cap = torch.ones(batch, caption_len, dtype=torch.int32, device=dev)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.out2: Optional[torch.Tensor] = None
+        self.warmup = warmup
+        self.launches_per_step = 0
+
+    def load(self, feats: torch.Tensor, pos: torch.Tensor, cap: torch.Tensor) -> None:
+        self.feats.copy_(feats, non_blocking=True)
+        self.pos.copy_(pos, non_blocking=True)
+        self.cap.copy_(cap, non_blocking=True)
+
+    def capture(self) -> None:
+        """Capture with whatever is currently staged in the input buffers (call load() first)."""
+        from . import _native
+        eng = self.eng
+        # warm-up on a side stream (allocator + function attributes), then roll the optimizer state back
+        p0, step0 = eng.p32.clone(), eng.step_dev.clone()
+        side = torch.cuda.Stream(device=eng.dev)
+        side.wait_stream(torch.cuda.current_stream(eng.dev))
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup):
+                eng.train_step(self.feats, self.pos, self.cap, lr=self.lr)
+        torch.cuda.current_stream(eng.dev).wait_stream(side)
+        eng.p32.copy_(p0)
+        eng.step_dev.copy_(step0)
+        eng.adam_m.zero_()
+        eng.adam_v.zero_()
+        eng.shadow_fresh = False
+        eng.refresh_shadow()
+        torch.cuda.synchronize(eng.dev)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = _native.launch_count
+        with torch.cuda.graph(self.graph):
+            self.out2 = eng.train_step(self.feats, self.pos, self.cap, lr=self.lr)
+        self.launches_per_step = _native.launch_count - n0
+
+    def step(self) -> torch.Tensor:
+        if self.graph is None:
+            self.capture()
+        self.graph.replay()
+        return self.out2[0]

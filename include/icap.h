@@ -1,0 +1,144 @@
+/*
+ * libicap.so -- C ABI of the B200-native caption-generator hot path.
+ *
+ * The reference (shao-chi/Image-Caption) is pure Python/PyTorch and has NO native boundary
+ * (SURVEY.md section 2.1); this header is the boundary a native port of its hot path binds to.
+ * Each entry point names the reference code whose arithmetic it replaces (file:line relative to
+ * the reference repo).  INTEGRATION.md shows the ctypes stub a maintainer adds on the reference
+ * side.
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers (tensor.data_ptr()), int64 sizes / leading dimensions in
+ *     ELEMENTS, dtype enums, and a cudaStream_t passed as void*.  No torch types.
+ *   - return value: 0 = OK, >0 = cudaError_t of the failed launch, <0 = argument/shape error.
+ *     icap_last_error() returns a thread-local description.  Nothing throws.
+ *   - every function only enqueues work on `stream` (no host sync, no allocation) and is therefore
+ *     CUDA-graph capturable.  The caller owns all memory.
+ *   - sm_100a only; icap_sm_check() refuses anything else.  There is no CPU fallback.
+ */
+#ifndef ICAP_H_
+#define ICAP_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICAP_F32 0
+#define ICAP_BF16 1
+
+/* epilogues of icap_gemm */
+#define ICAP_EPI_NONE 0
+#define ICAP_EPI_RELU 1      /* C = relu(AB + bias)            FeedForward position_wise_1 + ReLU, modules.py:113-114 */
+#define ICAP_EPI_RELU_MASK 2 /* C = (AB) * (aux > 0)           backward of that ReLU                                   */
+
+int icap_version(void);
+const char* icap_last_error(void);
+int icap_sm_check(int device);
+
+/* C[M,N] (+)= op(A)[M,K] . op(B)[K,N] (+ bias[N]) with an optional activation epilogue.
+ *   a_kmajor=1: A stored [M][K]; 0: stored [K][M].   b_kmajor=1: B stored [N][K]; 0: stored [K][N].
+ *   ab_dtype ICAP_F32 : true-fp32 SIMT kernel (fp32 parity mode), C fp32.
+ *   ab_dtype ICAP_BF16: TMA + tcgen05.mma + TMEM kernel, C fp32 or bf16 (c_dtype).
+ *   accumulate=1: C += ...; split_k>1 (needs accumulate=1, fp32 C) reduces K-slices with red.add.
+ * Replaces every nn.Linear / torch.matmul weight contraction of the path and their autograd
+ * backward: modules.py:42-44,59-60,72-77,86,100-101,113-116; model.py:68,93,235,246,295-306,392-394,433. */
+int icap_gemm(int ab_dtype, int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
+              const void* B, int64_t ldb, void* C, int64_t ldc, int c_dtype, const float* bias, int epilogue,
+              const void* aux, int64_t ldaux, int accumulate, int split_k, void* stream);
+
+/* Fused multi-head attention over packed projections (one CTA per (batch, head)).
+ *   q rows b*Lq+i at q + row*ldq + h*dk; k/v rows b*Lk+j likewise; o rows at o + row*ldo + h*dv.
+ *   key j of batch b is masked iff (kvalid && !kvalid[b*Lk+j]) || (causal && j > i).
+ *   p_drop / seed: dropout on the probabilities (fixed 0.1 in the reference, modules.py:8,24); the effective
+ *   seed is seed + seed_dev[0] * golden-ratio (seed_dev nullable) so a replayed CUDA graph gets fresh masks.
+ *   attn_mean (nullable, fp32 [B,Lq,Lk], pre-zeroed): += P / H  (greedy visualisation, model.py:123).
+ * Replaces ScaledDotProductAttention.forward and the head split/merge, modules.py:16-27,72-84. */
+int icap_mha_fwd(int dtype, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t dk, int64_t dv, const void* q,
+                 int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
+                 const uint8_t* kvalid, int causal, float p_drop, uint64_t seed, const int* seed_dev, float* attn_mean,
+                 void* stream);
+int icap_mha_bwd(int dtype, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t dk, int64_t dv, const void* q,
+                 int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* dout, int64_t lddo,
+                 void* dq, int64_t lddq, void* dk_out, int64_t lddk, void* dv_out, int64_t lddv,
+                 const uint8_t* kvalid, int causal, float p_drop, uint64_t seed, const int* seed_dev, void* stream);
+
+/* y = (LayerNorm(dropout(a) + res[row % res_rows]) * gamma + beta) * rowscale[row]   (eps given).
+ *   a: [M,d] of a_dtype (the GEMM output); res/y: act_dtype; write_sum=1 stores the pre-norm sum
+ *   back into a (needed by the backward); mean/rstd: fp32 [M] (nullable in inference).
+ * Replaces Dropout + residual + LayerNorm of modules.py:86-90,117-120, the embedding norms
+ * model.py:307-309,433-436 and `output *= non_pad_mask`, modules.py:154-155,203-204. */
+int icap_add_ln_fwd(int a_dtype, int act_dtype, int64_t M, int64_t d, void* a, const void* res, int64_t res_rows,
+                    const float* gamma, const float* beta, const float* rowscale, void* y, float* mean_out,
+                    float* rstd_out, int write_sum, float p_drop, uint64_t seed, const int* seed_dev, float eps,
+                    void* stream);
+/* dy = dy1 (+ dy2); ds -> residual branch, da = dropout-masked ds -> GEMM branch (nullable: use ds when p=0);
+ * dgamma/dbeta/dbias2 (fp32 [d], accumulated; dbias2 = column sums of da, nullable). */
+int icap_add_ln_bwd(int act_dtype, int64_t M, int64_t d, const void* dy1, const void* dy2, const void* s,
+                    const float* mean, const float* rstd, const float* gamma, const float* rowscale, void* ds, void* da,
+                    float* dgamma, float* dbeta, float* dbias2, float p_drop, uint64_t seed, const int* seed_dev,
+                    void* stream);
+
+/* Fused log-softmax + NLL per row; with write_grad=1 the logits are overwritten IN PLACE by
+ * (softmax - onehot) * inv_count[0] (zero rows for ignored targets).  row_loss: fp32 [M].
+ * Replaces CrossEntropyLoss(ignore_index=pad_idx, 'mean'), model.py:76,93-96. */
+int icap_xent(int dtype, int64_t M, int64_t V, void* logits, int64_t ldl, const int* targets, int ignore_index,
+              const float* inv_count, float* row_loss, int write_grad, void* stream);
+/* out2[0] = mean loss (focal=1: (1-exp(-ce))^2 * ce, loss.py:20-28); out2[1] = d loss / d ce. */
+int icap_xent_finalize(int64_t M, const float* row_loss, const float* inv_count, int focal, float* out2, void* stream);
+
+/* out[row*out_stride] = argmax_j logits[row][j] (lowest index on ties); gap = top1 - top2 (nullable).
+ * Replaces argmax(Softmax(classifer(.))), model.py:125-128. */
+int icap_argmax(int dtype, int64_t M, int64_t V, const void* logits, int64_t ldl, int* out, int64_t out_stride,
+                float* gap, void* stream);
+/* Beam step for B images: candidates (beam r, token j) score softmax(logits[b*kin+r])[j] + prev[b,r]
+ * (log_domain=1: log-softmax, the PolicyNetwork variant); writes the kout best in DESCENDING order:
+ * score, parent = r, token = j; gap[b] = score_k - score_{k+1} (nullable).
+ * Replaces Softmax + cat + topk + // and % of model.py:160-166,181-198 (model_RL.py:157,182). */
+int icap_beam_select(int dtype, int64_t B, int64_t kin, int64_t V, const void* logits, int64_t ldl,
+                     const float* prev_score, int64_t kout, float* out_score, int* out_parent, int* out_token,
+                     float* gap, int log_domain, void* stream);
+/* Reorder token buffer (and KV-cache slot table) by parent and append the new token: model.py:194-198. */
+int icap_beam_reorder(int64_t B, int64_t k, int64_t Tmax, int64_t t, const int* parent, const int* token,
+                      const int* tok_in, int* tok_out, const int* slot_in, int* slot_out, void* stream);
+
+/* KV-cached single-position attention for decoding (M = B*k rows, one query each).
+ *   self-attention (tokens != NULL): keys/values of positions 0..Lk-1 live in the cache at physical row
+ *                    slot[row*slot_ld+j] (own row when slot == NULL); position j is masked iff
+ *                    tokens[row*tok_ld+j] == pad_idx  (model.py:421-430).
+ *   cross-attention (tokens == NULL): keys are the Lk regions of image row / rows_per_image, masked by kvalid.
+ *   cache rows: k at kc + (slot*Tmax_or_Lk + j)*ldk + h*dk. */
+int icap_mha_decode(int dtype, int64_t rows, int64_t H, int64_t Lk, int64_t dk, int64_t dv, const void* q, int64_t ldq,
+                    const void* kc, int64_t ldk, const void* vc, int64_t ldv, int64_t kv_rows_per_seq, void* o,
+                    int64_t ldo, const int* slot, int64_t slot_ld, const int* tokens, int64_t tok_ld, int pad_idx,
+                    const uint8_t* kvalid, int64_t rows_per_image, float* attn_mean, void* stream);
+
+/* dst[r][c] (+)= convert(src[r][c]) : operand packing / dtype casts / gradient unpacking. */
+int icap_copy2d(const void* src, int src_dtype, int64_t src_ld, void* dst, int dst_dtype, int64_t dst_ld, int64_t rows,
+                int64_t cols, int accumulate, void* stream);
+/* kvalid[row] = rowscale[row] = any(pos[row,:] != 0) : get_attention_key_pad_mask / get_non_pad_mask,
+ * model.py:202-209,354-358. */
+int icap_region_valid(const float* pos, int64_t M, int64_t Dp, uint8_t* kvalid, float* rowscale, void* stream);
+/* inp = cap[:, :-1], tgt = cap[:, 1:], tok_valid/rowscale = inp != pad, count_f2 = {n, 1/n} with n the
+ * number of non-pad targets (model.py:88-89,421-430; the 'mean' denominator of model.py:76). */
+int icap_caption_prep(const void* captions, int cap_is_int64, int64_t B, int64_t L, int pad_idx, int* inp, int* tgt,
+                      uint8_t* tok_valid, float* rowscale, int* count_i, float* count_f2, void* stream);
+/* out[r,:] = table[tokens[r*tok_stride],:]  (nn.Embedding, model.py:432); rowscale[r] = token != pad (nullable);
+ * and the scatter-add backward (row pad_idx untouched). */
+int icap_embed_fwd(int table_dtype, int out_dtype, const int* tokens, int64_t tok_stride, int64_t M, int64_t E,
+                   const void* table, void* out, float* rowscale, int pad_idx, void* stream);
+int icap_embed_bwd(int dtype, const int* tokens, int64_t M, int64_t E, int pad_idx, const void* dout, float* dtable,
+                   void* stream);
+/* out[c] += sum_r x[r][c]  (bias gradients). */
+int icap_colsum(int dtype, int64_t M, int64_t N, const void* x, int64_t ld, float* out, void* stream);
+/* torch.optim.Adam step over flat fp32 buffers (+ bf16 shadow refresh); step counter on the device
+ * (tick=1 increments it first); gradients are pre-multiplied by gscale * gscale_dev[0].
+ * Replaces optimizer.step(), core/models.py:111-113,126. */
+int icap_adam_step(int64_t n, float* p, const float* g, float* m, float* v, void* shadow_bf16, float lr, float beta1,
+                   float beta2, float eps, int* step_dev, int tick, const float* gscale_dev, float gscale,
+                   void* stream);
+int icap_scale(float* x, int64_t n, const float* s_dev, float s, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICAP_H_ */
