@@ -37,6 +37,7 @@ SIGNATURES = {
     "icap_colsum": [I, L, L, P, L, P, P],
     "icap_adam_step": [L, P, P, P, P, P, F, F, F, F, P, I, P, F, P],
     "icap_scale": [P, L, P, F, P],
+    "icap_reciprocal": [P, P, F, P],
 }
 
 

@@ -175,6 +175,7 @@ __global__ void adam_kernel(int64_t n, float* __restrict__ p, const float* __res
   }
 }
 __global__ void step_tick_kernel(int* step) { *step += 1; }
+__global__ void reciprocal_kernel(const float* x, float* out, float num) { out[0] = num / x[0]; }
 
 __global__ void scale_kernel(float* __restrict__ x, int64_t n, const float* __restrict__ s_ptr, float s) {
   const float f = s * (s_ptr ? s_ptr[0] : 1.f);
@@ -285,6 +286,13 @@ extern "C" int icap_adam_step(int64_t n, float* p, const float* g, float* m, flo
   adam_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(n, p, g, m, v, (bf16*)shadow_bf16, lr, beta1, beta2, eps, step_dev,
                                                     gscale_dev, gscale);
   ICAP_LAUNCH_CHECK("icap_adam_step");
+  return 0;
+}
+
+extern "C" int icap_reciprocal(const float* x, float* out, float numerator, void* stream) {
+  ICAP_ARG(x && out, "icap_reciprocal: null argument");
+  reciprocal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(x, out, numerator);
+  ICAP_LAUNCH_CHECK("icap_reciprocal");
   return 0;
 }
 

@@ -157,7 +157,10 @@ class CaptionEngine:
         self.offsets, self.n_flat = flat_offsets(self.shapes)
         assert flat_params.numel() == self.n_flat
         self.p32 = flat_params
-        self.g32 = torch.zeros_like(flat_params)
+        self.g32 = torch.zeros(self.n_flat + 8, dtype=torch.float32, device=self.dev)   # tail slot: DP token count
+        self.one = torch.ones(1, dtype=torch.float32, device=self.dev)
+        self.dp_unnormalized = False     # data parallel: dlogits are NOT divided by the local token count
+        self._prof = None
         self.p16 = torch.empty(self.n_flat, dtype=torch.bfloat16, device=self.dev) if precision == "bf16" else None
         self.shadow_fresh = False
         self.adam_m: Optional[torch.Tensor] = None
@@ -233,10 +236,12 @@ class CaptionEngine:
         ab = BF16 if self.precision == "bf16" else F32
         if c_dtype is None:
             c_dtype = F32 if out.dtype == torch.float32 else BF16
+        ev = self._prof_begin()
         call("icap_gemm", ab, int(a_kmajor), int(b_kmajor), M, Nn, K,
              a.data_ptr() if a_ptr is None else a_ptr, a.shape[-1] if lda is None else lda, b_ptr, ldb,
              out.data_ptr() if c_ptr is None else c_ptr, (out.shape[-1] if ldc is None else ldc), c_dtype,
              bias, epi, _ptr(aux), (aux.shape[-1] if aux is not None else 0), int(accumulate), split_k, self._s())
+        self._prof_end(ev, 2.0 * M * Nn * K)
 
     def wgrad(self, dy: torch.Tensor, x: torch.Tensor, g_ptr: int, Nout: int, Kin: int, rows: int,
               ld_dy: Optional[int] = None, dy_ptr: Optional[int] = None, ldg: Optional[int] = None) -> None:
@@ -244,9 +249,35 @@ class CaptionEngine:
         tiles = ((Nout + 127) // 128) * ((Kin + 127) // 128)
         split = max(1, min(32, (148 * 2) // max(1, tiles), (rows + 511) // 512))
         ab = BF16 if self.precision == "bf16" else F32
+        ev = self._prof_begin()
         call("icap_gemm", ab, 0, 0, Nout, Kin, rows, dy.data_ptr() if dy_ptr is None else dy_ptr,
              dy.shape[-1] if ld_dy is None else ld_dy, x.data_ptr(), x.shape[-1], g_ptr, Kin if ldg is None else ldg,
              F32, None, 0, None, 0, 1, split, self._s())
+        self._prof_end(ev, 2.0 * Nout * Kin * rows)
+
+    def _prof_begin(self):
+        if self._prof is None:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def _prof_end(self, e0, flops: float) -> None:
+        if e0 is None:
+            return
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self._prof.append((e0, e1, flops))
+
+    def profile_gemms(self, fn) -> "List[Tuple[float, float]]":
+        """Run fn() eagerly with a CUDA-event pair around every GEMM launch; returns [(ms, flops)]."""
+        self._prof = []
+        try:
+            fn()
+            torch.cuda.synchronize(self.dev)
+            return [(a.elapsed_time(b), fl) for a, b, fl in self._prof]
+        finally:
+            self._prof = None
 
     def add_ln(self, a: torch.Tensor, res: Optional[torch.Tensor], res_rows: int, norm: str,
                rowscale: Optional[torch.Tensor], p_drop: float):
@@ -443,10 +474,11 @@ class CaptionEngine:
         else:
             e = self.new(M, d)
             self.gemm(xcat, True, wcat.data_ptr(), Kc, True, M, d, Kc, e)
-            x, mean, rstd, _, _ = self.add_ln(e, None, 1, "encoder.norm", None, 0.0)
+            x0, mean, rstd, _, _ = self.add_ln(e, None, 1, "encoder.norm", None, 0.0)
+            x = x0
             if self.tape is not None:
-                def bwd():
-                    ds, _ = self.ln_bwd(x, e, mean, rstd, "encoder.norm", None, 0.0, 0)
+                def bwd():      # NB: closes over x0 (x is re-bound by the block loop below)
+                    ds, _ = self.ln_bwd(x0, e, mean, rstd, "encoder.norm", None, 0.0, 0)
                     dwcat = self.new(d, Kc, dtype=torch.float32, zero=True)
                     self.wgrad(ds, xcat, dwcat.data_ptr(), d, Kc, M)
                     self._unpack_embed_grads(dwcat)
@@ -477,10 +509,11 @@ class CaptionEngine:
              emb.data_ptr(), None, cfg.pad_idx, self._s())
         we = self.new(M, d)
         self.gemm(emb, True, self.w("decoder.word_embedding_linear.weight"), E, True, M, d, E, we)
-        x, mean, rstd, _, _ = self.add_ln(we, self.pos_table_act, T, "decoder.norm", None, 0.0)
+        x0, mean, rstd, _, _ = self.add_ln(we, self.pos_table_act, T, "decoder.norm", None, 0.0)
+        x = x0
         if self.tape is not None:
-            def bwd():
-                ds, _ = self.ln_bwd(x, we, mean, rstd, "decoder.norm", None, 0.0, 0)
+            def bwd():          # NB: closes over x0 (x is re-bound by the block loop below)
+                ds, _ = self.ln_bwd(x0, we, mean, rstd, "decoder.norm", None, 0.0, 0)
                 self.wgrad(ds, emb, self.g("decoder.word_embedding_linear.weight"), d, E, M)
                 demb = self.new(M, E)
                 self.gemm(ds, True, self.w("decoder.word_embedding_linear.weight"), E, False, M, E, d, demb)
@@ -550,8 +583,12 @@ class CaptionEngine:
         row_loss = self.new(M, dtype=torch.float32)
         out2 = self.new(2, dtype=torch.float32)
         inv_count = count2[1:2]
-        call("icap_xent", self.act, M, V, logits.data_ptr(), ldl, tgt.data_ptr(), cfg.pad_idx, inv_count.data_ptr(),
+        grad_scale = self.one if self.dp_unnormalized else inv_count     # DP: divide by the GLOBAL count in Adam
+        call("icap_xent", self.act, M, V, logits.data_ptr(), ldl, tgt.data_ptr(), cfg.pad_idx, grad_scale.data_ptr(),
              row_loss.data_ptr(), int(record), self._s())
+        if self.dp_unnormalized and record:
+            call("icap_copy2d", count2.data_ptr(), F32, 1, self.g32.data_ptr() + 4 * self.n_flat, F32, 1, 1, 1, 1,
+                 self._s())
         call("icap_xent_finalize", M, row_loss.data_ptr(), inv_count.data_ptr(), int(cfg.focal), out2.data_ptr(),
              self._s())
         if record:
@@ -588,14 +625,21 @@ class CaptionEngine:
              _ptr(gscale_dev), gscale, self._s())
         self.shadow_fresh = True
 
-    def train_step(self, feats, pos, captions, lr: float = 5e-4) -> torch.Tensor:
+    def train_step(self, feats, pos, captions, lr: float = 5e-4, train_mode: bool = True) -> torch.Tensor:
         """zero_grad -> forward -> backward -> Adam (core/models.py:115-126), all on the current stream.
-        Returns the device tensor [loss, dloss/dce] (no host sync)."""
-        self.training = True
+        Returns the device tensor [loss, dloss/dce] (no host sync).  train_mode=False keeps dropout off
+        (the reference's eval-mode arithmetic, used by the parity tests)."""
+        out2 = self.forward_backward(feats, pos, captions, train_mode)
+        self.adam_step(lr, gscale_dev=out2[1:2] if self.cfg.focal else None)
+        return out2
+
+    def forward_backward(self, feats, pos, captions, train_mode: bool = True) -> torch.Tensor:
+        """zero_grad + forward + backward; gradients land in g32 (data parallel: all-reduce them next)."""
+        self.training = train_mode
+        self.g32.zero_()      # before the forward: in DP mode the forward deposits the token count in the tail slot
         logits, tgt, count2, dec = self.forward_logits(feats, pos, captions, record=True)
         out2 = self.loss_from_logits(logits, tgt, count2, dec, record=True)
-        self.backward(zero_grads=True)
-        self.adam_step(lr, gscale_dev=out2[1:2] if self.cfg.focal else None)
+        self.backward(zero_grads=False)
         return out2
 
     # ------------------------------------------------------------------ KV-cached decoding

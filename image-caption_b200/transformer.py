@@ -51,12 +51,11 @@ class _LossFn(torch.autograd.Function):
     """Lets `loss.backward()` (core/models.py:125) drive the explicit backward of the engine."""
 
     @staticmethod
-    def forward(ctx, model, feats, pos, captions, *params):
+    def forward(ctx, model, record, feats, pos, captions, *params):
         eng = model._engine()
         eng.training = model.training
         eng.shadow_fresh = False                       # an external optimizer may have stepped the weights
         f, p, c = eng.prepare_inputs(feats, pos, captions)
-        record = torch.is_grad_enabled() and any(q.requires_grad for q in params)
         logits, tgt, count2, dec = eng.forward_logits(f, p, c, record=record)
         out2 = eng.loss_from_logits(logits, tgt, count2, dec, record=record)
         ctx.model, ctx.out2, ctx.recorded = model, out2, record
@@ -78,7 +77,7 @@ class _LossFn(torch.autograd.Function):
         for name, q in model.named_parameters():
             off = eng.offsets[name]
             q.grad = eng.g32[off:off + q.numel()].view_as(q)
-        return (None,) * (4 + len(params))
+        return (None,) * (5 + len(params))
 
 
 class Transformer(nn.Module):
@@ -214,7 +213,8 @@ class Transformer(nn.Module):
     def forward(self, object_features, position_features, target_caption):
         """model.py:79-98 -> {'loss': 0-d tensor}."""
         params = [q for _, q in self.named_parameters()]
-        loss = _LossFn.apply(self, object_features, position_features, target_caption, *params)
+        record = torch.is_grad_enabled() and any(q.requires_grad for q in params)   # grad mode is off inside apply()
+        loss = _LossFn.apply(self, record, object_features, position_features, target_caption, *params)
         return {"loss": loss}
 
     @torch.no_grad()
@@ -257,13 +257,45 @@ class Transformer(nn.Module):
         return mask.unsqueeze(1).expand(k.size(0), q.size(1), k.size(1))
 
     # ------------------------------------------------------------------ fused training step
-    def train_step_fused(self, object_features, position_features, target_caption, lr: float = 5e-4) -> torch.Tensor:
+    def train_step_fused(self, object_features, position_features, target_caption, lr: float = 5e-4,
+                         train_mode: Optional[bool] = None) -> torch.Tensor:
         """zero_grad + forward + backward + Adam in one stream-ordered launch sequence
         (core/models.py:115-126).  Returns the device loss (0-d view, no host sync)."""
         eng = self._engine()
         f, p, c = eng.prepare_inputs(object_features, position_features, target_caption)
-        out2 = eng.train_step(f, p, c, lr=lr)
+        out2 = eng.train_step(f, p, c, lr=lr, train_mode=self.training if train_mode is None else train_mode)
         return out2[0]
+
+
+class DataParallel:
+    """Data parallelism by image: one process per GPU, replicated weights and Adam state.
+    Every rank back-propagates the SUM of its token losses (dlogits not divided by the local count); the flat
+    gradient buffer carries the local non-pad token count in its tail slot, so ONE all-reduce(SUM) yields both
+    the summed gradients and the global count, and Adam divides by it (gscale).  That reproduces the
+    reference's global `mean over non-pad targets` exactly, whatever the per-rank token counts are."""
+
+    def __init__(self, model: "Transformer", dist):
+        self.dist = dist
+        self.world = dist.get_world_size()
+        eng = model._engine()
+        eng.dp_unnormalized = True
+        dist.broadcast(eng.p32, src=0)          # identical replicas
+        eng.shadow_fresh = False
+        self.inv = torch.zeros(1, dtype=torch.float32, device=eng.dev)
+
+    @staticmethod
+    def allreduce_flat(dist, g32: torch.Tensor, n_flat: int) -> torch.Tensor:
+        """In-place SUM all-reduce of [grads | count]; returns the view holding the global token count."""
+        dist.all_reduce(g32, op=dist.ReduceOp.SUM)
+        return g32[n_flat:n_flat + 1]
+
+    def reduce(self, eng: CaptionEngine) -> None:
+        self.allreduce_flat(self.dist, eng.g32, eng.n_flat)
+
+    def finish(self, eng: CaptionEngine, lr: float) -> None:
+        from ._native import call
+        call("icap_reciprocal", eng.g32.data_ptr() + 4 * eng.n_flat, self.inv.data_ptr(), 1.0, eng._s())
+        eng.adam_step(lr, gscale_dev=self.inv)
 
 
 class GraphedTrainStep:
@@ -272,8 +304,10 @@ class GraphedTrainStep:
     device-side step counter into their seeds."""
 
     def __init__(self, model: Transformer, batch: int, regions: int, caption_len: int, lr: float = 5e-4,
-                 warmup: int = 2):
+                 warmup: int = 2, dp: Optional[DataParallel] = None):
         eng = model._engine()
+        self.dp = dp
+        self.graph2: Optional[torch.cuda.CUDAGraph] = None
         cfg = model.cfg
         dev = eng.dev
         self.model, self.eng, self.lr = model, eng, lr
@@ -301,7 +335,12 @@ class GraphedTrainStep:
         side.wait_stream(torch.cuda.current_stream(eng.dev))
         with torch.cuda.stream(side):
             for _ in range(self.warmup):
-                eng.train_step(self.feats, self.pos, self.cap, lr=self.lr)
+                if self.dp is None:
+                    eng.train_step(self.feats, self.pos, self.cap, lr=self.lr)
+                else:
+                    eng.forward_backward(self.feats, self.pos, self.cap)
+                    self.dp.reduce(eng)
+                    self.dp.finish(eng, self.lr)
         torch.cuda.current_stream(eng.dev).wait_stream(side)
         eng.p32.copy_(p0)
         eng.step_dev.copy_(step0)
@@ -312,12 +351,22 @@ class GraphedTrainStep:
         torch.cuda.synchronize(eng.dev)
         self.graph = torch.cuda.CUDAGraph()
         n0 = _native.launch_count
-        with torch.cuda.graph(self.graph):
-            self.out2 = eng.train_step(self.feats, self.pos, self.cap, lr=self.lr)
+        if self.dp is None:
+            with torch.cuda.graph(self.graph):
+                self.out2 = eng.train_step(self.feats, self.pos, self.cap, lr=self.lr)
+        else:     # graph 1: zero_grad/forward/backward ; NCCL all-reduce (eager) ; graph 2: 1/count + Adam
+            with torch.cuda.graph(self.graph):
+                self.out2 = eng.forward_backward(self.feats, self.pos, self.cap)
+            self.graph2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph2):
+                self.dp.finish(eng, self.lr)
         self.launches_per_step = _native.launch_count - n0
 
     def step(self) -> torch.Tensor:
         if self.graph is None:
             self.capture()
         self.graph.replay()
+        if self.dp is not None:
+            self.dp.reduce(self.eng)
+            self.graph2.replay()
         return self.out2[0]

@@ -137,6 +137,8 @@ int icap_adam_step(int64_t n, float* p, const float* g, float* m, float* v, void
                    float beta2, float eps, int* step_dev, int tick, const float* gscale_dev, float gscale,
                    void* stream);
 int icap_scale(float* x, int64_t n, const float* s_dev, float s, void* stream);
+/* out[0] = numerator / x[0]  (data parallel: 1 / all-reduced token count, consumed by icap_adam_step as gscale_dev). */
+int icap_reciprocal(const float* x, float* out, float numerator, void* stream);
 
 #ifdef __cplusplus
 }

@@ -67,7 +67,7 @@ LAYOUTS = [(1, 1), (1, 0), (0, 0)]
 @pytest.mark.parametrize("a_k,b_k", LAYOUTS)
 @pytest.mark.parametrize("M,Nn,K", [(128, 128, 64), (300, 200, 136), (37, 397, 84), (1024, 512, 2048)])
 def test_gemm_fp32_layouts(a_k, b_k, M, Nn, K):
-    assert _gemm_case(F32, a_k, b_k, M, Nn, K) < 2e-6
+    assert _gemm_case(F32, a_k, b_k, M, Nn, K) < 5e-6
 
 
 def test_gemm_fp32_epilogues():
