@@ -11,6 +11,17 @@
 // softmax uses warp shuffles.  Backward recomputes P (nothing but Q, K, V, dO is read).
 #include "icap_common.cuh"
 
+// tensor-core (mma.sync) variants for bf16 / head dim 64, attention_mma.cu
+bool icap_mha_mma_ok(int dtype, int64_t Lq, int64_t Lk, int64_t dk, int64_t dv, int64_t ldq, int64_t ldk, int64_t ldv,
+                     const void* q, const void* k, const void* v);
+int icap_mha_fwd_mma(int64_t B, int64_t H, int64_t Lq, int64_t Lk, const void* q, int64_t ldq, const void* k,
+                     int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo, const uint8_t* kvalid, int causal,
+                     float p_drop, uint64_t seed, const int* seed_dev, cudaStream_t st);
+int icap_mha_bwd_mma(int64_t B, int64_t H, int64_t Lq, int64_t Lk, const void* q, int64_t ldq, const void* k,
+                     int64_t ldk, const void* v, int64_t ldv, const void* dout, int64_t lddo, void* dq, int64_t lddq,
+                     void* dk_out, int64_t lddk, void* dv_out, int64_t lddv, const uint8_t* kvalid, int causal,
+                     float p_drop, uint64_t seed, const int* seed_dev, cudaStream_t st);
+
 namespace {
 
 constexpr int NT = 128;
@@ -349,6 +360,10 @@ extern "C" int icap_mha_fwd(int dtype, int64_t B, int64_t H, int64_t Lq, int64_t
                             void* o, int64_t ldo, const uint8_t* kvalid, int causal, float p_drop, uint64_t seed,
                             const int* seed_dev, float* attn_mean, void* stream) {
   if (int rc = check_dims("icap_mha_fwd", B, H, Lq, Lk, dk, dv)) return rc;
+  if (attn_mean == nullptr && icap_mha_mma_ok(dtype, Lq, Lk, dk, dv, ldq, ldk, ldv, q, k, v) && ldo % 8 == 0 &&
+      (uintptr_t)o % 16 == 0)
+    return icap_mha_fwd_mma(B, H, Lq, Lk, q, ldq, k, ldk, v, ldv, o, ldo, kvalid, causal, p_drop, seed, seed_dev,
+                            (cudaStream_t)stream);
   AttnDims D{(int)Lq, (int)Lk, (int)((Lk + 3) & ~3), (int)dk, (int)dv, (int)H};
   const size_t smem = sizeof(float) * ((size_t)D.Lq * D.dk + (size_t)D.dk * D.LkP + (size_t)D.Lk * D.dv +
                                        (size_t)D.Lq * D.LkP);
@@ -379,6 +394,11 @@ extern "C" int icap_mha_bwd(int dtype, int64_t B, int64_t H, int64_t Lq, int64_t
                             void* dv_out, int64_t lddv, const uint8_t* kvalid, int causal, float p_drop, uint64_t seed,
                             const int* seed_dev, void* stream) {
   if (int rc = check_dims("icap_mha_bwd", B, H, Lq, Lk, dk, dv)) return rc;
+  if (icap_mha_mma_ok(dtype, Lq, Lk, dk, dv, ldq, ldk, ldv, q, k, v) && lddo % 8 == 0 && lddq % 8 == 0 &&
+      lddk % 8 == 0 && lddv % 8 == 0 && (uintptr_t)dout % 16 == 0 && (uintptr_t)dq % 16 == 0 &&
+      (uintptr_t)dk_out % 16 == 0 && (uintptr_t)dv_out % 16 == 0)
+    return icap_mha_bwd_mma(B, H, Lq, Lk, q, ldq, k, ldk, v, ldv, dout, lddo, dq, lddq, dk_out, lddk, dv_out, lddv,
+                            kvalid, causal, p_drop, seed, seed_dev, (cudaStream_t)stream);
   AttnDims D{(int)Lq, (int)Lk, (int)((Lk + 3) & ~3), (int)dk, (int)dv, (int)H};
   const size_t smem = sizeof(float) * ((size_t)D.Lq * D.dk + (size_t)D.Lk * D.dk + (size_t)D.dk * D.LkP +
                                        (size_t)D.dv * D.LkP + (size_t)D.Lq * D.dv + 2 * (size_t)D.Lq * D.LkP);

@@ -14,6 +14,7 @@
 // Replaces the reference's nn.Linear / torch.matmul calls (modules.py:72-77,86,113-116;
 // model.py:93,295-306,433) in bf16 mode.
 #include <cuda.h>
+#include <stdlib.h>
 #include "icap_common.cuh"
 
 namespace {
@@ -52,6 +53,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tm), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tm), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -120,15 +129,17 @@ template <> struct OutVec<bf16> {
 
 template <bool A_KMAJOR, bool B_KMAJOR, typename TO>
 __global__ void __launch_bounds__(NTHREADS, 2)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmX, int M, int N, int K,
                TO* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int epi, const TO* __restrict__ aux,
-               int64_t ldaux, int accumulate, int kb_per_split, int vec_ok) {
+               int64_t ldaux, int accumulate, int kb_per_split, int vec_ok, int store_mode) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base, sB = smem_base + STAGES * TILE_BYTES;
   const uint32_t bars = sB + STAGES * TILE_BYTES;        // full[S], empty[S], tmem_full, tmem slot
   const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES, tfull_bar = bars + 16 * STAGES;
   const uint32_t slot_addr = tfull_bar + 8;
+  const uint32_t aux_bar = tfull_bar + 16;                // 4 x 8 B: one per epilogue warp (aux tile loads)
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen_base + (slot_addr - smem_base));
 
@@ -146,6 +157,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(empty_bar + 8 * i, 1);
     }
     mbar_init(tfull_bar, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(aux_bar + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -209,6 +221,88 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_wait(tfull_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const bool add_bias = (bias != nullptr) && (blockIdx.z == 0);
+    if (store_mode != 0) {
+      // ---- staged epilogue: TMEM -> registers -> 128B-swizzled smem slab (the drained pipeline stages are
+      // reused) -> TMA store / TMA reduce-add.  One 32-row slab per warp, so no cross-warp barrier is needed.
+      constexpr int ESZ = (int)sizeof(TO);
+      constexpr int COLS_PER_BOX = 128 / ESZ;               // 64 bf16 or 32 fp32 columns = one 128 B swizzle row
+      constexpr int NBOX = BN / COLS_PER_BOX;               // 2 or 4 boxes of 32 rows x 128 B = 4 KB
+      const uint32_t slab = sA + (uint32_t)q * (NBOX * 4096);
+      const uint32_t my_row = slab + (uint32_t)lane * 128;
+      const uint32_t sw = (uint32_t)(lane & 7);
+      if (epi == 2) {                                       // ReLU mask tile arrives by TMA into the same slab
+        if (lane == 0) {
+          mbar_expect_tx(aux_bar + 8 * q, NBOX * 4096);
+          for (int j = 0; j < NBOX; ++j)
+            tma_load_2d(slab + j * 4096, &tmX, n0 + j * COLS_PER_BOX, m0 + q * 32, aux_bar + 8 * q);
+        }
+        mbar_wait(aux_bar + 8 * q, 0);
+      }
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+        const int col0 = n0 + c * 32;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (add_bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (col0 + j < N) v[j] += __ldg(bias + col0 + j);
+        }
+        if (epi == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        const int box = (c * 32) / COLS_PER_BOX;
+        const int chunk0 = ((c * 32) % COLS_PER_BOX) * ESZ / 16;     // first 16 B chunk of this 32-column group
+        constexpr int NCH = 32 * ESZ / 16;                             // 4 (bf16) or 8 (fp32) chunks
+        constexpr int EPC = 16 / ESZ;                                  // elements per chunk
+#pragma unroll
+        for (int t = 0; t < NCH; ++t) {
+          const uint32_t addr = my_row + box * 4096 + (((uint32_t)(chunk0 + t) ^ sw) << 4);
+          if (epi == 2) {
+            uint4 a;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(addr));
+            if constexpr (ESZ == 2) {
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (!(__low2float(h[e]) > 0.f)) v[t * 8 + 2 * e] = 0.f;
+                if (!(__high2float(h[e]) > 0.f)) v[t * 8 + 2 * e + 1] = 0.f;
+              }
+            } else {
+              const float* fa = reinterpret_cast<const float*>(&a);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) if (!(fa[e] > 0.f)) v[t * 4 + e] = 0.f;
+            }
+          }
+          uint4 o;
+          if constexpr (ESZ == 2) {
+            __nv_bfloat162 h;
+            h = __floats2bfloat162_rn(v[t * 8 + 0], v[t * 8 + 1]); o.x = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2bfloat162_rn(v[t * 8 + 2], v[t * 8 + 3]); o.y = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2bfloat162_rn(v[t * 8 + 4], v[t * 8 + 5]); o.z = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2bfloat162_rn(v[t * 8 + 6], v[t * 8 + 7]); o.w = *reinterpret_cast<uint32_t*>(&h);
+          } else {
+            o.x = __float_as_uint(v[t * EPC + 0]); o.y = __float_as_uint(v[t * EPC + 1]);
+            o.z = __float_as_uint(v[t * EPC + 2]); o.w = __float_as_uint(v[t * EPC + 3]);
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0 && m0 + q * 32 < M) {
+        for (int j = 0; j < NBOX; ++j) {
+          if (n0 + j * COLS_PER_BOX >= N) break;
+          if (store_mode == 2) tma_reduce_add_2d(&tmC, slab + j * 4096, n0 + j * COLS_PER_BOX, m0 + q * 32);
+          else tma_store_2d(&tmC, slab + j * 4096, n0 + j * COLS_PER_BOX, m0 + q * 32);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+    } else
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t r[32];
@@ -291,15 +385,18 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 row-major tensor [rows][cols] (ld elements) with box {box_cols (=64), box_rows}, 128B swizzle
-int make_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// 2-D row-major tensor [rows][cols] (ld elements) with a 128-byte-wide box of box_rows rows, 128B swizzle
+int make_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+              int dtype = ICAP_BF16) {
   EncodeTiledFn fn = get_encode_fn();
   ICAP_ARG(fn != nullptr, "cuTensorMapEncodeTiled entry point not found (driver too old?)");
+  const int esz = dtype == ICAP_BF16 ? 2 : 4;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+  CUresult r = fn(tm, dtype == ICAP_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(ptr), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   ICAP_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): ptr=%p rows=%lld cols=%lld ld=%lld", (int)r, ptr,
@@ -308,9 +405,9 @@ int make_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int6
 }
 
 template <bool AK, bool BKM, typename TO>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, void* C, int64_t ldc, const float* bias,
-           int epi, const void* aux, int64_t ldaux, int accumulate, int kb_per_split, int splits, int vec_ok,
-           cudaStream_t st) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tx, int M, int N,
+           int K, void* C, int64_t ldc, const float* bias, int epi, const void* aux, int64_t ldaux, int accumulate,
+           int kb_per_split, int splits, int vec_ok, int store_mode, cudaStream_t st) {
   static bool attr_done = false;
   auto kern = gemm_tc_kernel<AK, BKM, TO>;
   if (!attr_done) {
@@ -318,8 +415,8 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, vo
     attr_done = true;
   }
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)splits);
-  kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(ta, tb, M, N, K, (TO*)C, ldc, bias, epi, (const TO*)aux, ldaux, accumulate,
-                                           kb_per_split, vec_ok);
+  kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(ta, tb, tc, tx, M, N, K, (TO*)C, ldc, bias, epi, (const TO*)aux, ldaux,
+                                           accumulate, kb_per_split, vec_ok, store_mode);
   ICAP_LAUNCH_CHECK("icap_gemm(bf16 tcgen05)");
   return 0;
 }
@@ -352,12 +449,20 @@ int icap_gemm_bf16_launch(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int6
   const int esz = c_dtype == ICAP_F32 ? 4 : 2;
   int vec_ok = ((uintptr_t)C % 16 == 0) && ((ldc * esz) % 16 == 0);
   if (epi == 2) vec_ok = vec_ok && ((uintptr_t)aux % 16 == 0) && ((ldaux * esz) % 16 == 0);
+  // staged TMA epilogue whenever C (and aux) satisfy the TMA alignment rules; accumulation = TMA reduce-add
+  int store_mode = vec_ok ? (accumulate ? 2 : 1) : 0;
+  if (getenv("ICAP_GEMM_DIRECT_EPILOGUE")) store_mode = 0;
+  CUtensorMap tc = ta, tx = ta;
+  if (store_mode) {
+    if ((rc = make_tmap(&tc, C, M, N, ldc, 32, c_dtype))) return rc;
+    if (epi == 2 && (rc = make_tmap(&tx, aux, M, N, ldaux, 32, c_dtype))) return rc;
+  }
 #define GO(AK, BKM)                                                                                                 \
   (c_dtype == ICAP_F32                                                                                              \
-       ? launch<AK, BKM, float>(ta, tb, (int)M, (int)N, (int)K, C, ldc, bias, epi, aux, ldaux, accumulate, kb_per,  \
-                                split_k, vec_ok, st)                                                                \
-       : launch<AK, BKM, bf16>(ta, tb, (int)M, (int)N, (int)K, C, ldc, bias, epi, aux, ldaux, accumulate, kb_per,   \
-                               split_k, vec_ok, st))
+       ? launch<AK, BKM, float>(ta, tb, tc, tx, (int)M, (int)N, (int)K, C, ldc, bias, epi, aux, ldaux, accumulate,  \
+                                kb_per, split_k, vec_ok, store_mode, st)                                            \
+       : launch<AK, BKM, bf16>(ta, tb, tc, tx, (int)M, (int)N, (int)K, C, ldc, bias, epi, aux, ldaux, accumulate,   \
+                               kb_per, split_k, vec_ok, store_mode, st))
   if (a_kmajor && b_kmajor) return GO(true, true);
   if (a_kmajor && !b_kmajor) return GO(true, false);
   return GO(false, false);

@@ -242,6 +242,12 @@ def test_mha_fwd_bwd(act, B, H, Lq, Lk, dk, dv, causal, usevalid):
     tol = 1e-5 if act == F32 else 1.5e-2
     assert rel_err(o, ref.detach().view(B * Lq, -1)) < tol
     assert rel_err(amean, att_ref.detach().mean(1)) < tol
+    # without the attention-mean output the bf16 / head-dim-64 cases take the mma.sync tensor-core kernel
+    o2 = torch.empty_like(o)
+    N.call("icap_mha_fwd", act, B, H, Lq, Lk, dk, dv, qb.data_ptr(), ldq, kvb.data_ptr(), ldkv,
+           kvb.data_ptr() + H * dk * esz, ldkv, o2.data_ptr(), H * dv, kvalid.data_ptr() if usevalid else None,
+           int(causal), 0.0, 0, None, None, S())
+    assert rel_err(o2, ref.detach().view(B * Lq, -1)) < tol
     dq = torch.zeros(B * Lq, ldq, device=dev(), dtype=tdt)
     dkv = torch.zeros(B * Lk, ldkv, device=dev(), dtype=tdt)
     N.call("icap_mha_bwd", act, B, H, Lq, Lk, dk, dv, qb.data_ptr(), ldq, kvb.data_ptr(), ldkv,
@@ -278,6 +284,31 @@ def test_mha_dropout_is_consistent_between_fwd_and_bwd():
     dO = dout.view(B, L, H, dkk).permute(0, 2, 1, 3)
     dV_ref = (Pd.transpose(2, 3) @ dO).permute(0, 2, 1, 3).reshape(B * L, H * dkk)
     assert rel_err(dv_, dV_ref) < 1e-5
+
+
+def test_mha_mma_dropout_is_consistent_between_fwd_and_bwd():
+    """Same probe for the tensor-core kernels (bf16, head dim 64): V = I exposes the dropped probabilities."""
+    B, H, L, dh = 2, 2, 64, 64
+    g = torch.Generator(device="cuda").manual_seed(13)
+    q = (torch.randn(B * L, H * dh, device=dev(), generator=g) * 0.5).bfloat16()
+    k = (torch.randn(B * L, H * dh, device=dev(), generator=g) * 0.5).bfloat16()
+    v = torch.eye(L, device=dev()).repeat(B, H).bfloat16().contiguous()
+    o = torch.empty(B * L, H * dh, device=dev(), dtype=torch.bfloat16)
+    p, seed = 0.25, 5
+    N.call("icap_mha_fwd", BF16, B, H, L, L, dh, dh, q.data_ptr(), H * dh, k.data_ptr(), H * dh, v.data_ptr(), H * dh,
+           o.data_ptr(), H * dh, None, 0, p, seed, None, None, S())
+    Pd = o.float().view(B, L, H, L).permute(0, 2, 1, 3)
+    assert abs(float((Pd == 0).float().mean()) - p) < 0.03
+    assert torch.allclose(Pd.sum(-1).mean(), torch.tensor(1.0, device=dev()), atol=0.05)     # E[sum] = 1
+    dout = torch.randn(B * L, H * dh, device=dev(), generator=g).bfloat16()
+    dq = torch.empty_like(q); dk_ = torch.empty_like(k); dv_ = torch.empty_like(v)
+    N.call("icap_mha_bwd", BF16, B, H, L, L, dh, dh, q.data_ptr(), H * dh, k.data_ptr(), H * dh, v.data_ptr(), H * dh,
+           dout.data_ptr(), H * dh, dq.data_ptr(), H * dh, dk_.data_ptr(), H * dh, dv_.data_ptr(), H * dh, None, 0, p,
+           seed, None, S())
+    torch.cuda.synchronize()
+    dO = dout.float().view(B, L, H, dh).permute(0, 2, 1, 3)
+    dV_ref = (Pd.transpose(2, 3) @ dO).permute(0, 2, 1, 3).reshape(B * L, H * dh)
+    assert rel_err(dv_, dV_ref) < 2e-2
 
 
 def test_mha_decode_matches_full_attention():
