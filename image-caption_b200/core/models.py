@@ -1,0 +1,103 @@
+"""Drop-in for the caption-model wrapper of the reference's core/models.py:18-135 (`MODEL_init`, `TRANSFORMER`):
+same methods, same argument meaning.  train_step runs the fused zero_grad/forward/backward/Adam sequence of
+libicap (core/models.py:115-126); inputs arrive as CPU tensors from a DataLoader and are moved to DEVICE here."""
+import os
+import pickle
+
+import torch
+import torch.nn as nn
+
+from core.TRANSFORMER.model import Transformer
+from core.config import *          # noqa: F401,F403  (the reference does the same, models.py:12)
+from core.utils import decode_captions
+
+
+class MODEL_init:
+
+    def __init__(self):
+        if os.path.exists(WORD_TO_IDX_PATH):
+            word_to_idx = pickle.load(open(WORD_TO_IDX_PATH, 'rb'))
+        else:   # offline / synthetic mode: the reference's special tokens (preprocess.py:303) + numbered words
+            word_to_idx = {'<NULL>': 0, '<START>': 1, '<END>': 2, '<UNK>': 3}
+            word_to_idx.update({f'w{i}': i for i in range(4, SYNTHETIC_VOCAB)})
+        self.num_vocab = len(word_to_idx)
+        self.idx_to_word = {i: w for w, i in word_to_idx.items()}
+        self.model = nn.Module()
+
+    def train_step(self):
+        raise NotImplementedError
+
+    def compute_loss(self):
+        raise NotImplementedError
+
+    def generate_caption(self, object_features, position_features, beam_size=None):
+        if beam_size in [None, 1]:
+            caption_vector, attention_list = self.model.generate_caption_vector(
+                object_features=object_features.to(DEVICE), position_features=position_features.to(DEVICE))
+            return self.decode_captions(caption_vector.cpu().numpy()), attention_list
+        elif isinstance(beam_size, int) and beam_size > 1:
+            caption_vector = self.model.beam_search(object_features=object_features.to(DEVICE),
+                                                    position_features=position_features.to(DEVICE),
+                                                    beam_size=beam_size)
+            return self.decode_captions(caption_vector.cpu().numpy()), None
+        else:
+            assert isinstance(beam_size, int)
+            assert beam_size > 1 or beam_size in [None, 1]
+
+    def decode_captions(self, caption_vector):
+        return decode_captions(captions=caption_vector, index_to_word=self.idx_to_word)
+
+    def save(self, path):
+        torch.save(self.model.state_dict(), path)
+
+    def load(self, path):
+        state_dict = torch.load(path, map_location=DEVICE)
+        self.model.load_state_dict(state_dict)
+        self.model.eval()
+
+    def preprocess(self, image_path, save_img=False, max_obj=False):
+        raise NotImplementedError("image feature extraction (YOLOv5 + ResNet-101, core/preprocess.py:91-138) is the "
+                                  "stage BEFORE the hot path and needs pretrained weights that are not available "
+                                  "offline; pass precomputed features (SURVEY.md §8f #4)")
+
+
+class TRANSFORMER(MODEL_init):
+
+    def __init__(self):
+        super(TRANSFORMER, self).__init__()
+        self.model = Transformer(num_vocab=self.num_vocab,
+                                 max_length=MAX_LENGTH + 2,
+                                 encode_dim_positions=ENCODE_DIM_POSITIONS,
+                                 encode_dim_features=ENCODE_DIM_FEATURES,
+                                 encode_input_size=ENCODE_INPUT_SIZE,
+                                 encode_q_k_dim=ENCODE_Q_K_DIM,
+                                 encode_v_dim=ENCODE_V_DIM,
+                                 encode_hidden_size=ENCODE_HIDDEN_SIZE,
+                                 encode_num_blocks=ENCODE_NUM_BLOCKS,
+                                 encode_num_heads=ENCODE_NUM_HEADS,
+                                 dim_word_embedding=DIM_WORD_EMBEDDING,
+                                 decode_input_size=DECODE_INPUT_SIZE,
+                                 decode_q_k_dim=DECODE_Q_K_DIM,
+                                 decode_v_dim=DECODE_V_DIM,
+                                 decode_hidden_size=DECODE_HIDDEN_SIZE,
+                                 decode_num_blocks=DECODE_NUM_BLOCKS,
+                                 decode_num_heads=DECODE_NUM_HEADS,
+                                 dropout=DROPOUT,
+                                 device=DEVICE,
+                                 output_name=OUTPUT_NAME,
+                                 encode_mask=ENCODE_MASK,
+                                 pad_idx=PAD_IDX,
+                                 move_first_image_feature=MOVE_FIRST_IMAGE_FAETURE,
+                                 split_position=SPLIT_POSITION,
+                                 split_image_objects=SPLIT_IMAGE_OBJECTS).to(DEVICE)
+        # Adam(lr=LEARNING_RATE) state lives in the engine's flat buffers (models.py:111-113)
+        self.last_loss = None
+
+    def train_step(self, batch_features, batch_positions, batch_captions):
+        self.last_loss = self.model.train_step_fused(batch_features, batch_positions, batch_captions, lr=LEARNING_RATE)
+
+    def compute_loss(self, object_features, position_features, target_caption):
+        with torch.no_grad():
+            return self.model(object_features=object_features.to(DEVICE),
+                              position_features=position_features.to(DEVICE),
+                              target_caption=target_caption.to(DEVICE))

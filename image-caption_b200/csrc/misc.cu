@@ -182,6 +182,40 @@ __global__ void scale_kernel(float* __restrict__ x, int64_t n, const float* __re
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] *= f;
 }
 
+// dst[r][:] = (base ? base[r][:] : 0) + src[(r / div) * mul + off][:]   (row broadcast / gather)
+template <typename T>
+__global__ void rows_gather_add_kernel(const T* __restrict__ src, int64_t src_ld, const T* __restrict__ base,
+                                       int64_t base_ld, T* __restrict__ dst, int64_t dst_ld, int64_t rows, int cols,
+                                       int div, int mul, int off) {
+  const int c4 = cols >> 2;
+  for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < rows * c4; u += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = u / c4;
+    const int c = (int)(u % c4) * 4;
+    float v[4];
+    load4(src + ((r / div) * mul + off) * src_ld + c, v);
+    if (base) {
+      float b[4];
+      load4(base + r * base_ld + c, b);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] += b[j];
+    }
+    store4(dst + r * dst_ld + c, v);
+  }
+}
+// dst[s * mul + off][:] += sum_{t < seg_len} src[s * seg_len + t][:]       (adjoint of the broadcast)
+template <typename T>
+__global__ void rows_segsum_add_kernel(const T* __restrict__ src, int64_t src_ld, T* __restrict__ dst, int64_t dst_ld,
+                                       int64_t nseg, int seg_len, int cols, int mul, int off) {
+  for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < nseg * cols; u += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t sg = u / cols;
+    const int c = (int)(u % cols);
+    float acc = 0.f;
+    for (int t = 0; t < seg_len; ++t) acc += to_f32(src[(sg * seg_len + t) * src_ld + c]);
+    T* d = dst + (sg * mul + off) * dst_ld + c;
+    *d = from_f32<T>(to_f32(*d) + acc);
+  }
+}
+
 inline unsigned grid_for(int64_t work, int threads) {
   int64_t b = ceil_div64(work, threads);
   const int64_t cap = 148 * 16;
@@ -205,6 +239,39 @@ extern "C" int icap_copy2d(const void* src, int src_dtype, int64_t src_ld, void*
   else GO(bf16, bf16);
 #undef GO
   ICAP_LAUNCH_CHECK("icap_copy2d");
+  return 0;
+}
+
+extern "C" int icap_rows_gather_add(int dtype, const void* src, int64_t src_ld, const void* base, int64_t base_ld,
+                                    void* dst, int64_t dst_ld, int64_t rows, int64_t cols, int64_t div, int64_t mul,
+                                    int64_t off, void* stream) {
+  ICAP_ARG(src && dst && rows > 0 && cols > 0 && cols % 4 == 0 && div > 0, "icap_rows_gather_add: bad argument");
+  ICAP_ARG(src_ld % 4 == 0 && dst_ld % 4 == 0 && (base == nullptr || base_ld % 4 == 0),
+           "icap_rows_gather_add: leading dimensions must be multiples of 4");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned g = grid_for(rows * cols / 4, 256);
+  if (dtype == ICAP_F32)
+    rows_gather_add_kernel<float><<<g, 256, 0, st>>>((const float*)src, src_ld, (const float*)base, base_ld, (float*)dst,
+                                                     dst_ld, rows, (int)cols, (int)div, (int)mul, (int)off);
+  else
+    rows_gather_add_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)src, src_ld, (const bf16*)base, base_ld, (bf16*)dst,
+                                                    dst_ld, rows, (int)cols, (int)div, (int)mul, (int)off);
+  ICAP_LAUNCH_CHECK("icap_rows_gather_add");
+  return 0;
+}
+
+extern "C" int icap_rows_segsum_add(int dtype, const void* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t nseg,
+                                    int64_t seg_len, int64_t cols, int64_t mul, int64_t off, void* stream) {
+  ICAP_ARG(src && dst && nseg > 0 && seg_len > 0 && cols > 0, "icap_rows_segsum_add: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned g = grid_for(nseg * cols, 256);
+  if (dtype == ICAP_F32)
+    rows_segsum_add_kernel<float><<<g, 256, 0, st>>>((const float*)src, src_ld, (float*)dst, dst_ld, nseg, (int)seg_len,
+                                                     (int)cols, (int)mul, (int)off);
+  else
+    rows_segsum_add_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)src, src_ld, (bf16*)dst, dst_ld, nseg, (int)seg_len,
+                                                    (int)cols, (int)mul, (int)off);
+  ICAP_LAUNCH_CHECK("icap_rows_segsum_add");
   return 0;
 }
 

@@ -244,14 +244,16 @@ class CaptionEngine:
         self._prof_end(ev, 2.0 * M * Nn * K)
 
     def wgrad(self, dy: torch.Tensor, x: torch.Tensor, g_ptr: int, Nout: int, Kin: int, rows: int,
-              ld_dy: Optional[int] = None, dy_ptr: Optional[int] = None, ldg: Optional[int] = None) -> None:
+              ld_dy: Optional[int] = None, dy_ptr: Optional[int] = None, ldg: Optional[int] = None,
+              x_ptr: Optional[int] = None, ldx: Optional[int] = None) -> None:
         """dW[Nout,Kin] += dy[rows,Nout]^T x[rows,Kin]  (fp32, split-K over rows so the grid fills the GPU)."""
         tiles = ((Nout + 127) // 128) * ((Kin + 127) // 128)
         split = max(1, min(32, (148 * 2) // max(1, tiles), (rows + 511) // 512))
         ab = BF16 if self.precision == "bf16" else F32
         ev = self._prof_begin()
         call("icap_gemm", ab, 0, 0, Nout, Kin, rows, dy.data_ptr() if dy_ptr is None else dy_ptr,
-             dy.shape[-1] if ld_dy is None else ld_dy, x.data_ptr(), x.shape[-1], g_ptr, Kin if ldg is None else ldg,
+             dy.shape[-1] if ld_dy is None else ld_dy, x.data_ptr() if x_ptr is None else x_ptr,
+             x.shape[-1] if ldx is None else ldx, g_ptr, Kin if ldg is None else ldg,
              F32, None, 0, None, 0, 1, split, self._s())
         self._prof_end(ev, 2.0 * Nout * Kin * rows)
 
@@ -469,19 +471,21 @@ class CaptionEngine:
         call("icap_copy2d", pos.data_ptr(), F32, Dp, xcat.data_ptr() + Df * xcat.element_size(), self.act, Kc, M, Dp, 0,
              self._s())
         wcat = self._pack_embed_weights()
+        rec = self.tape is not None
+        dwcat = self.new(d, Kc, dtype=torch.float32, zero=True) if rec else None
+        if rec:     # runs LAST in the backward: every embedding wgrad has been accumulated into dwcat by then
+            self.tape.append(lambda: self._unpack_embed_grads(dwcat))
         if cfg.split_image_objects:
-            x = self._encode_split_objects(xcat, wcat, kvalid, rowscale, B, R)
+            x = self._encode_split_objects(xcat, wcat, dwcat, kvalid, B, R)
         else:
             e = self.new(M, d)
             self.gemm(xcat, True, wcat.data_ptr(), Kc, True, M, d, Kc, e)
             x0, mean, rstd, _, _ = self.add_ln(e, None, 1, "encoder.norm", None, 0.0)
             x = x0
-            if self.tape is not None:
+            if rec:
                 def bwd():      # NB: closes over x0 (x is re-bound by the block loop below)
                     ds, _ = self.ln_bwd(x0, e, mean, rstd, "encoder.norm", None, 0.0, 0)
-                    dwcat = self.new(d, Kc, dtype=torch.float32, zero=True)
                     self.wgrad(ds, xcat, dwcat.data_ptr(), d, Kc, M)
-                    self._unpack_embed_grads(dwcat)
                 self.tape.append(bwd)
         for i in range(cfg.encode_num_blocks):
             pre = f"encoder.encoder.{i}"
@@ -495,8 +499,56 @@ class CaptionEngine:
                 x = self.ffn_block(pre + ".feed_forward", x, cfg.encode_hidden_size, None)
         return x, kvalid
 
-    def _encode_split_objects(self, xcat, wcat, kvalid, rowscale, B, R):
-        raise N.IcapError("split_image_objects=True is not built yet in the CUDA path")
+    def _encode_split_objects(self, xcat, wcat, dwcat, kvalid, B, R):
+        """split_image_objects branch (model.py:258-292): every region i becomes the 2-token sequence
+        [whole image (region 0), region i]; embed + LN, one extra `image_encoder` block with causal + key-pad
+        mask, keep token 1, re-add the position embedding, LN again."""
+        cfg = self.cfg
+        assert not cfg.split_position, "split_position + split_image_objects is a shape error in the reference too"
+        M, d, Kc, Df = B * R, cfg.encode_input_size, self._cat_width(), cfg.encode_dim_features
+        H = cfg.encode_num_heads
+        esz = xcat.element_size()
+        rec = self.tape is not None
+        # token 0 of pair (b, i) = region 0 of image b ; token 1 = region i
+        x2 = self.new(2 * M, Kc)
+        call("icap_rows_gather_add", self.act, xcat.data_ptr(), Kc, None, 0, x2.data_ptr(), 2 * Kc, M, Kc, R, R, 0, self._s())
+        call("icap_copy2d", xcat.data_ptr(), self.act, Kc, x2.data_ptr() + Kc * esz, self.act, 2 * Kc, M, Kc, 0, self._s())
+        kvalid2 = self.new(2 * M, dtype=torch.uint8)
+        rowscale2 = self.new(2 * M, dtype=torch.float32)
+        # validity of the pair tokens from the packed position columns (same rule: all-zero position row = padding)
+        pos2 = self.new(2 * M, Kc - Df, dtype=torch.float32)
+        call("icap_copy2d", x2.data_ptr() + Df * esz, self.act, Kc, pos2.data_ptr(), F32, Kc - Df, 2 * M, Kc - Df, 0, self._s())
+        call("icap_region_valid", pos2.data_ptr(), 2 * M, Kc - Df, kvalid2.data_ptr(), rowscale2.data_ptr(), self._s())
+        e2 = self.new(2 * M, d)
+        self.gemm(x2, True, wcat.data_ptr(), Kc, True, 2 * M, d, Kc, e2)
+        y2, mean2, rstd2, _, _ = self.add_ln(e2, None, 1, "encoder.norm", None, 0.0)
+        if rec:
+            def bwd_embed2():
+                ds, _ = self.ln_bwd(y2, e2, mean2, rstd2, "encoder.norm", None, 0.0, 0)
+                self.wgrad(ds, x2, dwcat.data_ptr(), d, Kc, 2 * M)
+            self.tape.append(bwd_embed2)
+        pre = "encoder.image_encoder"
+        z = self.mha_block(pre + ".multihead_attention", y2, y2, M, 2, 2, H, cfg.encode_q_k_dim, cfg.encode_v_dim,
+                           kvalid2, True)
+        z = self.ffn_block(pre + ".feed_forward", z, cfg.encode_hidden_size, rowscale2)
+        # embedded_feature = output[:, 1]; embedded_position = position_embedding(position)[:, 1]  (model.py:290-292)
+        tok1 = self.new(M, d)
+        call("icap_copy2d", z.data_ptr() + d * esz, self.act, 2 * d, tok1.data_ptr(), self.act, d, M, d, 0, self._s())
+        emb_p = self.new(M, d)
+        self.gemm(xcat, True, wcat.data_ptr() + Df * esz, Kc, True, M, d, Kc - Df, emb_p,
+                  a_ptr=xcat.data_ptr() + Df * esz, lda=Kc)
+        x, mean, rstd, _, _ = self.add_ln(tok1, emb_p, M, "encoder.norm", None, 0.0)
+        if rec:
+            def bwd_tail():
+                ds, _ = self.ln_bwd(x, tok1, mean, rstd, "encoder.norm", None, 0.0, 0)
+                # d position-embedding weights (tail columns of the packed matrix)
+                self.wgrad(ds, xcat, dwcat.data_ptr() + Df * 4, d, Kc - Df, M, x_ptr=xcat.data_ptr() + Df * esz, ldx=Kc,
+                           ldg=Kc)
+                dz = self.new(2 * M, d, zero=True)
+                call("icap_copy2d", ds.data_ptr(), self.act, d, dz.data_ptr() + d * esz, self.act, 2 * d, M, d, 0, self._s())
+                self.add_grad(z, dz)
+            self.tape.append(bwd_tail)
+        return x
 
     # ------------------------------------------------------------------ decoder (teacher forced)
     def decode_train(self, inp: torch.Tensor, tok_valid: torch.Tensor, rowscale: torch.Tensor, enc: torch.Tensor,
@@ -532,8 +584,29 @@ class CaptionEngine:
             x = self._move_first_tail(x, enc, B, T, R)
         return x
 
-    def _move_first_tail(self, x, enc, B, T, R):
-        raise N.IcapError("move_first_image_feature=True is not built yet in the CUDA path")
+    def _move_first_tail(self, x, enc, B, T, R, rows_per_image: int = 1):
+        """move_first_image_feature tail (model.py:451-457):
+        LN(Dropout(W2 relu(W1 (x + enc[:, 0]) + b1) + b2) + x) with the decoder-level position_wise / layer_norm."""
+        cfg = self.cfg
+        M, d = x.shape
+        gin = self.new(M, d)
+        # row r belongs to image r // (T * rows_per_image); its first region is row image * R of enc
+        call("icap_rows_gather_add", self.act, enc.data_ptr(), d, x.data_ptr(), d, gin.data_ptr(), d, M, d,
+             T * rows_per_image, R, 0, self._s())
+        y = self.ffn_block("decoder", x, cfg.decode_hidden_size, None, norm="decoder.layer_norm", x_in=gin)
+        if self.tape is not None:
+            def bwd():          # executed right after ffn_block's backward: gin's gradient flows to x and to enc[:, 0]
+                gs = self.gr.pop(id(gin), [])
+                assert len(gs) == 1
+                self.add_grad(x, gs[0])
+                gl = self.gr.setdefault(id(enc), [])
+                if not gl:
+                    gl.append(self.new(enc.shape[0], d, zero=True))
+                call("icap_rows_segsum_add", self.act, gs[0].data_ptr(), d, gl[0].data_ptr(), d, B, T * rows_per_image, d,
+                     R, 0, self._s())
+            # tape runs in reverse: this closure must run AFTER ffn_block's, so insert it BEFORE that one
+            self.tape.insert(len(self.tape) - 1, bwd)
+        return y
 
     # ------------------------------------------------------------------ full passes
     def prepare_inputs(self, feats, pos, captions=None):
@@ -736,7 +809,7 @@ class CaptionEngine:
                 # --- FFN + non-pad row mask (modules.py:202-204)
                 x = self.ffn_block(pre + ".feed_forward", x2, hid, rowscale)
             if cfg.move_first_image_feature:
-                x = self._move_first_tail(x, enc, B, 1, R)
+                x = self._move_first_tail(x, enc, B, 1, R, rows_per_image=k)
             logits = self.new(rows, ldl)
             self.gemm(x, True, self.w("classifer.weight"), d, True, rows, V, d, logits, ldc=ldl, bias=self.p("classifer.bias"))
             if k == 1:

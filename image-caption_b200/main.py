@@ -1,0 +1,136 @@
+"""`python main.py train | evaluation | demo` -- same entry points and arguments as the reference's main.py
+(main.py:25,156,193).  `fire` is not installable offline, so a small fire-compatible argv shim dispatches
+`--beam-size 5` / `--beam_size=5` style flags.  Without the COCO artefacts (data/<MODEL_NAME>/...) the loops run
+on synthetic data of the reference's shapes; metric scoring (pycocoevalcap, Java) is out of scope."""
+import os
+import sys
+import time
+
+import torch
+from torch.utils.data import DataLoader
+
+from core.models import DEVICE, TRANSFORMER
+from core.config import *          # noqa: F401,F403
+from core.dataset import SyntheticCaptionDataset
+from core.utils import save_pickle
+
+MODEL = None
+
+
+def _model():
+    global MODEL
+    if MODEL is None:
+        MODEL = TRANSFORMER()      # the reference builds it at import time (main.py:19-22)
+    return MODEL
+
+
+def _dataset(with_captions, n_images):
+    return SyntheticCaptionDataset(n_images, NUM_OBJECT, ENCODE_DIM_FEATURES, ENCODE_DIM_POSITIONS, MAX_LENGTH + 2,
+                                   _model().num_vocab, with_captions=with_captions)
+
+
+def train(num_images=64, max_iters=None):
+    model = _model()
+    model_dir = os.path.join(OUTPUT_PATH, 'model/')
+    os.makedirs(model_dir, exist_ok=True)
+    loader = DataLoader(_dataset(True, num_images), batch_size=BATCH_SIZE, shuffle=True, drop_last=True)
+    it = 0
+    for epoch in range(1, NUM_EPOCH + 1):
+        print(f'Epoch {epoch}')
+        for features, positions, captions, _ in loader:
+            model.train_step(features, positions, captions)
+            it += 1
+            if it % 100 == 0 or max_iters:
+                print(f'  iter {it} loss {float(model.last_loss):.4f}')
+            if max_iters and it >= max_iters:
+                break
+        model.save(path=os.path.join(model_dir, f'model_{epoch}.pt'))
+        if max_iters and it >= max_iters:
+            break
+
+
+def evaluation(split='test', epoch=90, beam_size=None, num_images=64):
+    model = _model()
+    model_path = os.path.join(OUTPUT_PATH, f'model/model_{epoch}.pt')
+    if os.path.exists(model_path):
+        model.load(path=model_path)
+    else:
+        print(f'[evaluation] {model_path} not found: using the current (random-init) weights')
+        model.model.eval()
+    ds = _dataset(False, num_images)
+    loader = DataLoader(ds, batch_size=BATCH_SIZE, shuffle=False)
+    captions_out = [''] * ds.len_image
+    t0 = time.time()
+    for features, positions, idxs in loader:
+        captions, _ = model.generate_caption(object_features=features, position_features=positions, beam_size=beam_size)
+        for i, idx in enumerate(idxs):
+            captions_out[int(idx)] = captions[i]
+    dt = time.time() - t0
+    target_dir = os.path.join(DATA_PATH, f'{split}/{OUTPUT_NAME}/')
+    os.makedirs(target_dir, exist_ok=True)
+    save_pickle(captions_out, os.path.join(target_dir, f'{split}.candidate.captions.pkl'))
+    print(f'[evaluation] {len(captions_out)} captions in {dt:.2f}s ({len(captions_out) / dt:.1f} captions/s); '
+          f'BLEU/METEOR/CIDEr scoring needs pycocoevalcap + Java and is out of scope')
+    return captions_out
+
+
+def demo(image_path=None, beam_size=None, epoch=90, save_img=False, max_obj=False, features_path=None):
+    """The reference runs YOLOv5 + ResNet-101 on `image_path` first (main.py:195-197); offline, pass
+    `--features-path file.pt` holding {'features': [R,2048], 'positions': [R,84]} or omit it for a synthetic image."""
+    model = _model()
+    start = time.time()
+    if features_path:
+        blob = torch.load(features_path)
+        feature, position = blob['features'].unsqueeze(0), blob['positions'].unsqueeze(0)
+    else:
+        ds = _dataset(False, 1)
+        feature, position = ds.features[:1], ds.positions[:1]
+    model_path = os.path.join(OUTPUT_PATH, f'model/model_{epoch}.pt')
+    if os.path.exists(model_path):
+        model.load(path=model_path)
+    else:
+        model.model.eval()
+    caption, attention_list = model.generate_caption(object_features=feature, position_features=position,
+                                                     beam_size=beam_size)
+    print('Generated Caption:', caption[0])
+    print('Spending Time:', time.time() - start)
+    return caption[0]
+
+
+def _fire(argv):
+    """fire.Fire() subset: `cmd --flag value`, `--flag=value`, dashes or underscores, ints/None/bools parsed."""
+    cmds = {'train': train, 'evaluation': evaluation, 'demo': demo}
+    if not argv or argv[0] not in cmds:
+        print('usage: main.py {train|evaluation|demo} [--flag value ...]')
+        return 2
+
+    def parse(v):
+        if v in ('None', 'none'):
+            return None
+        if v in ('True', 'False'):
+            return v == 'True'
+        try:
+            return int(v)
+        except ValueError:
+            return v
+
+    kwargs, i, args = {}, 1, argv
+    while i < len(args):
+        a = args[i]
+        assert a.startswith('--'), f'unexpected argument {a}'
+        if '=' in a:
+            k, v = a[2:].split('=', 1)
+            i += 1
+        elif i + 1 < len(args) and not args[i + 1].startswith('--'):
+            k, v = a[2:], args[i + 1]
+            i += 2
+        else:
+            k, v = a[2:], 'True'
+            i += 1
+        kwargs[k.replace('-', '_')] = parse(v)
+    cmds[argv[0]](**kwargs)
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(_fire(sys.argv[1:]))

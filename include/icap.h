@@ -115,6 +115,15 @@ int icap_mha_decode(int dtype, int64_t rows, int64_t H, int64_t Lk, int64_t dk, 
 /* dst[r][c] (+)= convert(src[r][c]) : operand packing / dtype casts / gradient unpacking. */
 int icap_copy2d(const void* src, int src_dtype, int64_t src_ld, void* dst, int dst_dtype, int64_t dst_ld, int64_t rows,
                 int64_t cols, int accumulate, void* stream);
+/* dst[r,:] = (base ? base[r,:] : 0) + src[(r / div) * mul + off, :]  -- row broadcast: the "whole image" token
+ * repeated per region (split_image_objects, model.py:262-271) and `decode_output + encode_output[:, 0]`
+ * (move_first_image_feature, model.py:452-453).  icap_rows_segsum_add is its adjoint:
+ * dst[s * mul + off, :] += sum_{t < seg_len} src[s * seg_len + t, :]. */
+int icap_rows_gather_add(int dtype, const void* src, int64_t src_ld, const void* base, int64_t base_ld, void* dst,
+                         int64_t dst_ld, int64_t rows, int64_t cols, int64_t div, int64_t mul, int64_t off,
+                         void* stream);
+int icap_rows_segsum_add(int dtype, const void* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t nseg,
+                         int64_t seg_len, int64_t cols, int64_t mul, int64_t off, void* stream);
 /* kvalid[row] = rowscale[row] = any(pos[row,:] != 0) : get_attention_key_pad_mask / get_non_pad_mask,
  * model.py:202-209,354-358. */
 int icap_region_valid(const float* pos, int64_t M, int64_t Dp, uint8_t* kvalid, float* rowscale, void* stream);

@@ -126,6 +126,57 @@ def test_golden_bf16_within_tolerance():
     assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < 2e-2
 
 
+@pytest.mark.parametrize("name", ["tiny_cfgpy", "tiny_variants"])
+def test_golden_variants_fp32(name):
+    """config.py-default flavour (encode_mask + split_image_objects, 8 heads of dim 4) and the
+    split_position + move_first_image_feature + FocalLoss flavour, against the reference's own outputs."""
+    g = load_gold(name)
+    m = build(g["ctor"], g["state_dict"], "fp32")
+    assert rel(m.logits(g["features"], g["positions"], g["captions"]), g["logits"]) < 1e-4
+    loss = m(g["features"], g["positions"], g["captions"])["loss"]
+    assert abs(float(loss.detach()) - float(g["loss"])) / float(g["loss"]) < 1e-5
+    loss.backward()
+    for pname, q in m.named_parameters():
+        ref = g["grads"][pname]
+        err = float((q.grad.cpu() - ref).norm() / (ref.norm() + 1e-12))
+        assert err < 5e-4, (pname, err)
+    ids, att = m.generate_caption_vector(g["features"], g["positions"])
+    assert not ids_match_except_near_ties(ids, g["greedy_ids"], m.last_gaps)
+    for k in (2, 3):
+        out = m.beam_search(g["features"], g["positions"], beam_size=k)
+        assert not ids_match_except_near_ties(out, g[f"beam{k}_ids"], m.last_gaps, tol=1e-6)
+    # fused train steps (explicit backward + flat Adam, focal factor folded into Adam's gradient scale)
+    m2 = build(g["ctor"], g["state_dict"], "fp32")
+    losses = [float(m2.train_step_fused(f, p, c, lr=5e-4, train_mode=False))
+              for f, p, c in ((g["features"], g["positions"], g["captions"]),
+                              (g["features2"], g["positions2"], g["captions2"]))]
+    np.testing.assert_allclose(losses, g["adam_losses"].numpy(), rtol=2e-5)
+    for k, v in m2.state_dict().items():
+        assert torch.allclose(v.cpu(), g["state_dict_after_2_steps"][k], rtol=1e-3, atol=2e-5), k
+
+
+def test_config1_shapes_bf16_and_fp32_vs_oracle():
+    """BASELINE configs[0]: core/config.py defaults (d256, 32 heads of dim 8, FFN 256, 2+5 blocks, encode_mask,
+    split_image_objects, max_length 51), batch 8 of 36x2048 regions, greedy decode."""
+    kw = dict(num_vocab=10000, max_length=51, encode_dim_positions=84, encode_dim_features=2048, output_name="x",
+              dropout=0.0, encode_mask=True, split_image_objects=True, encode_input_size=256, encode_q_k_dim=256,
+              encode_v_dim=256, encode_hidden_size=256, encode_num_blocks=2, encode_num_heads=32, dim_word_embedding=256,
+              decode_input_size=256, decode_q_k_dim=256, decode_v_dim=256, decode_hidden_size=256, decode_num_blocks=5,
+              decode_num_heads=32)
+    cfg = O.OracleConfig(**kw)
+    sd = O.init_state_dict(cfg, seed=0)
+    f, p, c = O.synthetic_batch(8, 36, 2048, 84, 51, 10000, seed=1234)
+    ref_logits = O.logits_forward(sd, cfg, f, p, c)
+    m = build(kw, sd, "fp32")
+    assert rel(m.logits(f, p, c), ref_logits) < 1e-4
+    ref_ids, _, ref_gaps = O.generate_caption_vector(sd, cfg, f, p, return_gaps=True)
+    ids, att = m.generate_caption_vector(f, p)
+    assert ids.shape == (8, 52) and len(att) == 50 and att[0].shape == (8, 36)
+    assert not ids_match_except_near_ties(ids, ref_ids, m.last_gaps)
+    mb = build(kw, sd, "bf16")
+    assert rel(mb.logits(f, p, c), ref_logits) < 2e-2
+
+
 # ------------------------------------------------------------------------------------------ oracle, model A shapes
 def model_a_cfg(**over):
     kw = dict(num_vocab=10000, max_length=22, encode_dim_positions=84, encode_dim_features=2048, output_name="x",
