@@ -333,16 +333,30 @@ mha_decode_kernel(int rows, int H, int Lk, int dk, int dv, const T* __restrict__
     const int j = jj * 32 + lane;
     if (attn_mean && j < Lk) atomicAdd(attn_mean + (int64_t)row * Lk + j, p[jj] / (float)H);
   }
-  for (int c0 = lane; c0 < dv; c0 += 32) {
-    float acc = 0.f;
-    for (int j = 0; j < Lk; ++j) {
-      const float pj = __shfl_sync(0xffffffffu, p[j >> 5], j & 31);
-      int64_t vrow;
-      if (self_mode) vrow = (int64_t)(slot ? slot[(int64_t)row * slot_ld + j] : row) * kv_rows_per_seq + j;
-      else vrow = (int64_t)seq * kv_rows_per_seq + j;
-      if (pj != 0.f) acc = fmaf(pj, to_f32(vc[vrow * ldv + h * dv + c0]), acc);
+  // P.V : every lane takes part in the probability broadcast (dv may be < 32), lanes own columns lane + 32*i
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int j = 0; j < Lk; ++j) {
+    float pj = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const float t = __shfl_sync(0xffffffffu, p[jj], j & 31);
+      if ((j >> 5) == jj) pj = t;
     }
-    o[(int64_t)row * ldo + h * dv + c0] = from_f32<T>(acc);
+    if (pj == 0.f) continue;                      // warp-uniform
+    int64_t vrow;
+    if (self_mode) vrow = (int64_t)(slot ? slot[(int64_t)row * slot_ld + j] : row) * kv_rows_per_seq + j;
+    else vrow = (int64_t)seq * kv_rows_per_seq + j;
+    const T* vp = vc + vrow * ldv + h * dv;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c0 = lane + 32 * i;
+      if (c0 < dv) acc[i] = fmaf(pj, to_f32(vp[c0]), acc[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c0 = lane + 32 * i;
+    if (c0 < dv) o[(int64_t)row * ldo + h * dv + c0] = from_f32<T>(acc[i]);
   }
 }
 
@@ -430,6 +444,7 @@ extern "C" int icap_mha_decode(int dtype, int64_t rows, int64_t H, int64_t Lk, i
                                int64_t rows_per_image, float* attn_mean, void* stream) {
   if (int rc = check_dims("icap_mha_decode", rows, H, 1, Lk, dk, dv)) return rc;
   ICAP_ARG(Lk <= 128, "icap_mha_decode: at most 128 keys per query (got %lld)", (long long)Lk);
+  ICAP_ARG(dv <= 128, "icap_mha_decode: head dim of V must be <= 128 (got %lld)", (long long)dv);
   ICAP_ARG(slot == nullptr || tokens != nullptr, "icap_mha_decode: a slot table needs the token buffer (self mode)");
   ICAP_ARG(rows_per_image >= 1, "icap_mha_decode: rows_per_image must be >= 1");
   cudaStream_t st = (cudaStream_t)stream;

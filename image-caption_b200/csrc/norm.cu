@@ -79,119 +79,136 @@ add_ln_fwd_kernel(int M, int d, TA* __restrict__ a, const TR* __restrict__ res, 
 }
 
 // Backward.  dy = dy1 (+ dy2);  g = dy * rowscale
-//   dgamma += sum_rows g * xhat ; dbeta += sum_rows g
 //   ds = rstd * (g*gamma - mean(g*gamma) - xhat * mean(g*gamma*xhat))      (-> residual branch)
 //   da = dropout mask(ds) / (1-p)                                          (-> GEMM branch; == ds if p = 0)
-//   dbias2 += sum_rows da   (optional: bias of the GEMM that produced a)
-// Persistent over rows: each warp keeps per-lane column partials in registers, one smem + atomic
-// reduction per block at the end.
+//   dgamma += sum_rows g * xhat ; dbeta += sum_rows g ; dbias2 += sum_rows da
+// Two kernels, both streaming at high occupancy: a row kernel (one warp per row, ~60 registers) for ds / da,
+// and a column kernel (thread = 2 adjacent columns, rows split over grid.y) for the three column sums.  (A single
+// fused kernel needed 180 registers for the per-lane column partials -> 12 % occupancy, 1/5 of HBM speed: ncu r1.)
 template <int NIT, typename T>
 __global__ void __launch_bounds__(256)
-add_ln_bwd_kernel(int M, int d, const T* __restrict__ dy1, const T* __restrict__ dy2, const T* __restrict__ s,
-                  const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
-                  const float* __restrict__ gamma, const float* __restrict__ rowscale, T* __restrict__ ds,
-                  T* __restrict__ da, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                  float* __restrict__ dbias2, float p_drop, uint32_t thresh, uint64_t seed,
-                  const int* __restrict__ seed_dev) {
+add_ln_bwd_rows_kernel(int M, int d, const T* __restrict__ dy1, const T* __restrict__ dy2, const T* __restrict__ s,
+                       const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                       const float* __restrict__ gamma, const float* __restrict__ rowscale, T* __restrict__ ds,
+                       T* __restrict__ da, float p_drop, uint32_t thresh, uint64_t seed,
+                       const int* __restrict__ seed_dev) {
   if (seed_dev) seed += (uint64_t)(*seed_dev) * 0x9E3779B97F4A7C15ull;
-  extern __shared__ float red[];   // [3][d]
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
   const int nvec = d >> 2;
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
-  float pg[NIT][4], pb[NIT][4], pc[NIT][4];
-#pragma unroll
-  for (int it = 0; it < NIT; ++it)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { pg[it][j] = 0.f; pb[it][j] = 0.f; pc[it][j] = 0.f; }
-  float gam[NIT][4];
-#pragma unroll
-  for (int it = 0; it < NIT; ++it) {
-    const int vi = it * 32 + lane;
-    if (vi < nvec) load4(gamma + vi * 4, gam[it]);
-  }
-
-  for (int row = blockIdx.x * wpb + wib; row < M; row += gridDim.x * wpb) {
-    const float mean = mean_in[row], rstd = rstd_in[row];
-    const float rs = rowscale ? rowscale[row] : 1.f;
-    float xh[NIT][4], gg[NIT][4];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-      const int vi = it * 32 + lane;
-      if (vi < nvec) {
-        float g[4], x[4];
-        load4(dy1 + (int64_t)row * d + vi * 4, g);
-        if (dy2) {
-          float g2[4];
-          load4(dy2 + (int64_t)row * d + vi * 4, g2);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) g[j] += g2[j];
-        }
-        load4(s + (int64_t)row * d + vi * 4, x);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float gr = g[j] * rs;
-          const float xhat = (x[j] - mean) * rstd;
-          pg[it][j] += gr * xhat;
-          pb[it][j] += gr;
-          const float gx = gr * gam[it][j];
-          xh[it][j] = xhat;
-          gg[it][j] = gx;
-          s1 += gx;
-          s2 += gx * xhat;
-        }
-      }
-    }
-    s1 = warp_sum(s1) / (float)d;
-    s2 = warp_sum(s2) / (float)d;
-#pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-      const int vi = it * 32 + lane;
-      if (vi < nvec) {
-        float o[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = rstd * (gg[it][j] - s1 - xh[it][j] * s2);
-        if (ds) store4(ds + (int64_t)row * d + vi * 4, o);
-        if (da) {
-          if (p_drop > 0.f) {
-            uint32_t keep = dropout_keep4(seed, (uint64_t)row * nvec + vi, thresh);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = (keep >> j) & 1 ? o[j] * keep_scale : 0.f;
-          }
-          store4(da + (int64_t)row * d + vi * 4, o);
-        }
-        if (dbias2) {
-          if (!da && p_drop > 0.f) {
-            uint32_t keep = dropout_keep4(seed, (uint64_t)row * nvec + vi, thresh);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = (keep >> j) & 1 ? o[j] * keep_scale : 0.f;
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) pc[it][j] += o[j];
-        }
-      }
-    }
-  }
-  // block reduction of the column partials
-  for (int i = threadIdx.x; i < 3 * d; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
+  const float mean = mean_in[row], rstd = rstd_in[row];
+  const float rs = rowscale ? rowscale[row] : 1.f;
+  float xh[NIT][4], gg[NIT][4];
+  float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int it = 0; it < NIT; ++it) {
     const int vi = it * 32 + lane;
     if (vi < nvec) {
+      float g[4], x[4], gam[4];
+      load4(dy1 + (int64_t)row * d + vi * 4, g);
+      if (dy2) {
+        float g2[4];
+        load4(dy2 + (int64_t)row * d + vi * 4, g2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) g[j] += g2[j];
+      }
+      load4(s + (int64_t)row * d + vi * 4, x);
+      load4(gamma + vi * 4, gam);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        atomicAdd(&red[vi * 4 + j], pg[it][j]);
-        atomicAdd(&red[d + vi * 4 + j], pb[it][j]);
-        if (dbias2) atomicAdd(&red[2 * d + vi * 4 + j], pc[it][j]);
+        const float xhat = (x[j] - mean) * rstd;
+        const float gx = g[j] * rs * gam[j];
+        xh[it][j] = xhat;
+        gg[it][j] = gx;
+        s1 += gx;
+        s2 += gx * xhat;
       }
     }
   }
+  s1 = warp_sum(s1) / (float)d;
+  s2 = warp_sum(s2) / (float)d;
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int vi = it * 32 + lane;
+    if (vi < nvec) {
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = rstd * (gg[it][j] - s1 - xh[it][j] * s2);
+      if (ds) store4(ds + (int64_t)row * d + vi * 4, o);
+      if (da) {
+        if (p_drop > 0.f) {
+          uint32_t keep = dropout_keep4(seed, (uint64_t)row * nvec + vi, thresh);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = (keep >> j) & 1 ? o[j] * keep_scale : 0.f;
+        }
+        store4(da + (int64_t)row * d + vi * 4, o);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void load2(const float* p, float (&v)[2]) {
+  float2 t = *reinterpret_cast<const float2*>(p);
+  v[0] = t.x; v[1] = t.y;
+}
+__device__ __forceinline__ void load2(const bf16* p, float (&v)[2]) {
+  __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(p);
+  v[0] = __low2float(t); v[1] = __high2float(t);
+}
+
+// block (32, 8): 64 columns x 8 row lanes; grid (d/64, row splits)
+template <typename T>
+__global__ void __launch_bounds__(256)
+add_ln_bwd_cols_kernel(int M, int d, const T* __restrict__ dy1, const T* __restrict__ dy2, const T* __restrict__ s,
+                       const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                       const float* __restrict__ rowscale, const T* __restrict__ dab, float* __restrict__ dgamma,
+                       float* __restrict__ dbeta, float* __restrict__ dbias2, int rows_per_block) {
+  __shared__ float red[3][8][64];
+  const int c = blockIdx.x * 64 + threadIdx.x * 2;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float ag[2] = {0.f, 0.f}, ab[2] = {0.f, 0.f}, ac[2] = {0.f, 0.f};
+  if (c < d) {
+#pragma unroll 4
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      float g[2], x[2];
+      load2(dy1 + (int64_t)r * d + c, g);
+      if (dy2) {
+        float g2[2];
+        load2(dy2 + (int64_t)r * d + c, g2);
+        g[0] += g2[0]; g[1] += g2[1];
+      }
+      load2(s + (int64_t)r * d + c, x);
+      const float mean = mean_in[r], rstd = rstd_in[r], rs = rowscale ? rowscale[r] : 1.f;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float gr = g[j] * rs;
+        ag[j] += gr * (x[j] - mean) * rstd;
+        ab[j] += gr;
+      }
+      if (dbias2) {
+        float a[2];
+        load2(dab + (int64_t)r * d + c, a);
+        ac[0] += a[0]; ac[1] += a[1];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    red[0][threadIdx.y][threadIdx.x * 2 + j] = ag[j];
+    red[1][threadIdx.y][threadIdx.x * 2 + j] = ab[j];
+    red[2][threadIdx.y][threadIdx.x * 2 + j] = ac[j];
+  }
   __syncthreads();
-  for (int i = threadIdx.x; i < d; i += blockDim.x) {
-    if (dgamma) atomicAdd(dgamma + i, red[i]);
-    if (dbeta) atomicAdd(dbeta + i, red[d + i]);
-    if (dbias2) atomicAdd(dbias2 + i, red[2 * d + i]);
+  const int t = threadIdx.y * 32 + threadIdx.x;
+  if (t < 192) {
+    const int which = t / 64, col = t % 64;
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc += red[which][i][col];
+    float* dst = which == 0 ? dgamma : which == 1 ? dbeta : dbias2;
+    if (dst && blockIdx.x * 64 + col < d) atomicAdd(dst + blockIdx.x * 64 + col, acc);
   }
 }
 
@@ -238,20 +255,31 @@ extern "C" int icap_add_ln_bwd(int act_dtype, int64_t M, int64_t d, const void* 
            MAX_IT * 128);
   ICAP_ARG(M > 0 && dy1 && s && mean && rstd && gamma, "icap_add_ln_bwd: null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  int64_t blocks = ceil_div64(M, 8);
-  if (blocks > 148 * 2) blocks = 148 * 2;   // few blocks: the column reductions end in one global atomic per block
   const uint32_t th = dropout_threshold(p_drop);
-  size_t smem = 3 * d * sizeof(float);
+  const unsigned row_blocks = (unsigned)ceil_div64(M, 8);
+  const int64_t col_blocks = ceil_div64(d, 64);
+  int64_t row_splits = ceil_div64(148 * 4, col_blocks);
+  if (row_splits > ceil_div64(M, 32)) row_splits = ceil_div64(M, 32);
+  const int rows_per_block = (int)ceil_div64(M, row_splits);
+  dim3 cgrid((unsigned)col_blocks, (unsigned)ceil_div64(M, rows_per_block)), cblock(32, 8);
+  const void* dab = da ? da : ds;       // dbias2 sums the GEMM-branch gradient
+  ICAP_ARG(dbias2 == nullptr || dab != nullptr, "icap_add_ln_bwd: dbias2 needs ds or da");
 #define GOB(NIT, T)                                                                                               \
-  add_ln_bwd_kernel<NIT, T><<<(unsigned)blocks, 256, smem, st>>>(                                                 \
-      (int)M, (int)d, (const T*)dy1, (const T*)dy2, (const T*)s, mean, rstd, gamma, rowscale, (T*)ds, (T*)da,     \
-      dgamma, dbeta, dbias2, p_drop, th, seed, seed_dev)
+  add_ln_bwd_rows_kernel<NIT, T><<<row_blocks, 256, 0, st>>>((int)M, (int)d, (const T*)dy1, (const T*)dy2,        \
+                                                             (const T*)s, mean, rstd, gamma, rowscale, (T*)ds,   \
+                                                             (T*)da, p_drop, th, seed, seed_dev)
 #define GOBT(T)                                                                                                   \
   do {                                                                                                            \
-    if (d <= 128) GOB(1, T);                                                                                      \
-    else if (d <= 256) GOB(2, T);                                                                                 \
-    else if (d <= 512) GOB(4, T);                                                                                 \
-    else GOB(8, T);                                                                                               \
+    if (ds || da) {                                                                                               \
+      if (d <= 128) GOB(1, T);                                                                                    \
+      else if (d <= 256) GOB(2, T);                                                                               \
+      else if (d <= 512) GOB(4, T);                                                                               \
+      else GOB(8, T);                                                                                             \
+    }                                                                                                             \
+    if (dgamma || dbeta || dbias2)                                                                                \
+      add_ln_bwd_cols_kernel<T><<<cgrid, cblock, 0, st>>>((int)M, (int)d, (const T*)dy1, (const T*)dy2,           \
+                                                          (const T*)s, mean, rstd, rowscale, (const T*)dab,      \
+                                                          dgamma, dbeta, dbias2, rows_per_block);                 \
   } while (0)
   if (act_dtype == ICAP_F32) GOBT(float);
   else GOBT(bf16);
