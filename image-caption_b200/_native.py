@@ -18,6 +18,7 @@ P, I, L, F, U = c_void_p, c_int, c_int64, c_float, c_uint64
 SIGNATURES = {
     "icap_version": [],
     "icap_sm_check": [I],
+    "icap_set_pdl": [I],
     "icap_gemm": [I, I, I, L, L, L, P, L, P, L, P, L, I, P, I, P, L, I, I, P],
     "icap_mha_fwd": [I, L, L, L, L, L, L, P, L, P, L, P, L, P, L, P, I, F, U, P, P, P],
     "icap_mha_bwd": [I, L, L, L, L, L, L, P, L, P, L, P, L, P, L, P, L, P, L, P, L, P, I, F, U, P, P],

@@ -1,15 +1,21 @@
 // bf16 tensor-core GEMM for sm_100a: TMA (cp.async.bulk.tensor) -> 128B-swizzled shared memory ->
-// tcgen05.mma (cta_group::1, kind::f16, 128x128x16) with the fp32 accumulator in TMEM ->
-// tcgen05.ld epilogue (bias / ReLU / ReLU-mask / accumulate / split-K reduction).
+// tcgen05.mma (cta_group::1, kind::f16, 128 x BN x 16, BN = 128 or 256) with fp32 accumulators in TMEM ->
+// tcgen05.ld epilogue (bias / ReLU / ReLU-mask / accumulate / split-K reduction) -> swizzled smem -> TMA store.
 //
 //   C[M,N] (+)= op(A)[M,K] . op(B)[K,N]
 //
 // Same operand conventions as gemm_simt.cu (a_kmajor / b_kmajor); MN-major operands are fed to the
 // tensor core directly through the UMMA descriptor major bits, so dgrad / wgrad need no transposes.
 //
-// CTA = 192 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = epilogue (each owns the TMEM lane quarter warp_id % 4).  3-stage 32 KB ring so two
-// CTAs are resident per SM: one CTA's epilogue overlaps the other's main loop.
+// PERSISTENT, warp-specialised: grid = min(#tiles, #SMs), one CTA per SM (all of TMEM, ~225 KB smem).
+//   warp 0      : TMA producer (one lane), 4-stage (BN=256) / 6-stage (BN=128) ring of 64-wide k-blocks
+//   warp 1      : TMEM allocator + single-thread MMA issuer; TWO accumulator stages in TMEM, so the
+//                 main loop of tile i+1 runs while the epilogue warps drain tile i
+//   warps 2..5  : epilogue; each owns the TMEM lane quarter (warp_id % 4) and a double-buffered 2 x 4 KB
+//                 staging slab: TMEM -> registers -> swizzled smem -> TMA store / TMA reduce-add
+// The GEMMs of this model are small (2-20 GFLOP, K = 512 mostly): per-CTA setup (barrier init, TMEM
+// allocation, descriptor prefetch) is paid once per launch instead of once per tile, and the kernel is
+// PDL-aware (griddepcontrol) so that setup can overlap the tail of the previous kernel in the stream.
 //
 // Replaces the reference's nn.Linear / torch.matmul calls (modules.py:72-77,86,113-116;
 // model.py:93,295-306,433) in bf16 mode.
@@ -19,11 +25,21 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3, UMMA_K = 16;
-constexpr int TILE_BYTES = BM * BK * 2;          // 16 KB per operand per stage
-constexpr int TMEM_COLS = 128;
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+constexpr int A_TILE_BYTES = BM * BK * 2;        // 16 KB per stage
 constexpr int NTHREADS = 192;
-constexpr int SMEM_BYTES = STAGES * 2 * TILE_BYTES + 1024 /*align slack*/ + 128 /*barriers*/;
+constexpr int EPI_WARPS = 4;
+constexpr int EPI_BOX_BYTES = 4096;              // 32 rows x 128 B: one TMA store box
+constexpr int EPI_BYTES = EPI_WARPS * 2 * EPI_BOX_BYTES;
+
+template <int BN> struct Cfg {
+  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;       // two accumulator stages
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/ + 512 /*bias staging*/ +
+                                    1024 /*align slack*/;
+};
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -127,41 +143,82 @@ template <> struct OutVec<bf16> {
   }
 };
 
-template <bool A_KMAJOR, bool B_KMAJOR, typename TO>
-__global__ void __launch_bounds__(NTHREADS, 2)
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// 32 consecutive elements of the ReLU-mask operand (aux) of one row, as raw 16-byte words
+template <typename TO> struct AuxRow { uint4 w[32 * sizeof(TO) / 16]; };
+template <typename TO>
+__device__ __forceinline__ void aux_load(AuxRow<TO>& a, const TO* __restrict__ p, bool vec, int ncols) {
+  constexpr int NW = 32 * sizeof(TO) / 16, EPW = 16 / sizeof(TO);
+  if (vec) {
+#pragma unroll
+    for (int t = 0; t < NW; ++t) a.w[t] = __ldg(reinterpret_cast<const uint4*>(p) + t);
+  } else {
+    TO* e = reinterpret_cast<TO*>(a.w);
+#pragma unroll
+    for (int j = 0; j < NW * EPW; ++j) e[j] = j < ncols ? p[j] : from_f32<TO>(0.f);
+  }
+}
+template <typename TO>
+__device__ __forceinline__ void aux_mask(const AuxRow<TO>& a, float (&v)[32]) {
+  const TO* e = reinterpret_cast<const TO*>(a.w);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) if (!(to_f32(e[j]) > 0.f)) v[j] = 0.f;
+}
+
+struct GemmArgs {
+  int M, N, K;
+  void* C;
+  int64_t ldc;
+  const float* bias;
+  int epi;
+  const void* aux;
+  int64_t ldaux;
+  int accumulate;      // 0 store, 1 C += (load/add/store or TMA reduce), 2 atomics (split-K on the direct path)
+  int kb_per_split, splits, tiles_m, tiles_n;
+  int vec_ok, store_mode;   // store_mode: 0 direct global stores, 1 TMA store, 2 TMA reduce-add
+};
+
+template <int BN, bool A_KMAJOR, bool B_KMAJOR, typename TO>
+__global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmX, int M, int N, int K,
-               TO* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int epi, const TO* __restrict__ aux,
-               int64_t ldaux, int accumulate, int kb_per_split, int vec_ok, int store_mode) {
+               const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
+  using CF = Cfg<BN>;
+  constexpr int STAGES = CF::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sA = smem_base, sB = smem_base + STAGES * TILE_BYTES;
-  const uint32_t bars = sB + STAGES * TILE_BYTES;        // full[S], empty[S], tmem_full, tmem slot
+  const uint32_t sA = smem_base, sB = sA + STAGES * A_TILE_BYTES, sE = sB + STAGES * CF::B_TILE_BYTES;
+  const uint32_t bars = sE + EPI_BYTES;                  // full[S], empty[S], tfull[2], tempty[2], tmem slot
   const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES, tfull_bar = bars + 16 * STAGES;
-  const uint32_t slot_addr = tfull_bar + 8;
-  const uint32_t aux_bar = tfull_bar + 16;                // 4 x 8 B: one per epilogue warp (aux tile loads)
-  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen_base + (slot_addr - smem_base));
+  const uint32_t tempty_bar = tfull_bar + 16, slot_addr = tempty_bar + 16;
+  const uint32_t sBias = bars + 256;                     // 4 x 128 B: one 32-float bias row per epilogue warp
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + (slot_addr - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int nkb_total = (K + BK - 1) / BK;
-  const int kb0 = blockIdx.z * kb_per_split;
-  const int nkb = min(kb_per_split, nkb_total - kb0);
+  const int M = g.M, N = g.N;
+  const int nkb_total = (g.K + BK - 1) / BK;
+  const int total_tiles = g.tiles_m * g.tiles_n * g.splits;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (g.store_mode) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(full_bar + 8 * i, 1);
       mbar_init(empty_bar + 8 * i, 1);
     }
-    mbar_init(tfull_bar, 1);
-    for (int i = 0; i < 4; ++i) mbar_init(aux_bar + 8 * i, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar + 8 * i, 1);
+      mbar_init(tempty_bar + 8 * i, EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_addr), "n"(TMEM_COLS)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_addr), "n"(CF::TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -169,25 +226,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();        // everything above overlaps the previous kernel's tail when launched with PDL
 
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------------------ TMA producer
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES, ph = (i / STAGES) & 1;
-        mbar_wait(empty_bar + 8 * s, ph ^ 1);
-        mbar_expect_tx(full_bar + 8 * s, 2 * TILE_BYTES);
-        const int k0 = (kb0 + i) * BK;
-        const uint32_t dA = sA + s * TILE_BYTES, dB = sB + s * TILE_BYTES;
-        if (A_KMAJOR) tma_load_2d(dA, &tmA, k0, m0, full_bar + 8 * s);           // box {64 k, 128 m}
-        else {                                                                    // 2 boxes {64 m, 64 k}
-          tma_load_2d(dA, &tmA, m0, k0, full_bar + 8 * s);
-          tma_load_2d(dA + TILE_BYTES / 2, &tmA, m0 + 64, k0, full_bar + 8 * s);
-        }
-        if (B_KMAJOR) tma_load_2d(dB, &tmB, k0, n0, full_bar + 8 * s);
-        else {
-          tma_load_2d(dB, &tmB, n0, k0, full_bar + 8 * s);
-          tma_load_2d(dB + TILE_BYTES / 2, &tmB, n0 + 64, k0, full_bar + 8 * s);
+      int s = 0, ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n0 = (tile % g.tiles_n) * BN, m0 = ((tile / g.tiles_n) % g.tiles_m) * BM;
+        const int kb0 = (tile / (g.tiles_n * g.tiles_m)) * g.kb_per_split;
+        const int nkb = min(g.kb_per_split, nkb_total - kb0);
+        for (int i = 0; i < nkb; ++i) {
+          mbar_wait(empty_bar + 8 * s, ph ^ 1);
+          mbar_expect_tx(full_bar + 8 * s, CF::STAGE_BYTES);
+          const int k0 = (kb0 + i) * BK;
+          const uint32_t dA = sA + s * A_TILE_BYTES, dB = sB + s * CF::B_TILE_BYTES;
+          if (A_KMAJOR) tma_load_2d(dA, &tmA, k0, m0, full_bar + 8 * s);          // box {64 k, 128 m}
+          else {                                                                   // 2 boxes {64 m, 64 k}
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(dA + j * 8192, &tmA, m0 + 64 * j, k0, full_bar + 8 * s);
+          }
+          if (B_KMAJOR) tma_load_2d(dB, &tmB, k0, n0, full_bar + 8 * s);          // box {64 k, BN n}
+          else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(dB + j * 8192, &tmB, n0 + 64 * j, k0, full_bar + 8 * s);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -197,174 +261,171 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // instruction descriptor: D=f32, A=B=bf16, majors, N>>3, M>>4
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_KMAJOR ? 0u : 1u) << 15) |
                              ((B_KMAJOR ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES, ph = (i / STAGES) & 1;
-        mbar_wait(full_bar + 8 * s, ph);
+      int s = 0, ph = 0, it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int kb0 = (tile / (g.tiles_n * g.tiles_m)) * g.kb_per_split;
+        const int nkb = min(g.kb_per_split, nkb_total - kb0);
+        const int as = it & 1, aph = (it >> 1) & 1;
+        mbar_wait(tempty_bar + 8 * as, aph ^ 1);          // epilogue has drained this accumulator stage
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t aS = sA + s * TILE_BYTES, bS = sB + s * TILE_BYTES;
+        const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
+        for (int i = 0; i < nkb; ++i) {
+          mbar_wait(full_bar + 8 * s, ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t aS = sA + s * A_TILE_BYTES, bS = sB + s * CF::B_TILE_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // K-major : 8-row groups 1024 B apart (SBO), +32 B per 16-element k step inside the swizzle atom
-          // MN-major: 64-element MN atoms 8192 B apart (LBO), 8-k groups 1024 B apart (SBO), +2048 B per k step
-          const uint64_t ad = A_KMAJOR ? make_sdesc(aS + k * 32, 16, 1024) : make_sdesc(aS + k * 2048, 8192, 1024);
-          const uint64_t bd = B_KMAJOR ? make_sdesc(bS + k * 32, 16, 1024) : make_sdesc(bS + k * 2048, 8192, 1024);
-          umma_bf16(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major : 8-row groups 1024 B apart (SBO), +32 B per 16-element k step inside the swizzle atom
+            // MN-major: 64-element MN atoms 8192 B apart (LBO), 8-k groups 1024 B apart (SBO), +2048 B per k step
+            const uint64_t ad = A_KMAJOR ? make_sdesc(aS + k * 32, 16, 1024) : make_sdesc(aS + k * 2048, 8192, 1024);
+            const uint64_t bd = B_KMAJOR ? make_sdesc(bS + k * 32, 16, 1024) : make_sdesc(bS + k * 2048, 8192, 1024);
+            umma_bf16(tacc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar + 8 * s);      // smem slot free once these MMAs have read it
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(empty_bar + 8 * s);      // smem slot free once these MMAs have read it
+        umma_commit(tfull_bar + 8 * as);       // accumulator complete
       }
-      umma_commit(tfull_bar);                // accumulator complete
+      pdl_launch_dependents();
     }
   } else {
     // ---------------------------------------------------------------- epilogue warps
-    const int q = warp & 3;                  // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
-    mbar_wait(tfull_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const bool add_bias = (bias != nullptr) && (blockIdx.z == 0);
-    if (store_mode != 0) {
-      // ---- staged epilogue: TMEM -> registers -> 128B-swizzled smem slab (the drained pipeline stages are
-      // reused) -> TMA store / TMA reduce-add.  One 32-row slab per warp, so no cross-warp barrier is needed.
-      constexpr int ESZ = (int)sizeof(TO);
-      constexpr int COLS_PER_BOX = 128 / ESZ;               // 64 bf16 or 32 fp32 columns = one 128 B swizzle row
-      constexpr int NBOX = BN / COLS_PER_BOX;               // 2 or 4 boxes of 32 rows x 128 B = 4 KB
-      const uint32_t slab = sA + (uint32_t)q * (NBOX * 4096);
-      const uint32_t my_row = slab + (uint32_t)lane * 128;
-      const uint32_t sw = (uint32_t)(lane & 7);
-      if (epi == 2) {                                       // ReLU mask tile arrives by TMA into the same slab
-        if (lane == 0) {
-          mbar_expect_tx(aux_bar + 8 * q, NBOX * 4096);
-          for (int j = 0; j < NBOX; ++j)
-            tma_load_2d(slab + j * 4096, &tmX, n0 + j * COLS_PER_BOX, m0 + q * 32, aux_bar + 8 * q);
-        }
-        mbar_wait(aux_bar + 8 * q, 0);
-      }
+    constexpr int ESZ = (int)sizeof(TO);
+    constexpr int CPB = 128 / ESZ;             // columns per TMA store box (one 128 B swizzle row): 64 bf16 / 32 fp32
+    constexpr int CHUNKS_PER_BOX = CPB / 32;   // 32-column TMEM loads per box
+    constexpr int NCH = 32 * ESZ / 16;         // 16 B smem chunks per 32 columns: 4 (bf16) / 8 (fp32)
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const uint32_t ebuf = sE + (uint32_t)q * (2 * EPI_BOX_BYTES);
+    const uint32_t sw = (uint32_t)(lane & 7);
+    TO* const C = reinterpret_cast<TO*>(g.C);
+    const TO* const aux = reinterpret_cast<const TO*>(g.aux);
+    int it = 0, nbox = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int n0 = (tile % g.tiles_n) * BN, m0 = ((tile / g.tiles_n) % g.tiles_m) * BM;
+      const bool add_bias = (g.bias != nullptr) && (tile < g.tiles_n * g.tiles_m);     // split 0 only
+      const int as = it & 1, aph = (it >> 1) & 1;
+      const int row0 = m0 + q * 32, row = row0 + lane;
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      const int nchunks = min(BN / 32, (N - n0 + 31) / 32);       // >= 1
+      AuxRow<TO> a_cur, a_nxt;
+      const bool aux_vec = g.vec_ok != 0;
+      if (g.epi == 2 && row < M)
+        aux_load(a_cur, aux + (int64_t)row * g.ldaux + n0, aux_vec && n0 + 32 <= N, N - n0);
+      mbar_wait(tfull_bar + 8 * as, aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+      for (int c = 0; c < nchunks; ++c) {
         const int col0 = n0 + c * 32;
+        if (g.epi == 2 && row < M && c + 1 < nchunks)
+          aux_load(a_nxt, aux + (int64_t)row * g.ldaux + col0 + 32, aux_vec && col0 + 64 <= N, N - col0 - 32);
+        float bias_l = 0.f;                     // lane j holds bias[col0 + j]; broadcast through smem below
+        if (add_bias && col0 + lane < N) bias_l = __ldg(g.bias + col0 + lane);
+        uint32_t r[32];
+        tmem_ld32(tacc + (uint32_t)(c * 32), r);
+        if (c == nchunks - 1) {                 // accumulator fully read: hand the TMEM stage back to the MMA warp
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar + 8 * as);
+        }
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         if (add_bias) {
+          const uint32_t bslot = sBias + (uint32_t)q * 128;
+          __syncwarp();                         // previous chunk's reads of the slot are done
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(bslot + (uint32_t)lane * 4), "f"(bias_l) : "memory");
+          __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) if (col0 + j < N) v[j] += __ldg(bias + col0 + j);
+          for (int j = 0; j < 32; j += 4) {
+            float4 b4;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(bslot + (uint32_t)j * 4));
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          }
         }
-        if (epi == 1) {
+        if (g.epi == 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (g.epi == 2) {
+          if (row < M) aux_mask<TO>(a_cur, v);
+          a_cur = a_nxt;
         }
-        const int box = (c * 32) / COLS_PER_BOX;
-        const int chunk0 = ((c * 32) % COLS_PER_BOX) * ESZ / 16;     // first 16 B chunk of this 32-column group
-        constexpr int NCH = 32 * ESZ / 16;                             // 4 (bf16) or 8 (fp32) chunks
-        constexpr int EPC = 16 / ESZ;                                  // elements per chunk
+        if (g.store_mode != 0) {
+          // ---- staged: registers -> 128B-swizzled smem box (32 rows x 128 B) -> TMA store / reduce-add
+          const int cc = c % CHUNKS_PER_BOX;
+          const uint32_t buf = ebuf + (uint32_t)(nbox & 1) * EPI_BOX_BYTES;
+          if (cc == 0) {                        // the TMA store that last read this buffer must be done
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+          }
+          const uint32_t my_row = buf + (uint32_t)lane * 128;
 #pragma unroll
-        for (int t = 0; t < NCH; ++t) {
-          const uint32_t addr = my_row + box * 4096 + (((uint32_t)(chunk0 + t) ^ sw) << 4);
-          if (epi == 2) {
-            uint4 a;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(addr));
+          for (int t = 0; t < NCH; ++t) {
+            const uint32_t addr = my_row + ((((uint32_t)(cc * NCH + t)) ^ sw) << 4);
+            uint4 o;
             if constexpr (ESZ == 2) {
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (!(__low2float(h[e]) > 0.f)) v[t * 8 + 2 * e] = 0.f;
-                if (!(__high2float(h[e]) > 0.f)) v[t * 8 + 2 * e + 1] = 0.f;
-              }
+              __nv_bfloat162 h;
+              h = __floats2bfloat162_rn(v[t * 8 + 0], v[t * 8 + 1]); o.x = *reinterpret_cast<uint32_t*>(&h);
+              h = __floats2bfloat162_rn(v[t * 8 + 2], v[t * 8 + 3]); o.y = *reinterpret_cast<uint32_t*>(&h);
+              h = __floats2bfloat162_rn(v[t * 8 + 4], v[t * 8 + 5]); o.z = *reinterpret_cast<uint32_t*>(&h);
+              h = __floats2bfloat162_rn(v[t * 8 + 6], v[t * 8 + 7]); o.w = *reinterpret_cast<uint32_t*>(&h);
             } else {
-              const float* fa = reinterpret_cast<const float*>(&a);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) if (!(fa[e] > 0.f)) v[t * 4 + e] = 0.f;
+              o.x = __float_as_uint(v[t * 4 + 0]); o.y = __float_as_uint(v[t * 4 + 1]);
+              o.z = __float_as_uint(v[t * 4 + 2]); o.w = __float_as_uint(v[t * 4 + 3]);
             }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
           }
-          uint4 o;
-          if constexpr (ESZ == 2) {
-            __nv_bfloat162 h;
-            h = __floats2bfloat162_rn(v[t * 8 + 0], v[t * 8 + 1]); o.x = *reinterpret_cast<uint32_t*>(&h);
-            h = __floats2bfloat162_rn(v[t * 8 + 2], v[t * 8 + 3]); o.y = *reinterpret_cast<uint32_t*>(&h);
-            h = __floats2bfloat162_rn(v[t * 8 + 4], v[t * 8 + 5]); o.z = *reinterpret_cast<uint32_t*>(&h);
-            h = __floats2bfloat162_rn(v[t * 8 + 6], v[t * 8 + 7]); o.w = *reinterpret_cast<uint32_t*>(&h);
+          if (cc == CHUNKS_PER_BOX - 1 || c == nchunks - 1) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              if (row0 < M) {
+                const int bc0 = n0 + (c / CHUNKS_PER_BOX) * CPB;
+                if (g.store_mode == 2) tma_reduce_add_2d(&tmC, buf, bc0, row0);
+                else tma_store_2d(&tmC, buf, bc0, row0);
+              }
+              // one (possibly empty) group per box keeps `wait_group.read 1` == "the other buffer is free"
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            ++nbox;
+          }
+        } else if (row < M) {
+          // ---- direct global stores (C not TMA-aligned)
+          TO* crow = C + (int64_t)row * g.ldc + col0;
+          const bool full = g.vec_ok && (col0 + 32 <= N);
+          if (g.accumulate == 2) {
+            if constexpr (sizeof(TO) == 4) {
+              for (int j = 0; j < 32; ++j) if (col0 + j < N) atomicAdd(reinterpret_cast<float*>(crow) + j, v[j]);
+            }
+          } else if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (g.accumulate == 1) {
+                float o[8];
+                OutVec<TO>::load8(crow + j, o);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) v[j + t] += o[t];
+              }
+              OutVec<TO>::store8(crow + j, v + j);
+            }
           } else {
-            o.x = __float_as_uint(v[t * EPC + 0]); o.y = __float_as_uint(v[t * EPC + 1]);
-            o.z = __float_as_uint(v[t * EPC + 2]); o.w = __float_as_uint(v[t * EPC + 3]);
-          }
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
-        }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0 && m0 + q * 32 < M) {
-        for (int j = 0; j < NBOX; ++j) {
-          if (n0 + j * COLS_PER_BOX >= N) break;
-          if (store_mode == 2) tma_reduce_add_2d(&tmC, slab + j * 4096, n0 + j * COLS_PER_BOX, m0 + q * 32);
-          else tma_store_2d(&tmC, slab + j * 4096, n0 + j * COLS_PER_BOX, m0 + q * 32);
-        }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      }
-    } else
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-      const int col0 = n0 + c * 32;
-      if (row >= M || col0 >= N) continue;
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      if (add_bias) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) if (col0 + j < N) v[j] += __ldg(bias + col0 + j);
-      }
-      TO* crow = C + (int64_t)row * ldc + col0;
-      const bool full = vec_ok && (col0 + 32 <= N);
-      if (epi == 1) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-      } else if (epi == 2) {
-        const TO* arow = aux + (int64_t)row * ldaux + col0;
-        if (full) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            float a[8];
-            OutVec<TO>::load8(arow + j, a);
-#pragma unroll
-            for (int t = 0; t < 8; ++t) v[j + t] = a[t] > 0.f ? v[j + t] : 0.f;
-          }
-        } else {
-          for (int j = 0; j < 32; ++j) if (col0 + j < N) v[j] = to_f32(arow[j]) > 0.f ? v[j] : 0.f;
-        }
-      }
-      if (accumulate == 2) {
-        if constexpr (sizeof(TO) == 4) {
-          for (int j = 0; j < 32; ++j) if (col0 + j < N) atomicAdd(reinterpret_cast<float*>(crow) + j, v[j]);
-        }
-      } else if (full) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          if (accumulate == 1) {
-            float o[8];
-            OutVec<TO>::load8(crow + j, o);
-#pragma unroll
-            for (int t = 0; t < 8; ++t) v[j + t] += o[t];
-          }
-          OutVec<TO>::store8(crow + j, v + j);
-        }
-      } else {
-        for (int j = 0; j < 32; ++j) {
-          if (col0 + j < N) {
-            float o = v[j];
-            if (accumulate == 1) o += to_f32(crow[j]);
-            crow[j] = from_f32<TO>(o);
+            for (int j = 0; j < 32; ++j) {
+              if (col0 + j < N) {
+                float o = v[j];
+                if (g.accumulate == 1) o += to_f32(crow[j]);
+                crow[j] = from_f32<TO>(o);
+              }
+            }
           }
         }
       }
     }
+    if (g.store_mode != 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(CF::TMEM_COLS) : "memory");
   }
 }
 
@@ -404,24 +465,57 @@ int make_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int6
   return 0;
 }
 
-template <bool AK, bool BKM, typename TO>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tx, int M, int N,
-           int K, void* C, int64_t ldc, const float* bias, int epi, const void* aux, int64_t ldaux, int accumulate,
-           int kb_per_split, int splits, int vec_ok, int store_mode, cudaStream_t st) {
+int g_num_sms = 0;
+int g_pdl = 0;         // launch with programmatic stream serialization (icap_set_pdl)
+
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      g_num_sms = n;
+    else
+      g_num_sms = 148;
+    if (const char* e = getenv("ICAP_GEMM_SMS")) { int v = atoi(e); if (v > 0) g_num_sms = v; }
+  }
+  return g_num_sms;
+}
+
+template <int BN, bool AK, bool BKM, typename TO>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmArgs& g, cudaStream_t st) {
   static bool attr_done = false;
-  auto kern = gemm_tc_kernel<AK, BKM, TO>;
+  auto kern = gemm_tc_kernel<BN, AK, BKM, TO>;
   if (!attr_done) {
-    ICAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    ICAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
     attr_done = true;
   }
-  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)splits);
-  kern<<<grid, NTHREADS, SMEM_BYTES, st>>>(ta, tb, tc, tx, M, N, K, (TO*)C, ldc, bias, epi, (const TO*)aux, ldaux,
-                                           accumulate, kb_per_split, vec_ok, store_mode);
-  ICAP_LAUNCH_CHECK("icap_gemm(bf16 tcgen05)");
+  const int total = g.tiles_m * g.tiles_n * g.splits;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(total < num_sms() ? total : num_sms()), 1, 1);
+  cfg.blockDim = dim3(NTHREADS, 1, 1);
+  cfg.dynamicSmemBytes = Cfg<BN>::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  ICAP_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, g));
   return 0;
 }
 
+// estimated tensor-pipe clocks of the whole launch for a tile width (persistent: waves x per-tile main loop,
+// plus one exposed epilogue); used to pick BN and the split-K factor
+double est_cost(int64_t tiles, int nkb, int bn, int sms) {
+  const double waves = (double)((tiles + sms - 1) / sms);
+  // 128-wide tiles move 1.5x the operand bytes per flop from L2 (measured ~1.3x slower main loop, tools/gemm_bench.py)
+  const double per_kb = bn == 256 ? 512.0 : 256.0 * 1.35;
+  return waves * (double)nkb * per_kb + 4.0 * bn + 1500.0;
+}
+
 }  // namespace
+
+extern "C" int icap_set_pdl(int on) { g_pdl = on ? 1 : 0; return 0; }
 
 int icap_gemm_bf16_launch(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
                           const void* B, int64_t ldb, void* C, int64_t ldc, int c_dtype, const float* bias, int epi,
@@ -429,42 +523,67 @@ int icap_gemm_bf16_launch(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int6
   ICAP_ARG((uintptr_t)A % 16 == 0 && (uintptr_t)B % 16 == 0, "icap_gemm(bf16): A/B must be 16-byte aligned");
   ICAP_ARG(lda % 8 == 0 && ldb % 8 == 0, "icap_gemm(bf16): lda/ldb must be multiples of 8 (TMA 16-byte strides)");
   ICAP_ARG(!(a_kmajor == 0 && b_kmajor == 1), "icap_gemm(bf16): (A MN-major, B K-major) is not instantiated");
+  const int sms = num_sms();
+  const int nkb = (int)ceil_div64(K, BK);
+  const int64_t tiles_m = ceil_div64(M, BM);
+  const bool can_split = accumulate != 0 && epi == 0 && c_dtype == ICAP_F32 && bias == nullptr;
+  // ---- tile width and split-K factor: split_k <= 0 = automatic (fill the SMs, >= 4 k-blocks per split)
+  int best_bn = 128, best_split = 1;
+  double best_cost = 1e30;
+  const char* force_bn = getenv("ICAP_GEMM_BN");
+  for (int bn = 256; bn >= 128; bn -= 128) {
+    if (force_bn && atoi(force_bn) != bn) continue;
+    if (bn == 256 && N <= 128) continue;
+    const int64_t tiles = tiles_m * ceil_div64(N, bn);
+    int split = split_k;
+    if (split <= 0) {
+      split = 1;
+      if (can_split && tiles < sms) {
+        split = (int)(sms / tiles);
+        if (split > nkb / 4) split = nkb / 4;
+        if (split < 1) split = 1;
+      }
+    }
+    if (split > nkb) split = nkb;
+    if (split > 1 && !can_split) split = 1;
+    int kb_per = (nkb + split - 1) / split;
+    split = (nkb + kb_per - 1) / kb_per;
+    const double cost = est_cost(tiles * split, kb_per, bn, sms);
+    if (cost < best_cost) { best_cost = cost; best_bn = bn; best_split = split; }
+  }
+  if (split_k > 1)
+    ICAP_ARG(can_split, "icap_gemm(bf16): split_k>1 needs fp32 C, accumulate!=0, no bias and no activation epilogue");
+  split_k = best_split;
+  const int BN = best_bn;
+  const int kb_per = (nkb + split_k - 1) / split_k;
+  if (split_k > 1) accumulate = 2;
+  ICAP_ARG(accumulate != 2 || c_dtype == ICAP_F32, "icap_gemm(bf16): atomic accumulate needs fp32 C");
+
   CUtensorMap ta, tb;
   int rc;
   if (a_kmajor) rc = make_tmap(&ta, A, M, K, lda, BM); else rc = make_tmap(&ta, A, K, M, lda, 64);
   if (rc) return rc;
   if (b_kmajor) rc = make_tmap(&tb, B, N, K, ldb, BN); else rc = make_tmap(&tb, B, K, N, ldb, 64);
   if (rc) return rc;
-  const int nkb = (int)ceil_div64(K, BK);
-  if (split_k < 1) split_k = 1;
-  if (split_k > nkb) split_k = nkb;
-  int kb_per = (nkb + split_k - 1) / split_k;
-  split_k = (nkb + kb_per - 1) / kb_per;
-  if (split_k > 1) {
-    ICAP_ARG(accumulate != 0 && epi == 0 && c_dtype == ICAP_F32,
-             "icap_gemm(bf16): split_k>1 needs fp32 C, accumulate!=0 and no activation epilogue");
-    accumulate = 2;
-  }
-  ICAP_ARG(accumulate != 2 || c_dtype == ICAP_F32, "icap_gemm(bf16): atomic accumulate needs fp32 C");
   const int esz = c_dtype == ICAP_F32 ? 4 : 2;
   int vec_ok = ((uintptr_t)C % 16 == 0) && ((ldc * esz) % 16 == 0);
-  if (epi == 2) vec_ok = vec_ok && ((uintptr_t)aux % 16 == 0) && ((ldaux * esz) % 16 == 0);
-  // staged TMA epilogue whenever C (and aux) satisfy the TMA alignment rules; accumulation = TMA reduce-add
+  // staged TMA epilogue whenever C satisfies the TMA alignment rules; accumulation = TMA reduce-add
   int store_mode = vec_ok ? (accumulate ? 2 : 1) : 0;
   if (getenv("ICAP_GEMM_DIRECT_EPILOGUE")) store_mode = 0;
-  CUtensorMap tc = ta, tx = ta;
-  if (store_mode) {
-    if ((rc = make_tmap(&tc, C, M, N, ldc, 32, c_dtype))) return rc;
-    if (epi == 2 && (rc = make_tmap(&tx, aux, M, N, ldaux, 32, c_dtype))) return rc;
-  }
-#define GO(AK, BKM)                                                                                                 \
-  (c_dtype == ICAP_F32                                                                                              \
-       ? launch<AK, BKM, float>(ta, tb, tc, tx, (int)M, (int)N, (int)K, C, ldc, bias, epi, aux, ldaux, accumulate,  \
-                                kb_per, split_k, vec_ok, store_mode, st)                                            \
-       : launch<AK, BKM, bf16>(ta, tb, tc, tx, (int)M, (int)N, (int)K, C, ldc, bias, epi, aux, ldaux, accumulate,   \
-                               kb_per, split_k, vec_ok, store_mode, st))
+  if (epi == 2) vec_ok = vec_ok && ((uintptr_t)aux % 16 == 0) && ((ldaux * esz) % 16 == 0);
+  CUtensorMap tc = ta;
+  if (store_mode && (rc = make_tmap(&tc, C, M, N, ldc, 32, c_dtype))) return rc;
+  GemmArgs g;
+  g.M = (int)M; g.N = (int)N; g.K = (int)K;
+  g.C = C; g.ldc = ldc; g.bias = bias; g.epi = epi; g.aux = aux; g.ldaux = ldaux; g.accumulate = accumulate;
+  g.kb_per_split = kb_per; g.splits = split_k; g.tiles_m = (int)tiles_m; g.tiles_n = (int)ceil_div64(N, BN);
+  g.vec_ok = vec_ok; g.store_mode = store_mode;
+#define GO2(BNV, AK, BKM) \
+  (c_dtype == ICAP_F32 ? launch<BNV, AK, BKM, float>(ta, tb, tc, g, st) : launch<BNV, AK, BKM, bf16>(ta, tb, tc, g, st))
+#define GO(AK, BKM) (BN == 256 ? GO2(256, AK, BKM) : GO2(128, AK, BKM))
   if (a_kmajor && b_kmajor) return GO(true, true);
   if (a_kmajor && !b_kmajor) return GO(true, false);
   return GO(false, false);
 #undef GO
+#undef GO2
 }

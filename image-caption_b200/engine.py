@@ -247,9 +247,12 @@ class CaptionEngine:
               ld_dy: Optional[int] = None, dy_ptr: Optional[int] = None, ldg: Optional[int] = None,
               x_ptr: Optional[int] = None, ldx: Optional[int] = None) -> None:
         """dW[Nout,Kin] += dy[rows,Nout]^T x[rows,Kin]  (fp32, split-K over rows so the grid fills the GPU)."""
-        tiles = ((Nout + 127) // 128) * ((Kin + 127) // 128)
-        split = max(1, min(32, (148 * 2) // max(1, tiles), (rows + 511) // 512))
         ab = BF16 if self.precision == "bf16" else F32
+        if ab == BF16:
+            split = 0           # automatic: the persistent tcgen05 kernel picks tile width + split to fill the SMs
+        else:
+            tiles = ((Nout + 127) // 128) * ((Kin + 127) // 128)
+            split = max(1, min(32, (148 * 2) // max(1, tiles), (rows + 511) // 512))
         ev = self._prof_begin()
         call("icap_gemm", ab, 0, 0, Nout, Kin, rows, dy.data_ptr() if dy_ptr is None else dy_ptr,
              dy.shape[-1] if ld_dy is None else ld_dy, x.data_ptr() if x_ptr is None else x_ptr,

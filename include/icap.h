@@ -34,12 +34,16 @@ extern "C" {
 int icap_version(void);
 const char* icap_last_error(void);
 int icap_sm_check(int device);
+/* on=1: tcgen05 GEMMs are launched with programmatic stream serialization (PDL): their per-CTA setup overlaps
+ * the tail of the previous kernel in the stream (griddepcontrol.wait guards every dependent access). */
+int icap_set_pdl(int on);
 
 /* C[M,N] (+)= op(A)[M,K] . op(B)[K,N] (+ bias[N]) with an optional activation epilogue.
  *   a_kmajor=1: A stored [M][K]; 0: stored [K][M].   b_kmajor=1: B stored [N][K]; 0: stored [K][N].
  *   ab_dtype ICAP_F32 : true-fp32 SIMT kernel (fp32 parity mode), C fp32.
  *   ab_dtype ICAP_BF16: TMA + tcgen05.mma + TMEM kernel, C fp32 or bf16 (c_dtype).
- *   accumulate=1: C += ...; split_k>1 (needs accumulate=1, fp32 C) reduces K-slices with red.add.
+ *   accumulate=1: C += ...; split_k>1 (needs accumulate=1, fp32 C, no bias) reduces K-slices with red.add;
+ *   split_k<=0 (bf16): the kernel picks the split that fills the SMs (1 unless accumulate=1 and C is fp32).
  * Replaces every nn.Linear / torch.matmul weight contraction of the path and their autograd
  * backward: modules.py:42-44,59-60,72-77,86,100-101,113-116; model.py:68,93,235,246,295-306,392-394,433. */
 int icap_gemm(int ab_dtype, int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,

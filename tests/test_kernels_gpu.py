@@ -93,6 +93,26 @@ def test_gemm_bf16_tcgen05_epilogues():
     assert _gemm_case(BF16, 0, 0, 512, 512, 9216, accumulate=1, split_k=18) < 1e-5
 
 
+@pytest.mark.parametrize("bn", ["128", "256"])
+def test_gemm_bf16_persistent_multi_tile(bn, monkeypatch):
+    """More tiles than SMs: every CTA loops over several tiles (TMEM accumulator double buffering, smem ring
+    phases carried across tiles), both tile widths, every epilogue, automatic split-K."""
+    monkeypatch.setenv("ICAP_GEMM_BN", bn)
+    assert _gemm_case(BF16, 1, 1, 9216, 2048, 512, c_dtype=BF16, bias=True, epi=1) < 6e-3      # FFN1 forward
+    assert _gemm_case(BF16, 1, 0, 9216, 2048, 512, c_dtype=BF16, epi=2) < 6e-3                 # FFN2 dgrad + ReLU mask
+    assert _gemm_case(BF16, 1, 1, 5376, 10000, 512, c_dtype=BF16, bias=True) < 6e-3            # classifier
+    assert _gemm_case(BF16, 1, 0, 5376, 512, 10000, c_dtype=BF16) < 6e-3                       # classifier dgrad
+    assert _gemm_case(BF16, 1, 1, 4000, 1000, 200, c_dtype=F32, bias=True) < 1e-5              # ragged everything
+    assert _gemm_case(BF16, 1, 0, 4000, 1000, 200, c_dtype=F32, accumulate=1) < 1e-5
+    assert _gemm_case(BF16, 0, 0, 2048, 512, 9216, accumulate=1, split_k=0) < 1e-5             # wgrad, auto split
+    assert _gemm_case(BF16, 0, 0, 10000, 512, 5376, accumulate=1, split_k=0) < 1e-5            # classifier wgrad
+    assert _gemm_case(BF16, 0, 0, 512, 2136, 9216, accumulate=1, split_k=0) < 1e-5             # embedding wgrad
+    monkeypatch.setenv("ICAP_GEMM_DIRECT_EPILOGUE", "1")
+    assert _gemm_case(BF16, 1, 1, 3000, 1000, 200, c_dtype=BF16, bias=True, epi=1) < 6e-3
+    assert _gemm_case(BF16, 1, 0, 3000, 1000, 200, c_dtype=BF16, epi=2) < 6e-3
+    assert _gemm_case(BF16, 0, 0, 520, 392, 5000, accumulate=1, split_k=0) < 1e-5
+
+
 def test_gemm_bf16_vocab_shapes():
     """classifier-like shapes: N = V not a multiple of the tile, padded leading dimension."""
     M, V, d, ldl = 300, 1000, 512, 1000
