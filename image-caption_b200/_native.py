@@ -73,9 +73,14 @@ def last_error() -> str:
     return lib().icap_last_error().decode("utf-8", "replace")
 
 
+call_log = None           # profiling: when a list, every call is appended as (name, args) -- see tools/step_breakdown.py
+
+
 def call(name: str, *args) -> None:
     """Invoke an entry point; raise IcapError on a non-zero return code."""
     global launch_count
+    if call_log is not None:
+        call_log.append((name, args))
     rc = getattr(lib(), name)(*args)
     if rc != 0:
         raise IcapError(f"{name} failed (rc={rc}): {last_error()}")

@@ -9,6 +9,7 @@
 // Heads are addressed in the packed projection outputs ([rows, H*dh] with a row stride), so no
 // transpose / contiguous copies exist.  The whole (b, h) problem (L <= ~128) lives in shared memory;
 // softmax uses warp shuffles.  Backward recomputes P (nothing but Q, K, V, dO is read).
+#include <stdlib.h>
 #include "icap_common.cuh"
 
 // tensor-core (mma.sync) variants for bf16 / head dim 64, attention_mma.cu
@@ -98,9 +99,8 @@ __device__ __forceinline__ void scores_softmax(float* P, float* Praw, const floa
       if (Praw) Praw[i * D.LkP + j] = p;
       if (p_drop > 0.f) {
         const uint64_t e = (bh * D.Lq + i) * (uint64_t)D.LkP + j;
-        const uint4 r = philox4x32(seed, e >> 2);
-        const uint32_t rv = (e & 3) == 0 ? r.x : (e & 3) == 1 ? r.y : (e & 3) == 2 ? r.z : r.w;
-        p = rv >= thresh ? p * keep_scale : 0.f;
+        const uint32_t keep = dropout_keep2(seed_fold(seed), e >> 1, thresh);
+        p = ((keep >> (e & 1)) & 1u) ? p * keep_scale : 0.f;
       }
       row[j] = p;
     }
@@ -360,6 +360,209 @@ mha_decode_kernel(int rows, int H, int Lk, int dk, int dv, const T* __restrict__
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fast KV-cached decoding attention for head dim 64 (dk == dv == 64), any dtype.
+// One warp per (query group, head); a group = G queries that read the SAME keys/values:
+//   cross-attention: the G = rows_per_image beams of one image (K/V of the image are read once, not per beam)
+//   self-attention : G = 1 (every beam has its own cache rows through the slot table)
+// K / V rows are 128 B (bf16) or 256 B (fp32): 8 lanes x 8 elements cover one row with 16-byte loads, so a warp
+// reads 4 keys per load instruction, fully coalesced.  Scores are reduced over the 8 lanes of a key with three
+// xor-shuffles, staged in shared memory for the softmax, then P.V accumulates 8 output columns per lane and is
+// reduced over the 4 key sub-groups with two more shuffles.
+constexpr int DEC_WARPS = 8, DEC_LK = 128;
+
+template <typename T>
+__device__ __forceinline__ void ld8(const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void ld8<float>(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void ld8<bf16>(const bf16* p, float (&v)[8]) {
+  const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+}
+__device__ __forceinline__ void st8(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void st8(bf16* p, const float (&v)[8]) {
+  uint4 t;
+  __nv_bfloat162 h;
+  h = __floats2bfloat162_rn(v[0], v[1]); t.x = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(v[2], v[3]); t.y = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(v[4], v[5]); t.z = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(v[6], v[7]); t.w = *reinterpret_cast<uint32_t*>(&h);
+  *reinterpret_cast<uint4*>(p) = t;
+}
+
+template <typename T, int G>
+__global__ void __launch_bounds__(DEC_WARPS * 32)
+mha_decode64_kernel(int groups, int H, int Lk, const T* __restrict__ q, int64_t ldq, const T* __restrict__ kc,
+                    int64_t ldk, const T* __restrict__ vc, int64_t ldv, int kv_rows_per_seq, T* __restrict__ o,
+                    int64_t ldo, const int* __restrict__ slot, int64_t slot_ld, const int* __restrict__ tokens,
+                    int64_t tok_ld, int pad_idx, const uint8_t* __restrict__ kvalid, float* __restrict__ attn_mean) {
+  __shared__ float ps[DEC_WARPS][G][DEC_LK];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int unit = blockIdx.x * DEC_WARPS + warp;
+  if (unit >= groups * H) return;
+  const int grp = unit / H, h = unit % H;
+  const int sub = lane >> 3, ch = lane & 7;
+  const bool self_mode = tokens != nullptr;      // G == 1: the group is the row
+  float qv[G][8];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    ld8<T>(q + (int64_t)(grp * G + g) * ldq + h * 64 + ch * 8, qv[g]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) qv[g][e] *= 0.125f;                 // 1 / sqrt(64), applied to q as in modules.py:18
+  }
+  // ---- physical cache row of every key (or -1 = masked), gathered up front: lane l owns keys l, l+32, ...
+  // (tokens / slot / kvalid loads are coalesced and off the critical path of the K / V loads below)
+  int kr[DEC_LK / 32];
+#pragma unroll
+  for (int jj = 0; jj < DEC_LK / 32; ++jj) {
+    const int j = jj * 32 + lane;
+    int r_ = -1;
+    if (j < Lk) {
+      if (self_mode) {
+        const int sl = slot ? slot[(int64_t)grp * slot_ld + j] : grp;
+        if (tokens[(int64_t)grp * tok_ld + j] != pad_idx) r_ = sl * kv_rows_per_seq + j;
+      } else if (!(kvalid && !kvalid[(int64_t)grp * Lk + j])) {
+        r_ = grp * kv_rows_per_seq + j;
+      }
+    }
+    kr[jj] = r_;
+  }
+  constexpr int UB = 4;                              // key batches of 4 x 4: four independent 16-byte loads in flight
+  // ---- scores
+  for (int jb = 0; jb < Lk; jb += 4 * UB) {
+    float kv[UB][8];
+    int rr[UB];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const int j = jb + u * 4 + sub;                // < DEC_LK + 16: clamp the source lane, mask by j < Lk
+      const int jj = (j >> 5) & (DEC_LK / 32 - 1);
+      const int src = jj == 0 ? kr[0] : jj == 1 ? kr[1] : jj == 2 ? kr[2] : kr[3];
+      const int got = __shfl_sync(0xffffffffu, src, j & 31);
+      rr[u] = j < Lk ? got : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) kv[u][e] = 0.f;
+      if (rr[u] >= 0) ld8<T>(kc + (int64_t)rr[u] * ldk + h * 64 + ch * 8, kv[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const int j = jb + u * 4 + sub;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        float part = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) part = fmaf(qv[g][e], kv[u][e], part);
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        part += __shfl_xor_sync(0xffffffffu, part, 4);
+        if (ch == 0 && j < Lk) ps[warp][g][j] = rr[u] >= 0 ? part : -INFINITY;
+      }
+    }
+  }
+  __syncwarp();
+  // ---- softmax over the keys, one query at a time (lanes own keys)
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    float sv[DEC_LK / 32];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < DEC_LK / 32; ++jj) {
+      const int j = jj * 32 + lane;
+      sv[jj] = j < Lk ? ps[warp][g][j] : -INFINITY;
+      mx = fmaxf(mx, sv[jj]);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < DEC_LK / 32; ++jj) {
+      sv[jj] = (sv[jj] == -INFINITY) ? 0.f : expf(sv[jj] - mx);
+      sum += sv[jj];
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int jj = 0; jj < DEC_LK / 32; ++jj) {
+      const int j = jj * 32 + lane;
+      if (j < Lk) {
+        const float pj = sv[jj] * inv;
+        ps[warp][g][j] = pj;
+        if (attn_mean) atomicAdd(attn_mean + (int64_t)(grp * G + g) * Lk + j, pj / (float)H);
+      }
+    }
+  }
+  __syncwarp();
+  // ---- P.V
+  float acc[G][8];
+#pragma unroll
+  for (int g = 0; g < G; ++g)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[g][e] = 0.f;
+  for (int jb = 0; jb < Lk; jb += 4 * UB) {
+    float vv[UB][8];
+    int rr[UB];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const int j = jb + u * 4 + sub;
+      const int jj = (j >> 5) & (DEC_LK / 32 - 1);
+      const int src = jj == 0 ? kr[0] : jj == 1 ? kr[1] : jj == 2 ? kr[2] : kr[3];
+      const int got = __shfl_sync(0xffffffffu, src, j & 31);
+      rr[u] = j < Lk ? got : -1;                     // masked keys have p == 0 for every query: never loaded
+    }
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) vv[u][e] = 0.f;
+      if (rr[u] >= 0) ld8<T>(vc + (int64_t)rr[u] * ldv + h * 64 + ch * 8, vv[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const int j = jb + u * 4 + sub;
+      if (rr[u] >= 0) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float pj = ps[warp][g][j];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[g][e] = fmaf(pj, vv[u][e], acc[g][e]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      acc[g][e] += __shfl_xor_sync(0xffffffffu, acc[g][e], 8);
+      acc[g][e] += __shfl_xor_sync(0xffffffffu, acc[g][e], 16);
+    }
+    if (sub == 0) st8(o + (int64_t)(grp * G + g) * ldo + h * 64 + ch * 8, acc[g]);
+  }
+}
+
+template <typename T, int G>
+int launch_decode64(int64_t groups, int64_t H, int64_t Lk, const void* q, int64_t ldq, const void* kc, int64_t ldk,
+                    const void* vc, int64_t ldv, int64_t kv_rows_per_seq, void* o, int64_t ldo, const int* slot,
+                    int64_t slot_ld, const int* tokens, int64_t tok_ld, int pad_idx, const uint8_t* kvalid,
+                    float* attn_mean, cudaStream_t st) {
+  const unsigned grid = (unsigned)ceil_div64(groups * H, DEC_WARPS);
+  mha_decode64_kernel<T, G><<<grid, DEC_WARPS * 32, 0, st>>>(
+      (int)groups, (int)H, (int)Lk, (const T*)q, ldq, (const T*)kc, ldk, (const T*)vc, ldv, (int)kv_rows_per_seq, (T*)o,
+      ldo, slot, slot_ld, tokens, tok_ld, pad_idx, kvalid, attn_mean);
+  ICAP_LAUNCH_CHECK("icap_mha_decode(64)");
+  return 0;
+}
+
 int check_dims(const char* fn, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t dk, int64_t dv) {
   ICAP_ARG(B > 0 && H > 0 && Lq > 0 && Lk > 0, "%s: empty problem", fn);
   ICAP_ARG(dk % 4 == 0 && dv % 4 == 0 && dk > 0 && dv > 0, "%s: head dims must be multiples of 4 (dk=%lld dv=%lld)", fn,
@@ -448,6 +651,35 @@ extern "C" int icap_mha_decode(int dtype, int64_t rows, int64_t H, int64_t Lk, i
   ICAP_ARG(slot == nullptr || tokens != nullptr, "icap_mha_decode: a slot table needs the token buffer (self mode)");
   ICAP_ARG(rows_per_image >= 1, "icap_mha_decode: rows_per_image must be >= 1");
   cudaStream_t st = (cudaStream_t)stream;
+  const int esz = dtype == ICAP_F32 ? 4 : 2;
+  const bool al = ((uintptr_t)q % 16 == 0) && ((uintptr_t)kc % 16 == 0) && ((uintptr_t)vc % 16 == 0) &&
+                  ((uintptr_t)o % 16 == 0) && (ldq * esz) % 16 == 0 && (ldk * esz) % 16 == 0 && (ldv * esz) % 16 == 0 &&
+                  (ldo * esz) % 16 == 0;
+  if (dk == 64 && dv == 64 && al && !getenv("ICAP_DECODE_SLOW")) {
+    // group size: beams of one image share K/V in cross-attention; self-attention rows are independent
+    int64_t G = tokens ? 1 : rows_per_image;
+    if (G > 8 || rows % G != 0 || (G > 5 && G != 8)) G = 1;
+    const int64_t groups = rows / G;
+    // odd beam sizes (6, 7, > 8) in cross mode fall through to the generic kernel below
+    if (tokens != nullptr || G == rows_per_image) {
+#define DEC(T, GG)                                                                                                   \
+  return launch_decode64<T, GG>(groups, H, Lk, q, ldq, kc, ldk, vc, ldv, kv_rows_per_seq, o, ldo, slot, slot_ld,      \
+                                tokens, tok_ld, pad_idx, kvalid, attn_mean, st)
+#define DECT(T)                                                                                                      \
+  switch (G) {                                                                                                       \
+    case 1: DEC(T, 1);                                                                                               \
+    case 2: DEC(T, 2);                                                                                               \
+    case 3: DEC(T, 3);                                                                                               \
+    case 4: DEC(T, 4);                                                                                               \
+    case 5: DEC(T, 5);                                                                                               \
+    case 8: DEC(T, 8);                                                                                               \
+    default: break;                                                                                                  \
+  }
+      if (dtype == ICAP_F32) { DECT(float) } else { DECT(bf16) }
+#undef DECT
+#undef DEC
+    }
+  }
   const size_t smem = (NT / 32) * dk * sizeof(float);
   const unsigned grid = (unsigned)ceil_div64(rows * H, NT / 32);
   if (dtype == ICAP_F32)

@@ -112,22 +112,19 @@ __device__ __forceinline__ void softmax_tile(float (&s)[NT8][4], int m0, int lan
   }
 }
 
-// keep-mask bits for this thread's elements: bit (nt*4 + e) ; element (row, j) uses philox counter
-// (bh*Lq + row) * (NT8*2) + (j >> 2), component j & 3  -- identical in forward and backward
+// keep-mask bits for this thread's elements: bit (nt*4 + e).  The element pair (row, columns 8*nt + 2*(lane%4) + {0,1})
+// has pair index ((bh*Lq + row) * NT8 + nt) * 4 + lane%4  -- identical in forward and backward
 template <int NT8>
 __device__ __forceinline__ uint64_t dropout_bits(uint64_t seed, uint32_t thresh, uint64_t bh, int Lq, int m0, int lane) {
   uint64_t bits = 0;
   const int r0 = m0 + (lane >> 2);
+  const uint32_t sf = seed_fold(seed);
 #pragma unroll
-  for (int nt = 0; nt < NT8; ++nt) {
-    const int j = nt * 8 + 2 * (lane & 3);
+  for (int h = 0; h < 2; ++h) {
+    const uint64_t base = ((bh * Lq + (uint64_t)(r0 + 8 * h)) * (uint64_t)NT8) * 4 + (uint64_t)(lane & 3);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const uint4 r = philox4x32(seed, (bh * Lq + (uint64_t)(r0 + 8 * h)) * (uint64_t)(NT8 * 2) + (uint64_t)(j >> 2));
-      const uint32_t a = (j & 2) ? r.z : r.x, b = (j & 2) ? r.w : r.y;
-      if (a >= thresh) bits |= 1ull << (nt * 4 + 2 * h);
-      if (b >= thresh) bits |= 1ull << (nt * 4 + 2 * h + 1);
-    }
+    for (int nt = 0; nt < NT8; ++nt)
+      bits |= (uint64_t)dropout_keep2(sf, base + (uint64_t)(nt * 4), thresh) << (nt * 4 + 2 * h);
   }
   return bits;
 }

@@ -83,28 +83,33 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// ---- counter-based RNG for dropout (Philox4x32-10) ---------------------------------------------
-// One call yields 4x32 random bits for a (seed, counter) pair; the same (seed, element index)
-// is re-evaluated in the backward kernels so no mask tensor is ever stored.
-__device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t ctr) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x1CA9B200u, c3 = 0u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
-    uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
-    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-    k0 += W0; k1 += W1;
-  }
-  return make_uint4(c0, c1, c2, c3);
+// ---- counter-based RNG for dropout ----------------------------------------------------------------
+// Stateless: the keep decision of an element is a pure function of (seed, element index), so the backward
+// kernels re-evaluate it and no mask tensor is ever stored.  One 32-bit integer hash (lowbias32, two
+// multiplies + three xor-shifts) yields two 16-bit uniforms = two elements; an element is kept iff its 16-bit
+// uniform >= thresh >> 16.  (Philox4x32-10 here cost ~70 instructions per 4 elements and made the attention
+// and LayerNorm kernels issue-bound: ncu r1, profiles/r1_summary.md.)
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU;
+  x ^= x >> 15; x *= 0x846ca68bU;
+  x ^= x >> 16;
+  return x;
 }
-// keep-mask for 4 consecutive elements starting at element index e4*4: bit j set = keep
+__device__ __forceinline__ uint32_t seed_fold(uint64_t seed) {          // loop-invariant: hoisted by the compiler
+  return hash32((uint32_t)seed ^ hash32((uint32_t)(seed >> 32) + 0x9E3779B9u));
+}
+__device__ __forceinline__ uint32_t rand32(uint32_t seed_folded, uint64_t idx) {
+  return hash32((uint32_t)idx * 0x9E3779B1u + (uint32_t)(idx >> 32) * 0x85EBCA77u + seed_folded);
+}
+// keep-mask for the element pair with pair index e2 (elements 2*e2, 2*e2+1): bit j set = keep
+__device__ __forceinline__ uint32_t dropout_keep2(uint32_t seed_folded, uint64_t e2, uint32_t thresh) {
+  const uint32_t h = rand32(seed_folded, e2), t16 = thresh >> 16;
+  return ((h & 0xFFFFu) >= t16 ? 1u : 0u) | ((h >> 16) >= t16 ? 2u : 0u);
+}
+// keep-mask for 4 consecutive elements starting at element index e4*4
 __device__ __forceinline__ uint32_t dropout_keep4(uint64_t seed, uint64_t e4, uint32_t thresh) {
-  uint4 r = philox4x32(seed, e4);
-  return (r.x >= thresh ? 1u : 0u) | (r.y >= thresh ? 2u : 0u) | (r.z >= thresh ? 4u : 0u) |
-         (r.w >= thresh ? 8u : 0u);
+  const uint32_t sf = seed_fold(seed);
+  return dropout_keep2(sf, 2 * e4, thresh) | (dropout_keep2(sf, 2 * e4 + 1, thresh) << 2);
 }
 static inline uint32_t dropout_threshold(float p) {
   double t = (double)p * 4294967296.0;

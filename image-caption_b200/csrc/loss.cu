@@ -106,6 +106,28 @@ xent_finalize_kernel(int M, const float* __restrict__ row_loss, const float* __r
   }
 }
 
+// up to 8 consecutive logits starting at x[j] as fp32 (one 16-byte load when `vec` and all 8 are in range)
+template <typename T>
+__device__ __forceinline__ int load_chunk8(const T* __restrict__ x, int j, int V, bool vec, float (&v)[8]) {
+  const int n = min(8, V - j);
+  if (vec && n == 8) {
+    if constexpr (sizeof(T) == 2) {
+      const uint4 t = *reinterpret_cast<const uint4*>(x + j);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+    } else {
+      const float4 a = *reinterpret_cast<const float4*>(x + j), b = *reinterpret_cast<const float4*>(x + j + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = i < n ? to_f32(x[j + i]) : -INFINITY;
+  }
+  return n;
+}
+
+
 template <typename T>
 __global__ void __launch_bounds__(NT)
 argmax_kernel(int V, const T* __restrict__ logits, int64_t ldl, int* __restrict__ out, int64_t out_stride,
@@ -115,10 +137,17 @@ argmax_kernel(int V, const T* __restrict__ logits, int64_t ldl, int* __restrict_
   const T* x = logits + (int64_t)blockIdx.x * ldl;
   float best = -INFINITY, second = -INFINITY;
   int bi = 0x7fffffff;
-  for (int j = threadIdx.x; j < V; j += NT) {
-    const float v = to_f32(x[j]);
-    if (v > best) { second = best; best = v; bi = j; }
-    else if (v > second) second = v;
+  const bool vec = ((uintptr_t)logits % 16 == 0) && (ldl * sizeof(T)) % 16 == 0;
+  for (int j0 = threadIdx.x * 8; j0 < V; j0 += NT * 8) {       // ascending index per thread: first maximum is kept
+    float c[8];
+    const int n = load_chunk8(x, j0, V, vec, c);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i >= n) break;
+      const float v = c[i];
+      if (v > best) { second = best; best = v; bi = j0 + i; }
+      else if (v > second) second = v;
+    }
   }
   sv[threadIdx.x] = best; sv2[threadIdx.x] = second; si[threadIdx.x] = bi;
   __syncthreads();
@@ -156,35 +185,69 @@ beam_select_kernel(int kin, int V, const T* __restrict__ logits, int64_t ldl, co
   __shared__ float h_s[NT];
   __shared__ int h_i[NT], h_t[NT];
   const int b = blockIdx.x;
+  const bool vec = ((uintptr_t)logits % 16 == 0) && (ldl * sizeof(T)) % 16 == 0;
   for (int r = 0; r < kin; ++r) {
     const T* x = logits + ((int64_t)b * kin + r) * ldl;
     float mx = -INFINITY;
-    for (int j = threadIdx.x; j < V; j += NT) mx = fmaxf(mx, to_f32(x[j]));
+    for (int j = threadIdx.x * 8; j < V; j += NT * 8) {
+      float v[8];
+      load_chunk8(x, j, V, vec, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx = fmaxf(mx, v[i]);
+    }
     mx = block_max(mx, red);
     float sum = 0.f;
-    for (int j = threadIdx.x; j < V; j += NT) sum += expf(to_f32(x[j]) - mx);
+    for (int j = threadIdx.x * 8; j < V; j += NT * 8) {
+      float v[8];
+      const int n = load_chunk8(x, j, V, vec, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) if (i < n) sum += expf(v[i] - mx);
+    }
     sum = block_sum(sum, red);
     if (threadIdx.x == 0) { s_mx[r] = mx; s_den[r] = log_domain ? logf(sum) : sum; }
   }
   __syncthreads();
   const int L = kout + 1;
-  Cand lst[KMAX + 1];
+  Cand lst[KMAX + 1];                      // sorted, best first; only static indices (stays in registers)
 #pragma unroll
   for (int t = 0; t <= KMAX; ++t) { lst[t].s = -INFINITY; lst[t].i = 0x7fffffff; }
+  float worst_s = -INFINITY;               // == lst[L-1]: the entry a candidate has to beat
+  int worst_i = 0x7fffffff;
   for (int r = 0; r < kin; ++r) {
     const T* x = logits + ((int64_t)b * kin + r) * ldl;
     const float mx = s_mx[r], den = s_den[r], pv = prev ? prev[b * kin + r] : 0.f;
-    for (int j = threadIdx.x; j < V; j += NT) {
-      const float xv = to_f32(x[j]);
-      const float sc = (log_domain ? (xv - mx - den) : (expf(xv - mx) / den)) + pv;
-      const int idx = r * V + j;
-      if (better(sc, idx, lst[L - 1].s, lst[L - 1].i)) {
-        lst[L - 1].s = sc; lst[L - 1].i = idx;
+    // Cheap pre-filter in the logit domain: the score is monotonic in the logit, so only logits above
+    //   tl = logit whose score equals the current worst list entry (minus a 1e-3 safety margin)
+    // can enter the list; everything else costs one compare instead of expf + divide.
+    float tl;
+    auto refresh_tl = [&]() {
+      if (log_domain) tl = worst_s - pv + mx + den;
+      else { const float need = worst_s - pv; tl = need > 0.f ? mx + logf(need * den) : -INFINITY; }
+      tl -= 1e-3f;
+    };
+    refresh_tl();
+    for (int j0 = threadIdx.x * 8; j0 < V; j0 += NT * 8) {
+      float v[8];
+      const int n = load_chunk8(x, j0, V, vec, v);
 #pragma unroll
-        for (int t = KMAX; t > 0; --t) {
-          if (t < L && better(lst[t].s, lst[t].i, lst[t - 1].s, lst[t - 1].i)) {
-            Cand c = lst[t]; lst[t] = lst[t - 1]; lst[t - 1] = c;
+      for (int i = 0; i < 8; ++i) {
+        if (i >= n) break;
+        const float xv = v[i];
+        if (!(xv > tl)) continue;
+        const float sc = (log_domain ? (xv - mx - den) : (expf(xv - mx) / den)) + pv;
+        const int idx = r * V + j0 + i;
+        if (better(sc, idx, worst_s, worst_i)) {
+#pragma unroll
+          for (int t = 0; t <= KMAX; ++t) if (t == L - 1) { lst[t].s = sc; lst[t].i = idx; }
+#pragma unroll
+          for (int t = KMAX; t > 0; --t) {
+            if (t < L && better(lst[t].s, lst[t].i, lst[t - 1].s, lst[t - 1].i)) {
+              Cand c = lst[t]; lst[t] = lst[t - 1]; lst[t - 1] = c;
+            }
           }
+#pragma unroll
+          for (int t = 0; t <= KMAX; ++t) if (t == L - 1) { worst_s = lst[t].s; worst_i = lst[t].i; }
+          refresh_tl();
         }
       }
     }
@@ -193,8 +256,12 @@ beam_select_kernel(int kin, int V, const T* __restrict__ logits, int64_t ldl, co
   int head = 0;
   float kth = 0.f;
   for (int round = 0; round < L; ++round) {
-    h_s[threadIdx.x] = head < L ? lst[head].s : -INFINITY;
-    h_i[threadIdx.x] = head < L ? lst[head].i : 0x7fffffff;
+    float hs = -INFINITY;
+    int hi = 0x7fffffff;
+#pragma unroll
+    for (int t = 0; t <= KMAX; ++t) if (t == head && t < L) { hs = lst[t].s; hi = lst[t].i; }
+    h_s[threadIdx.x] = hs;
+    h_i[threadIdx.x] = hi;
     h_t[threadIdx.x] = threadIdx.x;
     __syncthreads();
     for (int s = NT / 2; s > 0; s >>= 1) {

@@ -7,6 +7,7 @@
 // embedding norms (model.py:307-309,433-436: res = positional table, res_rows = T) and the per-block
 // `output *= non_pad_mask` (modules.py:154-155,203-204) folded in as rowscale.  HBM-bound: one warp
 // per row, 16-byte vector accesses, warp-shuffle statistics, no shared memory.
+#include <stdlib.h>
 #include "icap_common.cuh"
 
 namespace {
@@ -212,6 +213,276 @@ add_ln_bwd_cols_kernel(int M, int d, const T* __restrict__ dy1, const T* __restr
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Fast path (d % 8 == 0, 16-byte aligned rows): 8 elements (16 B of bf16) per lane per access and TWO rows per
+// warp, so every warp has 2 x (a, res) [fwd] or 2 x (dy1, dy2, s) [bwd] independent 16-byte loads in flight.
+// Dropout indices are element based (e4 = (row*d + col) / 4), i.e. identical to the 4-wide kernels above.
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
+  uint4 t;
+  __nv_bfloat162 h;
+  h = __floats2bfloat162_rn(v[0], v[1]); t.x = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(v[2], v[3]); t.y = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(v[4], v[5]); t.z = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(v[6], v[7]); t.w = *reinterpret_cast<uint32_t*>(&h);
+  *reinterpret_cast<uint4*>(p) = t;
+}
+__device__ __forceinline__ uint32_t dropout_keep8(uint32_t sf, uint64_t e8, uint32_t thresh) {
+  return dropout_keep2(sf, 4 * e8, thresh) | (dropout_keep2(sf, 4 * e8 + 1, thresh) << 2) |
+         (dropout_keep2(sf, 4 * e8 + 2, thresh) << 4) | (dropout_keep2(sf, 4 * e8 + 3, thresh) << 6);
+}
+
+constexpr int RPW = 2;      // rows per warp
+
+template <int NIT, typename TA, typename TR, typename TY>
+__global__ void __launch_bounds__(256)
+add_ln_fwd8_kernel(int M, int d, TA* __restrict__ a, const TR* __restrict__ res, int res_rows,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ rowscale,
+                   TY* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int write_sum,
+                   float p_drop, uint32_t thresh, uint64_t seed, const int* __restrict__ seed_dev, float eps) {
+  if (seed_dev) seed += (uint64_t)(*seed_dev) * 0x9E3779B97F4A7C15ull;
+  const uint32_t sf = seed_fold(seed);
+  const int lane = threadIdx.x & 31;
+  const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
+  if (row0 >= M) return;
+  const int nvec = d >> 3;
+  const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  float v[RPW][NIT][8];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    const int row = row0 + r;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int vi = it * 32 + lane;
+      if (row < M && vi < nvec) load8(a + (int64_t)row * d + vi * 8, v[r][it]);
+    }
+  }
+  float mean[RPW], rstd[RPW];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    const int row = row0 + r;
+    const TR* rrow = res ? res + (int64_t)(row % res_rows) * d : nullptr;
+    float sum = 0.f;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int vi = it * 32 + lane;
+      if (row < M && vi < nvec) {
+        if (p_drop > 0.f) {
+          const uint32_t keep = dropout_keep8(sf, (uint64_t)row * nvec + vi, thresh);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[r][it][j] = (keep >> j) & 1 ? v[r][it][j] * keep_scale : 0.f;
+        }
+        if (rrow) {
+          float rr[8];
+          load8(rrow + vi * 8, rr);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[r][it][j] += rr[j];
+        }
+        if (write_sum) store8(a + (int64_t)row * d + vi * 8, v[r][it]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += v[r][it][j];
+      }
+    }
+    mean[r] = warp_sum(sum) / (float)d;
+    float sq = 0.f;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int vi = it * 32 + lane;
+      if (row < M && vi < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float c = v[r][it][j] - mean[r]; sq += c * c; }
+      }
+    }
+    rstd[r] = rsqrtf(warp_sum(sq) / (float)d + eps);
+  }
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int vi = it * 32 + lane;
+    if (vi < nvec) {
+      float g[8], b[8];
+      load8(gamma + vi * 8, g);
+      load8(beta + vi * 8, b);
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) {
+        const int row = row0 + r;
+        if (row < M) {
+          const float rs = rowscale ? rowscale[row] : 1.f;
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = ((v[r][it][j] - mean[r]) * rstd[r] * g[j] + b[j]) * rs;
+          store8(y + (int64_t)row * d + vi * 8, o);
+        }
+      }
+    }
+  }
+  if (lane == 0 && mean_out) {
+#pragma unroll
+    for (int r = 0; r < RPW; ++r)
+      if (row0 + r < M) { mean_out[row0 + r] = mean[r]; rstd_out[row0 + r] = rstd[r]; }
+  }
+}
+
+template <int NIT, typename T>
+__global__ void __launch_bounds__(256)
+add_ln_bwd_rows8_kernel(int M, int d, const T* __restrict__ dy1, const T* __restrict__ dy2, const T* __restrict__ s,
+                        const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                        const float* __restrict__ gamma, const float* __restrict__ rowscale, T* __restrict__ ds,
+                        T* __restrict__ da, float p_drop, uint32_t thresh, uint64_t seed,
+                        const int* __restrict__ seed_dev) {
+  if (seed_dev) seed += (uint64_t)(*seed_dev) * 0x9E3779B97F4A7C15ull;
+  const uint32_t sf = seed_fold(seed);
+  const int lane = threadIdx.x & 31;
+  const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
+  if (row0 >= M) return;
+  const int nvec = d >> 3;
+  const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  float xh[RPW][NIT][8], gg[RPW][NIT][8];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    const int row = row0 + r;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int vi = it * 32 + lane;
+      if (row < M && vi < nvec) {
+        load8(dy1 + (int64_t)row * d + vi * 8, gg[r][it]);
+        load8(s + (int64_t)row * d + vi * 8, xh[r][it]);
+        if (dy2) {
+          float g2[8];
+          load8(dy2 + (int64_t)row * d + vi * 8, g2);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gg[r][it][j] += g2[j];
+        }
+      }
+    }
+  }
+  float s1[RPW], s2[RPW], rstd[RPW];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    const int row = min(row0 + r, M - 1);
+    const float mean = mean_in[row], rs = rowscale ? rowscale[row] : 1.f;
+    rstd[r] = rstd_in[row];
+    float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int vi = it * 32 + lane;
+      if (row0 + r < M && vi < nvec) {
+        float gam[8];
+        load8(gamma + vi * 8, gam);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xhat = (xh[r][it][j] - mean) * rstd[r];
+          const float gx = gg[r][it][j] * rs * gam[j];
+          xh[r][it][j] = xhat;
+          gg[r][it][j] = gx;
+          a1 += gx;
+          a2 += gx * xhat;
+        }
+      }
+    }
+    s1[r] = warp_sum(a1) / (float)d;
+    s2[r] = warp_sum(a2) / (float)d;
+  }
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    const int row = row0 + r;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int vi = it * 32 + lane;
+      if (row < M && vi < nvec) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rstd[r] * (gg[r][it][j] - s1[r] - xh[r][it][j] * s2[r]);
+        if (ds) store8(ds + (int64_t)row * d + vi * 8, o);
+        if (da) {
+          if (p_drop > 0.f) {
+            const uint32_t keep = dropout_keep8(sf, (uint64_t)row * nvec + vi, thresh);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = (keep >> j) & 1 ? o[j] * keep_scale : 0.f;
+          }
+          store8(da + (int64_t)row * d + vi * 8, o);
+        }
+      }
+    }
+  }
+}
+
+// block (32, 8): 256 columns (8 per thread, 16-byte loads) x 8 row lanes; grid (d/256, row splits)
+template <typename T>
+__global__ void __launch_bounds__(256)
+add_ln_bwd_cols8_kernel(int M, int d, const T* __restrict__ dy1, const T* __restrict__ dy2, const T* __restrict__ s,
+                        const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                        const float* __restrict__ rowscale, const T* __restrict__ dab, float* __restrict__ dgamma,
+                        float* __restrict__ dbeta, float* __restrict__ dbias2, int rows_per_block) {
+  __shared__ float red[3][8][256 + 8];
+  const int c = blockIdx.x * 256 + threadIdx.x * 8;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float ag[8], ab[8], ac[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { ag[j] = 0.f; ab[j] = 0.f; ac[j] = 0.f; }
+  if (c < d) {
+#pragma unroll 2
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      float g[8], x[8];
+      load8(dy1 + (int64_t)r * d + c, g);
+      load8(s + (int64_t)r * d + c, x);
+      if (dy2) {
+        float g2[8];
+        load8(dy2 + (int64_t)r * d + c, g2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] += g2[j];
+      }
+      const float mean = mean_in[r], rstd = rstd_in[r], rs = rowscale ? rowscale[r] : 1.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float gr = g[j] * rs;
+        ag[j] += gr * (x[j] - mean) * rstd;
+        ab[j] += gr;
+      }
+      if (dbias2) {
+        float a[8];
+        load8(dab + (int64_t)r * d + c, a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ac[j] += a[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[0][threadIdx.y][threadIdx.x * 8 + j] = ag[j];
+    red[1][threadIdx.y][threadIdx.x * 8 + j] = ab[j];
+    red[2][threadIdx.y][threadIdx.x * 8 + j] = ac[j];
+  }
+  __syncthreads();
+  const int t = threadIdx.y * 32 + threadIdx.x;      // one column per thread, three sums
+  if (blockIdx.x * 256 + t < d) {
+#pragma unroll
+    for (int which = 0; which < 3; ++which) {
+      float* dst = which == 0 ? dgamma : which == 1 ? dbeta : dbias2;
+      if (!dst) continue;
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc += red[which][i][t];
+      atomicAdd(dst + blockIdx.x * 256 + t, acc);
+    }
+  }
+}
+
+inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
 }  // namespace
 
 extern "C" int icap_add_ln_fwd(int a_dtype, int act_dtype, int64_t M, int64_t d, void* a, const void* res,
@@ -226,6 +497,28 @@ extern "C" int icap_add_ln_fwd(int a_dtype, int act_dtype, int64_t M, int64_t d,
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((unsigned)ceil_div64(M, 8));
   const uint32_t th = dropout_threshold(p_drop);
+  if (d % 8 == 0 && aligned16(a) && aligned16(res) && aligned16(y) && aligned16(gamma) && aligned16(beta) &&
+      !getenv("ICAP_LN_NARROW")) {
+    dim3 grid8((unsigned)ceil_div64(M, 8 * RPW));
+#define GO8(NIT, TA, TR, TY)                                                                                      \
+  add_ln_fwd8_kernel<NIT, TA, TR, TY><<<grid8, 256, 0, st>>>((int)M, (int)d, (TA*)a, (const TR*)res,             \
+                                                             (int)res_rows, gamma, beta, rowscale, (TY*)y,       \
+                                                             mean_out, rstd_out, write_sum, p_drop, th, seed, seed_dev, eps)
+#define GOT8(TA, TR, TY)                                                                                          \
+  do {                                                                                                            \
+    if (d <= 256) GO8(1, TA, TR, TY);                                                                             \
+    else if (d <= 512) GO8(2, TA, TR, TY);                                                                        \
+    else GO8(4, TA, TR, TY);                                                                                      \
+  } while (0)
+    if (a_dtype == ICAP_F32 && act_dtype == ICAP_F32) GOT8(float, float, float);
+    else if (a_dtype == ICAP_BF16 && act_dtype == ICAP_BF16) GOT8(bf16, bf16, bf16);
+    else if (a_dtype == ICAP_F32 && act_dtype == ICAP_BF16) GOT8(float, bf16, bf16);
+    else ICAP_ARG(false, "icap_add_ln_fwd: unsupported dtype combination a=%d act=%d", a_dtype, act_dtype);
+#undef GOT8
+#undef GO8
+    ICAP_LAUNCH_CHECK("icap_add_ln_fwd");
+    return 0;
+  }
 #define GO1(NIT, TA, TR, TY)                                                                                      \
   add_ln_fwd_kernel<NIT, TA, TR, TY><<<grid, 256, 0, st>>>((int)M, (int)d, (TA*)a, (const TR*)res,               \
                                                             (int)res_rows, gamma, beta, rowscale, (TY*)y,        \
@@ -264,6 +557,37 @@ extern "C" int icap_add_ln_bwd(int act_dtype, int64_t M, int64_t d, const void* 
   dim3 cgrid((unsigned)col_blocks, (unsigned)ceil_div64(M, rows_per_block)), cblock(32, 8);
   const void* dab = da ? da : ds;       // dbias2 sums the GEMM-branch gradient
   ICAP_ARG(dbias2 == nullptr || dab != nullptr, "icap_add_ln_bwd: dbias2 needs ds or da");
+  if (d % 8 == 0 && aligned16(dy1) && aligned16(dy2) && aligned16(s) && aligned16(ds) && aligned16(da) &&
+      aligned16(gamma) && !getenv("ICAP_LN_NARROW")) {
+    const unsigned row_blocks8 = (unsigned)ceil_div64(M, 8 * RPW);
+    const int64_t col_blocks8 = ceil_div64(d, 256);
+    int64_t splits8 = ceil_div64(148 * 3, col_blocks8);
+    if (splits8 > ceil_div64(M, 16)) splits8 = ceil_div64(M, 16);
+    const int rpb8 = (int)ceil_div64(M, splits8);
+    dim3 cgrid8((unsigned)col_blocks8, (unsigned)ceil_div64(M, rpb8));
+#define GOB8(NIT, T)                                                                                              \
+  add_ln_bwd_rows8_kernel<NIT, T><<<row_blocks8, 256, 0, st>>>((int)M, (int)d, (const T*)dy1, (const T*)dy2,      \
+                                                               (const T*)s, mean, rstd, gamma, rowscale, (T*)ds, \
+                                                               (T*)da, p_drop, th, seed, seed_dev)
+#define GOBT8(T)                                                                                                  \
+  do {                                                                                                            \
+    if (ds || da) {                                                                                               \
+      if (d <= 256) GOB8(1, T);                                                                                   \
+      else if (d <= 512) GOB8(2, T);                                                                              \
+      else GOB8(4, T);                                                                                            \
+    }                                                                                                             \
+    if (dgamma || dbeta || dbias2)                                                                                \
+      add_ln_bwd_cols8_kernel<T><<<cgrid8, cblock, 0, st>>>((int)M, (int)d, (const T*)dy1, (const T*)dy2,         \
+                                                            (const T*)s, mean, rstd, rowscale, (const T*)dab,    \
+                                                            dgamma, dbeta, dbias2, rpb8);                        \
+  } while (0)
+    if (act_dtype == ICAP_F32) GOBT8(float);
+    else GOBT8(bf16);
+#undef GOBT8
+#undef GOB8
+    ICAP_LAUNCH_CHECK("icap_add_ln_bwd");
+    return 0;
+  }
 #define GOB(NIT, T)                                                                                               \
   add_ln_bwd_rows_kernel<NIT, T><<<row_blocks, 256, 0, st>>>((int)M, (int)d, (const T*)dy1, (const T*)dy2,        \
                                                              (const T*)s, mean, rstd, gamma, rowscale, (T*)ds,   \

@@ -161,6 +161,7 @@ class CaptionEngine:
         self.one = torch.ones(1, dtype=torch.float32, device=self.dev)
         self.dp_unnormalized = False     # data parallel: dlogits are NOT divided by the local token count
         self._prof = None
+        self._gemm_log: Optional[List[tuple]] = None     # bench: argument tuples of every GEMM launch of a step
         self.p16 = torch.empty(self.n_flat, dtype=torch.bfloat16, device=self.dev) if precision == "bf16" else None
         self.shadow_fresh = False
         self.adam_m: Optional[torch.Tensor] = None
@@ -236,11 +237,14 @@ class CaptionEngine:
         ab = BF16 if self.precision == "bf16" else F32
         if c_dtype is None:
             c_dtype = F32 if out.dtype == torch.float32 else BF16
+        args = (ab, int(a_kmajor), int(b_kmajor), M, Nn, K,
+                a.data_ptr() if a_ptr is None else a_ptr, a.shape[-1] if lda is None else lda, b_ptr, ldb,
+                out.data_ptr() if c_ptr is None else c_ptr, (out.shape[-1] if ldc is None else ldc), c_dtype,
+                bias, epi, _ptr(aux), (aux.shape[-1] if aux is not None else 0), int(accumulate), split_k)
+        if self._gemm_log is not None:
+            self._gemm_log.append(args)
         ev = self._prof_begin()
-        call("icap_gemm", ab, int(a_kmajor), int(b_kmajor), M, Nn, K,
-             a.data_ptr() if a_ptr is None else a_ptr, a.shape[-1] if lda is None else lda, b_ptr, ldb,
-             out.data_ptr() if c_ptr is None else c_ptr, (out.shape[-1] if ldc is None else ldc), c_dtype,
-             bias, epi, _ptr(aux), (aux.shape[-1] if aux is not None else 0), int(accumulate), split_k, self._s())
+        call("icap_gemm", *args, self._s())
         self._prof_end(ev, 2.0 * M * Nn * K)
 
     def wgrad(self, dy: torch.Tensor, x: torch.Tensor, g_ptr: int, Nout: int, Kin: int, rows: int,
@@ -253,11 +257,14 @@ class CaptionEngine:
         else:
             tiles = ((Nout + 127) // 128) * ((Kin + 127) // 128)
             split = max(1, min(32, (148 * 2) // max(1, tiles), (rows + 511) // 512))
+        args = (ab, 0, 0, Nout, Kin, rows, dy.data_ptr() if dy_ptr is None else dy_ptr,
+                dy.shape[-1] if ld_dy is None else ld_dy, x.data_ptr() if x_ptr is None else x_ptr,
+                x.shape[-1] if ldx is None else ldx, g_ptr, Kin if ldg is None else ldg,
+                F32, None, 0, None, 0, 1, split)
+        if self._gemm_log is not None:
+            self._gemm_log.append(args)
         ev = self._prof_begin()
-        call("icap_gemm", ab, 0, 0, Nout, Kin, rows, dy.data_ptr() if dy_ptr is None else dy_ptr,
-             dy.shape[-1] if ld_dy is None else ld_dy, x.data_ptr() if x_ptr is None else x_ptr,
-             x.shape[-1] if ldx is None else ldx, g_ptr, Kin if ldg is None else ldg,
-             F32, None, 0, None, 0, 1, split, self._s())
+        call("icap_gemm", *args, self._s())
         self._prof_end(ev, 2.0 * Nout * Kin * rows)
 
     def _prof_begin(self):
@@ -283,6 +290,22 @@ class CaptionEngine:
             return [(a.elapsed_time(b), fl) for a, b, fl in self._prof]
         finally:
             self._prof = None
+
+    def record_gemms(self, fn) -> "List[tuple]":
+        """Run fn() and return the icap_gemm argument tuple of every GEMM it launched (bench: the GEMM-only graph)."""
+        self._gemm_log = []
+        try:
+            fn()
+            return self._gemm_log
+        finally:
+            self._gemm_log = None
+
+    def replay_gemms(self, log: "List[tuple]") -> float:
+        """Re-launch recorded GEMMs on the current stream (timing only: outputs land in recycled activation
+        memory); returns their total FLOPs."""
+        for args in log:
+            call("icap_gemm", *args, self._s())
+        return sum(2.0 * a[3] * a[4] * a[5] for a in log)
 
     def add_ln(self, a: torch.Tensor, res: Optional[torch.Tensor], res_rows: int, norm: str,
                rowscale: Optional[torch.Tensor], p_drop: float):

@@ -143,6 +143,7 @@ class Transformer(nn.Module):
                 _set_nested(self, name, nn.Parameter(view), is_buffer=False)
         self._init_parameters()
         self._eng: Optional[CaptionEngine] = None
+        self._decode_graphs: dict = {}
 
     # ------------------------------------------------------------------ init (SURVEY.md §8a "Initialisation")
     @torch.no_grad()
@@ -184,6 +185,7 @@ class Transformer(nn.Module):
             q.grad = None
         self._flat = flat
         self._eng = None
+        self._decode_graphs = {}
         if any_p.is_cuda:
             self.device = any_p.device
 
@@ -199,6 +201,7 @@ class Transformer(nn.Module):
         assert precision in ("bf16", "fp32")
         if precision != self.precision:
             self.precision, self._eng = precision, None
+            self._decode_graphs = {}
         return self
 
     def _engine(self) -> CaptionEngine:
@@ -227,12 +230,30 @@ class Transformer(nn.Module):
         B, T = c.shape[0], c.shape[1] - 1
         return lg[:, :self.num_vocab].float().view(B, T, self.num_vocab)
 
+    def _decode(self, f, p, beam_size: int, log_domain: bool, want_attention: bool):
+        """KV-cached decode of one batch; the whole fixed-trip-count loop (encoder + max_length-1 steps, ~2000
+        launches) is ONE CUDA graph per (batch, regions, beam) shape unless ICAP_DECODE_GRAPH=0."""
+        eng = self._engine()
+        eng.shadow_fresh = False                       # an external optimizer may have stepped the fp32 weights
+        if os.environ.get("ICAP_DECODE_GRAPH", "1") == "0":
+            return eng.decode(f, p, beam_size=beam_size, log_domain=log_domain, want_attention=want_attention,
+                              want_gaps=True)
+        key = (f.shape[0], f.shape[1], int(beam_size), bool(log_domain), bool(want_attention), id(eng))
+        gd = self._decode_graphs.get(key)
+        if gd is None:
+            if len(self._decode_graphs) >= 4:          # each graph owns its KV-cache pool: keep only a few shapes
+                self._decode_graphs.pop(next(iter(self._decode_graphs)))
+            gd = GraphedDecode(self, f.shape[0], f.shape[1], beam_size, log_domain=log_domain,
+                               want_attention=want_attention, want_gaps=True)
+            self._decode_graphs[key] = gd
+        return gd.run(f, p)
+
     def generate_caption_vector(self, object_features, position_features):
         """model.py:101-132 -> (LongTensor [B, max_length+1], list of max_length-1 float32 arrays [B, R])."""
         with torch.no_grad():
             eng = self._engine()
             f, p, _ = eng.prepare_inputs(object_features, position_features)
-            out = eng.decode(f, p, beam_size=1, want_attention=True, want_gaps=True)
+            out = self._decode(f, p, 1, False, True)
             B = f.shape[0]
             ids = torch.zeros(B, self.max_length + 1, dtype=torch.long, device=f.device)
             ids[:, :self.max_length] = out["ids"].long()
@@ -246,7 +267,7 @@ class Transformer(nn.Module):
         with torch.no_grad():
             eng = self._engine()
             f, p, _ = eng.prepare_inputs(object_features, position_features)
-            out = eng.decode(f, p, beam_size=int(beam_size), log_domain=self.log_domain_beam, want_gaps=True)
+            out = self._decode(f, p, int(beam_size), self.log_domain_beam, False)
             self.last_gaps = out["gaps"]
             return out["ids"].long().contiguous()
 
@@ -296,6 +317,49 @@ class DataParallel:
         from ._native import call
         call("icap_reciprocal", eng.g32.data_ptr() + 4 * eng.n_flat, self.inv.data_ptr(), 1.0, eng._s())
         eng.adam_step(lr, gscale_dev=self.inv)
+
+
+class GraphedDecode:
+    """The complete KV-cached greedy / beam decode of a fixed (batch, regions, beam) shape as ONE CUDA graph:
+    encoder, cross-K/V projection, and all max_length-1 steps (the reference's loops have a fixed trip count and
+    no EOS exit, model.py:114,169).  Replays cost one launch instead of ~2000 ctypes calls."""
+
+    def __init__(self, model: Transformer, batch: int, regions: int, beam_size: int, log_domain: bool = False,
+                 want_attention: bool = False, want_gaps: bool = False):
+        eng = model._engine()
+        cfg = model.cfg
+        self.eng = eng
+        self.kw = dict(beam_size=int(beam_size), log_domain=log_domain, want_attention=want_attention,
+                       want_gaps=want_gaps)
+        self.feats = torch.zeros(batch, regions, cfg.encode_dim_features, device=eng.dev)
+        self.pos = torch.zeros(batch, regions, cfg.encode_dim_positions, device=eng.dev)
+        self.pos[:, :, 2:4] = 1.0                      # placeholder keeps every region "valid" during warm-up
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.out = None
+
+    def capture(self) -> None:
+        eng = self.eng
+        with torch.no_grad():
+            side = torch.cuda.Stream(device=eng.dev)
+            side.wait_stream(torch.cuda.current_stream(eng.dev))
+            with torch.cuda.stream(side):
+                eng.decode(self.feats, self.pos, **self.kw)            # warm-up: function attributes, allocator
+            torch.cuda.current_stream(eng.dev).wait_stream(side)
+            torch.cuda.synchronize(eng.dev)
+            eng.refresh_shadow()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = eng.decode(self.feats, self.pos, **self.kw)
+
+    def run(self, feats: torch.Tensor, pos: torch.Tensor):
+        """Returns the engine's output dict (static device tensors, overwritten by the next run)."""
+        if self.graph is None:
+            self.capture()
+        self.feats.copy_(feats, non_blocking=True)
+        self.pos.copy_(pos, non_blocking=True)
+        self.eng.refresh_shadow()                      # weights may have been stepped since the capture
+        self.graph.replay()
+        return self.out
 
 
 class GraphedTrainStep:

@@ -526,6 +526,13 @@ def test_embed_colsum_adam():
     cs = torch.ones(77, device=dev())
     N.call("icap_colsum", F32, 1000, 77, x.data_ptr(), 77, cs.data_ptr(), S())
     assert torch.allclose(cs, x.sum(0) + 1, atol=1e-3)
+    # 16-byte path (N % 8 == 0), bf16 and fp32, padded leading dimension
+    for tdt, code, tol in ((torch.float32, F32, 1e-3), (torch.bfloat16, BF16, 2e-2)):
+        xw = torch.randn(3001, 520, device=dev(), generator=g).to(tdt)
+        cw = torch.ones(512, device=dev())
+        N.call("icap_colsum", code, 3001, 512, xw.data_ptr(), 520, cw.data_ptr(), S())
+        ref_w = xw[:, :512].float().sum(0) + 1
+        assert float((cw - ref_w).abs().max()) < tol * float(ref_w.abs().max())
     # Adam vs torch.optim.Adam for 3 steps
     n = 4096
     p = torch.randn(n, device=dev(), generator=g)
