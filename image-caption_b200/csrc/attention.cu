@@ -114,6 +114,7 @@ mha_fwd_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, in
                int64_t ldv, T* __restrict__ o, int64_t ldo, const uint8_t* __restrict__ kvalid, AttnDims D, int causal,
                float p_drop, uint32_t thresh, uint64_t seed, const int* __restrict__ seed_dev,
                float* __restrict__ attn_mean) {
+  pdl_prologue();
   if (seed_dev) seed += (uint64_t)(*seed_dev) * 0x9E3779B97F4A7C15ull;
   extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.x / D.H, h = blockIdx.x % D.H;
@@ -157,6 +158,7 @@ mha_bwd_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, in
                T* __restrict__ dk_, int64_t lddk, T* __restrict__ dv_, int64_t lddv,
                const uint8_t* __restrict__ kvalid, AttnDims D, int causal, float p_drop, uint32_t thresh,
                uint64_t seed, const int* __restrict__ seed_dev) {
+  pdl_prologue();
   if (seed_dev) seed += (uint64_t)(*seed_dev) * 0x9E3779B97F4A7C15ull;
   extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.x / D.H, h = blockIdx.x % D.H;
@@ -276,6 +278,7 @@ mha_decode_kernel(int rows, int H, int Lk, int dk, int dv, const T* __restrict__
                   T* __restrict__ o, int64_t ldo, const int* __restrict__ slot, int64_t slot_ld,
                   const int* __restrict__ tokens, int64_t tok_ld, int pad_idx, const uint8_t* __restrict__ kvalid,
                   int rows_per_image, float* __restrict__ attn_mean) {
+  pdl_prologue();
   extern __shared__ __align__(16) float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int unit = blockIdx.x * (NT / 32) + warp;
@@ -406,6 +409,7 @@ mha_decode64_kernel(int groups, int H, int Lk, const T* __restrict__ q, int64_t 
                     int64_t ldk, const T* __restrict__ vc, int64_t ldv, int kv_rows_per_seq, T* __restrict__ o,
                     int64_t ldo, const int* __restrict__ slot, int64_t slot_ld, const int* __restrict__ tokens,
                     int64_t tok_ld, int pad_idx, const uint8_t* __restrict__ kvalid, float* __restrict__ attn_mean) {
+  pdl_prologue();
   __shared__ float ps[DEC_WARPS][G][DEC_LK];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int unit = blockIdx.x * DEC_WARPS + warp;
@@ -556,7 +560,7 @@ int launch_decode64(int64_t groups, int64_t H, int64_t Lk, const void* q, int64_
                     int64_t slot_ld, const int* tokens, int64_t tok_ld, int pad_idx, const uint8_t* kvalid,
                     float* attn_mean, cudaStream_t st) {
   const unsigned grid = (unsigned)ceil_div64(groups * H, DEC_WARPS);
-  mha_decode64_kernel<T, G><<<grid, DEC_WARPS * 32, 0, st>>>(
+  icap_launch(mha_decode64_kernel<T, G>, grid, DEC_WARPS * 32, 0, st, 
       (int)groups, (int)H, (int)Lk, (const T*)q, ldq, (const T*)kc, ldk, (const T*)vc, ldv, (int)kv_rows_per_seq, (T*)o,
       ldo, slot, slot_ld, tokens, tok_ld, pad_idx, kvalid, attn_mean);
   ICAP_LAUNCH_CHECK("icap_mha_decode(64)");
@@ -591,13 +595,13 @@ extern "C" int icap_mha_fwd(int dtype, int64_t B, int64_t H, int64_t Lq, int64_t
   if (dtype == ICAP_F32) {
     static size_t cur = 48 * 1024;
     if (int rc = ensure_smem(mha_fwd_kernel<float>, smem, &cur)) return rc;
-    mha_fwd_kernel<float><<<(unsigned)(B * H), NT, smem, st>>>((const float*)q, ldq, (const float*)k, ldk,
+    icap_launch(mha_fwd_kernel<float>, (unsigned)(B * H), NT, smem, st, (const float*)q, ldq, (const float*)k, ldk,
                                                                (const float*)v, ldv, (float*)o, ldo, kvalid, D, causal,
                                                                p_drop, th, seed, seed_dev, attn_mean);
   } else {
     static size_t cur = 48 * 1024;
     if (int rc = ensure_smem(mha_fwd_kernel<bf16>, smem, &cur)) return rc;
-    mha_fwd_kernel<bf16><<<(unsigned)(B * H), NT, smem, st>>>((const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v,
+    icap_launch(mha_fwd_kernel<bf16>, (unsigned)(B * H), NT, smem, st, (const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v,
                                                               ldv, (bf16*)o, ldo, kvalid, D, causal, p_drop, th, seed,
                                                               seed_dev, attn_mean);
   }
@@ -626,13 +630,13 @@ extern "C" int icap_mha_bwd(int dtype, int64_t B, int64_t H, int64_t Lq, int64_t
   if (dtype == ICAP_F32) {
     static size_t cur = 48 * 1024;
     if (int rc = ensure_smem(mha_bwd_kernel<float>, smem, &cur)) return rc;
-    mha_bwd_kernel<float><<<(unsigned)(B * H), NT, smem, st>>>(
+    icap_launch(mha_bwd_kernel<float>, (unsigned)(B * H), NT, smem, st, 
         (const float*)q, ldq, (const float*)k, ldk, (const float*)v, ldv, (const float*)dout, lddo, (float*)dq, lddq,
         (float*)dk_out, lddk, (float*)dv_out, lddv, kvalid, D, causal, p_drop, th, seed, seed_dev);
   } else {
     static size_t cur = 48 * 1024;
     if (int rc = ensure_smem(mha_bwd_kernel<bf16>, smem, &cur)) return rc;
-    mha_bwd_kernel<bf16><<<(unsigned)(B * H), NT, smem, st>>>(
+    icap_launch(mha_bwd_kernel<bf16>, (unsigned)(B * H), NT, smem, st, 
         (const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v, ldv, (const bf16*)dout, lddo, (bf16*)dq, lddq,
         (bf16*)dk_out, lddk, (bf16*)dv_out, lddv, kvalid, D, causal, p_drop, th, seed, seed_dev);
   }
@@ -683,12 +687,12 @@ extern "C" int icap_mha_decode(int dtype, int64_t rows, int64_t H, int64_t Lk, i
   const size_t smem = (NT / 32) * dk * sizeof(float);
   const unsigned grid = (unsigned)ceil_div64(rows * H, NT / 32);
   if (dtype == ICAP_F32)
-    mha_decode_kernel<float><<<grid, NT, smem, st>>>((int)rows, (int)H, (int)Lk, (int)dk, (int)dv, (const float*)q, ldq,
+    icap_launch(mha_decode_kernel<float>, grid, NT, smem, st, (int)rows, (int)H, (int)Lk, (int)dk, (int)dv, (const float*)q, ldq,
                                                      (const float*)kc, ldk, (const float*)vc, ldv,
                                                      (int)kv_rows_per_seq, (float*)o, ldo, slot, slot_ld, tokens,
                                                      tok_ld, pad_idx, kvalid, (int)rows_per_image, attn_mean);
   else
-    mha_decode_kernel<bf16><<<grid, NT, smem, st>>>((int)rows, (int)H, (int)Lk, (int)dk, (int)dv, (const bf16*)q, ldq,
+    icap_launch(mha_decode_kernel<bf16>, grid, NT, smem, st, (int)rows, (int)H, (int)Lk, (int)dk, (int)dv, (const bf16*)q, ldq,
                                                     (const bf16*)kc, ldk, (const bf16*)vc, ldv, (int)kv_rows_per_seq,
                                                     (bf16*)o, ldo, slot, slot_ld, tokens, tok_ld, pad_idx, kvalid,
                                                     (int)rows_per_image, attn_mean);

@@ -182,6 +182,7 @@ mha_fwd_mma_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* __restri
                    const bf16* __restrict__ v, int64_t ldv, bf16* __restrict__ o, int64_t ldo,
                    const uint8_t* __restrict__ kvalid, int H, int Lq, int Lk, int causal, float p_drop, uint32_t thresh,
                    uint64_t seed, const int* __restrict__ seed_dev) {
+  pdl_prologue();
   extern __shared__ __align__(128) uint8_t smem[];
   if (seed_dev) seed += (uint64_t)(*seed_dev) * 0x9E3779B97F4A7C15ull;
   const int b = blockIdx.x / H, h = blockIdx.x % H;
@@ -217,6 +218,7 @@ mha_bwd_mma_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* __restri
                    bf16* __restrict__ dq, int64_t lddq, bf16* __restrict__ dk_, int64_t lddk, bf16* __restrict__ dv_,
                    int64_t lddv, const uint8_t* __restrict__ kvalid, int H, int Lq, int Lk, int causal, float p_drop,
                    uint32_t thresh, uint64_t seed, const int* __restrict__ seed_dev) {
+  pdl_prologue();
   extern __shared__ __align__(128) uint8_t smem[];
   if (seed_dev) seed += (uint64_t)(*seed_dev) * 0x9E3779B97F4A7C15ull;
   const int b = blockIdx.x / H, h = blockIdx.x % H;
@@ -348,7 +350,7 @@ int icap_mha_fwd_mma(int64_t B, int64_t H, int64_t Lq, int64_t Lk, const void* q
     static size_t cur = 48 * 1024;                                                                                 \
     const size_t smem = (size_t)(LqP + 2 * NT * 8) * ROWB;                                                         \
     if (int rc = ensure_smem(mha_fwd_mma_kernel<NT>, smem, &cur)) return rc;                                       \
-    mha_fwd_mma_kernel<NT><<<(unsigned)(B * H), nthreads, smem, st>>>(                                             \
+    icap_launch(mha_fwd_mma_kernel<NT>, (unsigned)(B * H), nthreads, smem, st,                                              \
         (const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v, ldv, (bf16*)o, ldo, kvalid, (int)H, (int)Lq,     \
         (int)Lk, causal, p_drop, th, seed, seed_dev);                                                              \
   }
@@ -370,7 +372,7 @@ int icap_mha_bwd_mma(int64_t B, int64_t H, int64_t Lq, int64_t Lk, const void* q
     static size_t cur = 48 * 1024;                                                                                 \
     const size_t smem = (size_t)(2 * LqP + 2 * NT * 8) * ROWB + 2 * (size_t)LqP * (NT * 16 + 16);                  \
     if (int rc = ensure_smem(mha_bwd_mma_kernel<NT>, smem, &cur)) return rc;                                       \
-    mha_bwd_mma_kernel<NT><<<(unsigned)(B * H), nthreads, smem, st>>>(                                             \
+    icap_launch(mha_bwd_mma_kernel<NT>, (unsigned)(B * H), nthreads, smem, st,                                              \
         (const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v, ldv, (const bf16*)dout, lddo, (bf16*)dq, lddq,   \
         (bf16*)dk_out, lddk, (bf16*)dv_out, lddv, kvalid, (int)H, (int)Lq, (int)Lk, causal, p_drop, th, seed,      \
         seed_dev);                                                                                                 \

@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(NT)
 gemm_f32_kernel(int M, int N, int K, const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
                 int64_t ldb, float* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int epi,
                 const float* __restrict__ aux, int64_t ldaux, int accumulate, int kchunk, int vecA, int vecB) {
+  pdl_prologue();
   __shared__ __align__(16) float As[2][BK][BM + PAD];
   __shared__ __align__(16) float Bs[2][BK][BN + PAD];
   const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
@@ -159,7 +160,7 @@ int icap_gemm_f32_launch(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64
   int vecB = ((uintptr_t)B % 16 == 0) && (ldb % 4 == 0);
   dim3 grid((unsigned)ceil_div64(N, BN), (unsigned)ceil_div64(M, BM), (unsigned)split_k);
 #define LAUNCH(AK, BKM)                                                                                            \
-  gemm_f32_kernel<AK, BKM><<<grid, NT, 0, st>>>((int)M, (int)N, (int)K, A, lda, B, ldb, C, ldc, bias, epi, aux, \
+  icap_launch(gemm_f32_kernel<AK, BKM>, grid, NT, 0, st, (int)M, (int)N, (int)K, A, lda, B, ldb, C, ldc, bias, epi, aux, \
                                                 ldaux, accumulate, kchunk, vecA, vecB)
   if (a_kmajor && b_kmajor) LAUNCH(true, true);
   else if (a_kmajor && !b_kmajor) LAUNCH(true, false);

@@ -146,8 +146,6 @@ template <> struct OutVec<bf16> {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // 32 consecutive elements of the ReLU-mask operand (aux) of one row, as raw 16-byte words
 template <typename TO> struct AuxRow { uint4 w[32 * sizeof(TO) / 16]; };
@@ -226,7 +224,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();        // everything above overlaps the previous kernel's tail when launched with PDL
+  pdl_prologue();    // everything above overlaps the previous kernel's tail when launched with PDL
 
   if (warp == 0) {
     if (lane == 0) {
@@ -286,7 +284,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         umma_commit(tfull_bar + 8 * as);       // accumulator complete
       }
-      pdl_launch_dependents();
     }
   } else {
     // ---------------------------------------------------------------- epilogue warps
@@ -466,7 +463,6 @@ int make_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int6
 }
 
 int g_num_sms = 0;
-int g_pdl = 0;         // launch with programmatic stream serialization (icap_set_pdl)
 
 int num_sms() {
   if (g_num_sms == 0) {
@@ -490,17 +486,8 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
     attr_done = true;
   }
   const int total = g.tiles_m * g.tiles_n * g.splits;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(total < num_sms() ? total : num_sms()), 1, 1);
-  cfg.blockDim = dim3(NTHREADS, 1, 1);
-  cfg.dynamicSmemBytes = Cfg<BN>::SMEM_BYTES;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = g_pdl ? 1 : 0;
-  ICAP_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, g));
+  ICAP_CUDA(icap_launch(kern, dim3((unsigned)(total < num_sms() ? total : num_sms())), dim3(NTHREADS),
+                        (size_t)Cfg<BN>::SMEM_BYTES, st, ta, tb, tc, g));
   return 0;
 }
 
@@ -515,7 +502,6 @@ double est_cost(int64_t tiles, int nkb, int bn, int sms) {
 
 }  // namespace
 
-extern "C" int icap_set_pdl(int on) { g_pdl = on ? 1 : 0; return 0; }
 
 int icap_gemm_bf16_launch(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
                           const void* B, int64_t ldb, void* C, int64_t ldc, int c_dtype, const float* bias, int epi,

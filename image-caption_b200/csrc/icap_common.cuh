@@ -37,6 +37,32 @@ void icap_set_error(const char* fmt, ...);
     }                                                                         \
   } while (0)
 
+// ---- launches: every kernel goes through icap_launch so that programmatic dependent launch (PDL) can be
+// switched on for the whole library (icap_set_pdl).  Kernels call pdl_wait() before touching global memory
+// and pdl_launch_dependents() right after it: the next kernel's CTAs become resident (and run their own
+// prologue) while this one is still working, and start the moment this grid has completed and flushed.
+extern int icap_g_pdl;
+template <typename... KArgs, typename... Args>
+static inline cudaError_t icap_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                      Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = icap_g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() { pdl_wait(); pdl_launch_dependents(); }
+#endif
+
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- dtype helpers -----------------------------------------------------------------------------

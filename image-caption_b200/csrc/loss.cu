@@ -39,6 +39,7 @@ template <typename T>
 __global__ void __launch_bounds__(NT)
 xent_kernel(int V, T* __restrict__ logits, int64_t ldl, const int* __restrict__ targets, int ignore_index,
             const float* __restrict__ inv_count, float* __restrict__ row_loss, int write_grad, int cached, int vec) {
+  pdl_prologue();
   extern __shared__ __align__(16) float xs[];
   __shared__ float red[NT / 32];
   const int row = blockIdx.x;
@@ -89,6 +90,7 @@ xent_kernel(int V, T* __restrict__ logits, int64_t ldl, const int* __restrict__ 
 __global__ void __launch_bounds__(NT)
 xent_finalize_kernel(int M, const float* __restrict__ row_loss, const float* __restrict__ inv_count, int focal,
                      float* __restrict__ out) {
+  pdl_prologue();
   __shared__ float red[NT / 32];
   float s = 0.f;
   for (int i = threadIdx.x; i < M; i += NT) s += row_loss[i];
@@ -132,6 +134,7 @@ template <typename T>
 __global__ void __launch_bounds__(NT)
 argmax_kernel(int V, const T* __restrict__ logits, int64_t ldl, int* __restrict__ out, int64_t out_stride,
               float* __restrict__ gap) {
+  pdl_prologue();
   __shared__ float sv[NT], sv2[NT];
   __shared__ int si[NT];
   const T* x = logits + (int64_t)blockIdx.x * ldl;
@@ -180,6 +183,7 @@ __global__ void __launch_bounds__(NT)
 beam_select_kernel(int kin, int V, const T* __restrict__ logits, int64_t ldl, const float* __restrict__ prev,
                    int kout, float* __restrict__ out_score, int* __restrict__ out_parent, int* __restrict__ out_token,
                    float* __restrict__ gap, int log_domain) {
+  pdl_prologue();
   __shared__ float red[NT / 32];
   __shared__ float s_mx[KMAX], s_den[KMAX];
   __shared__ float h_s[NT];
@@ -298,6 +302,7 @@ __global__ void beam_reorder_kernel(int B, int k, int Tmax, int t, const int* __
                                     const int* __restrict__ token, const int* __restrict__ tok_in,
                                     int* __restrict__ tok_out, const int* __restrict__ slot_in,
                                     int* __restrict__ slot_out) {
+  pdl_prologue();
   const int row = blockIdx.x;            // b*k + s
   const int b = row / k;
   const int src = b * k + parent[row];
@@ -324,14 +329,14 @@ extern "C" int icap_xent(int dtype, int64_t M, int64_t V, void* logits, int64_t 
       ICAP_CUDA(cudaFuncSetAttribute(xent_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       cur_f = smem;
     }
-    xent_kernel<float><<<(unsigned)M, NT, smem, st>>>((int)V, (float*)logits, ldl, targets, ignore_index, inv_count,
+    icap_launch(xent_kernel<float>, (unsigned)M, NT, smem, st, (int)V, (float*)logits, ldl, targets, ignore_index, inv_count,
                                                       row_loss, write_grad, cached, vec);
   } else {
     if (smem > cur_b) {
       ICAP_CUDA(cudaFuncSetAttribute(xent_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       cur_b = smem;
     }
-    xent_kernel<bf16><<<(unsigned)M, NT, smem, st>>>((int)V, (bf16*)logits, ldl, targets, ignore_index, inv_count,
+    icap_launch(xent_kernel<bf16>, (unsigned)M, NT, smem, st, (int)V, (bf16*)logits, ldl, targets, ignore_index, inv_count,
                                                      row_loss, write_grad, cached, vec);
   }
   ICAP_LAUNCH_CHECK("icap_xent");
@@ -341,7 +346,7 @@ extern "C" int icap_xent(int dtype, int64_t M, int64_t V, void* logits, int64_t 
 extern "C" int icap_xent_finalize(int64_t M, const float* row_loss, const float* inv_count, int focal, float* out2,
                                   void* stream) {
   ICAP_ARG(M > 0 && row_loss && inv_count && out2, "icap_xent_finalize: null/empty argument");
-  xent_finalize_kernel<<<1, NT, 0, (cudaStream_t)stream>>>((int)M, row_loss, inv_count, focal, out2);
+  icap_launch(xent_finalize_kernel, 1, NT, 0, (cudaStream_t)stream, (int)M, row_loss, inv_count, focal, out2);
   ICAP_LAUNCH_CHECK("icap_xent_finalize");
   return 0;
 }
@@ -350,8 +355,8 @@ extern "C" int icap_argmax(int dtype, int64_t M, int64_t V, const void* logits, 
                            int64_t out_stride, float* gap, void* stream) {
   ICAP_ARG(M > 0 && V > 0 && logits && out, "icap_argmax: null/empty argument");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == ICAP_F32) argmax_kernel<float><<<(unsigned)M, NT, 0, st>>>((int)V, (const float*)logits, ldl, out, out_stride, gap);
-  else argmax_kernel<bf16><<<(unsigned)M, NT, 0, st>>>((int)V, (const bf16*)logits, ldl, out, out_stride, gap);
+  if (dtype == ICAP_F32) icap_launch(argmax_kernel<float>, (unsigned)M, NT, 0, st, (int)V, (const float*)logits, ldl, out, out_stride, gap);
+  else icap_launch(argmax_kernel<bf16>, (unsigned)M, NT, 0, st, (int)V, (const bf16*)logits, ldl, out, out_stride, gap);
   ICAP_LAUNCH_CHECK("icap_argmax");
   return 0;
 }
@@ -364,10 +369,10 @@ extern "C" int icap_beam_select(int dtype, int64_t B, int64_t kin, int64_t V, co
   ICAP_ARG(kin * V > kout, "icap_beam_select: fewer candidates than beams");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == ICAP_F32)
-    beam_select_kernel<float><<<(unsigned)B, NT, 0, st>>>((int)kin, (int)V, (const float*)logits, ldl, prev_score,
+    icap_launch(beam_select_kernel<float>, (unsigned)B, NT, 0, st, (int)kin, (int)V, (const float*)logits, ldl, prev_score,
                                                           (int)kout, out_score, out_parent, out_token, gap, log_domain);
   else
-    beam_select_kernel<bf16><<<(unsigned)B, NT, 0, st>>>((int)kin, (int)V, (const bf16*)logits, ldl, prev_score,
+    icap_launch(beam_select_kernel<bf16>, (unsigned)B, NT, 0, st, (int)kin, (int)V, (const bf16*)logits, ldl, prev_score,
                                                          (int)kout, out_score, out_parent, out_token, gap, log_domain);
   ICAP_LAUNCH_CHECK("icap_beam_select");
   return 0;
@@ -377,7 +382,7 @@ extern "C" int icap_beam_reorder(int64_t B, int64_t k, int64_t Tmax, int64_t t, 
                                  const int* tok_in, int* tok_out, const int* slot_in, int* slot_out, void* stream) {
   ICAP_ARG(B > 0 && k > 0 && parent && token && tok_in && tok_out, "icap_beam_reorder: null/empty argument");
   ICAP_ARG(tok_in != tok_out && (slot_in == nullptr || slot_in != slot_out), "icap_beam_reorder: must be out of place");
-  beam_reorder_kernel<<<(unsigned)(B * k), 32, 0, (cudaStream_t)stream>>>((int)B, (int)k, (int)Tmax, (int)t, parent,
+  icap_launch(beam_reorder_kernel, (unsigned)(B * k), 32, 0, (cudaStream_t)stream, (int)B, (int)k, (int)Tmax, (int)t, parent,
                                                                          token, tok_in, tok_out, slot_in, slot_out);
   ICAP_LAUNCH_CHECK("icap_beam_reorder");
   return 0;

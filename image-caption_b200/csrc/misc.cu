@@ -14,6 +14,9 @@ void icap_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 extern "C" const char* icap_last_error() { return g_err; }
+int icap_g_pdl = 0;       // launch attribute for every kernel of the library, see icap_launch()
+extern "C" int icap_set_pdl(int on) { icap_g_pdl = on ? 1 : 0; return 0; }
+
 extern "C" int icap_version() { return 100; }
 
 // Refuses to run on anything but Blackwell (sm_100): there is no CPU or other-arch fallback.
@@ -30,6 +33,7 @@ namespace {
 template <typename TS, typename TD>
 __global__ void copy2d_kernel(const TS* __restrict__ src, int64_t src_ld, TD* __restrict__ dst, int64_t dst_ld,
                               int64_t rows, int64_t cols, int accumulate, int vec) {
+  pdl_prologue();
   if (vec) {
     const int64_t c4 = cols >> 2;
     for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < rows * c4; u += (int64_t)gridDim.x * blockDim.x) {
@@ -57,6 +61,7 @@ __global__ void copy2d_kernel(const TS* __restrict__ src, int64_t src_ld, TD* __
 // a region is padding iff its position row is all zero (model.py:206); one warp per row
 __global__ void region_valid_kernel(const float* __restrict__ pos, int64_t M, int Dp, uint8_t* __restrict__ kvalid,
                                     float* __restrict__ rowscale) {
+  pdl_prologue();
   const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -74,6 +79,7 @@ template <typename TI>
 __global__ void caption_prep_kernel(const TI* __restrict__ cap, int B, int L, int pad, int* __restrict__ inp,
                                     int* __restrict__ tgt, uint8_t* __restrict__ tok_valid,
                                     float* __restrict__ rowscale, int* __restrict__ count) {
+  pdl_prologue();
   const int T = L - 1;
   int local = 0;
   for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < B * T; u += gridDim.x * blockDim.x) {
@@ -90,6 +96,7 @@ __global__ void caption_prep_kernel(const TI* __restrict__ cap, int B, int L, in
 }
 
 __global__ void count_finish_kernel(const int* __restrict__ count, float* __restrict__ out2) {
+  pdl_prologue();
   out2[0] = (float)(*count);
   out2[1] = 1.f / (float)(*count);
 }
@@ -98,6 +105,7 @@ template <typename TT, typename TO>
 __global__ void embed_fwd_kernel(const int* __restrict__ tok, int64_t tok_stride, int64_t M, int E,
                                  const TT* __restrict__ table, TO* __restrict__ out, float* __restrict__ rowscale,
                                  int pad) {
+  pdl_prologue();
   const int e4 = E >> 2;
   for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < M * e4; u += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = u / e4;
@@ -113,6 +121,7 @@ __global__ void embed_fwd_kernel(const int* __restrict__ tok, int64_t tok_stride
 template <typename T>
 __global__ void embed_bwd_kernel(const int* __restrict__ tok, int64_t M, int E, int pad, const T* __restrict__ dout,
                                  float* __restrict__ dtable) {
+  pdl_prologue();
   for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < M * E; u += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = u / E;
     const int c = (int)(u % E);
@@ -125,6 +134,7 @@ __global__ void embed_bwd_kernel(const int* __restrict__ tok, int64_t M, int E, 
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ x, int64_t ld, int64_t M, int64_t N, float* __restrict__ out,
                               int rows_per_block) {
+  pdl_prologue();
   __shared__ float red[8][33];
   const int64_t c = blockIdx.x * 32 + threadIdx.x;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
@@ -146,6 +156,7 @@ __global__ void colsum_kernel(const T* __restrict__ x, int64_t ld, int64_t M, in
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum8_kernel(const T* __restrict__ x, int64_t ld, int64_t M, int64_t N, float* __restrict__ out, int rows_per_block) {
+  pdl_prologue();
   __shared__ float red[8][256 + 8];
   const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x * 8;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
@@ -188,6 +199,7 @@ colsum8_kernel(const T* __restrict__ x, int64_t ld, int64_t M, int64_t N, float*
 __global__ void adam_kernel(int64_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, bf16* __restrict__ shadow, float lr, float b1, float b2, float eps,
                             const int* __restrict__ step_ptr, const float* __restrict__ gscale_ptr, float gscale) {
+  pdl_prologue();
   const int step = *step_ptr;
   const float bc1 = 1.f - powf(b1, (float)step);
   const float bc2 = 1.f - powf(b2, (float)step);
@@ -213,10 +225,13 @@ __global__ void adam_kernel(int64_t n, float* __restrict__ p, const float* __res
     if (shadow) store4(shadow + i * 4, P);
   }
 }
-__global__ void step_tick_kernel(int* step) { *step += 1; }
-__global__ void reciprocal_kernel(const float* x, float* out, float num) { out[0] = num / x[0]; }
+__global__ void step_tick_kernel(int* step) {
+  pdl_prologue(); *step += 1; }
+__global__ void reciprocal_kernel(const float* x, float* out, float num) {
+  pdl_prologue(); out[0] = num / x[0]; }
 
 __global__ void scale_kernel(float* __restrict__ x, int64_t n, const float* __restrict__ s_ptr, float s) {
+  pdl_prologue();
   const float f = s * (s_ptr ? s_ptr[0] : 1.f);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] *= f;
 }
@@ -226,6 +241,7 @@ template <typename T>
 __global__ void rows_gather_add_kernel(const T* __restrict__ src, int64_t src_ld, const T* __restrict__ base,
                                        int64_t base_ld, T* __restrict__ dst, int64_t dst_ld, int64_t rows, int cols,
                                        int div, int mul, int off) {
+  pdl_prologue();
   const int c4 = cols >> 2;
   for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < rows * c4; u += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = u / c4;
@@ -245,6 +261,7 @@ __global__ void rows_gather_add_kernel(const T* __restrict__ src, int64_t src_ld
 template <typename T>
 __global__ void rows_segsum_add_kernel(const T* __restrict__ src, int64_t src_ld, T* __restrict__ dst, int64_t dst_ld,
                                        int64_t nseg, int seg_len, int cols, int mul, int off) {
+  pdl_prologue();
   for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < nseg * cols; u += (int64_t)gridDim.x * blockDim.x) {
     const int64_t sg = u / cols;
     const int c = (int)(u % cols);
@@ -271,7 +288,7 @@ extern "C" int icap_copy2d(const void* src, int src_dtype, int64_t src_ld, void*
                   (src_ld % 4 == 0) && (dst_ld % 4 == 0);
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned g = grid_for(vec ? rows * cols / 4 : rows * cols, 256);
-#define GO(TS, TD) copy2d_kernel<TS, TD><<<g, 256, 0, st>>>((const TS*)src, src_ld, (TD*)dst, dst_ld, rows, cols, accumulate, vec)
+#define GO(TS, TD) icap_launch(copy2d_kernel<TS, TD>, g, 256, 0, st, (const TS*)src, src_ld, (TD*)dst, dst_ld, rows, cols, accumulate, vec)
   if (src_dtype == ICAP_F32 && dst_dtype == ICAP_F32) GO(float, float);
   else if (src_dtype == ICAP_F32 && dst_dtype == ICAP_BF16) GO(float, bf16);
   else if (src_dtype == ICAP_BF16 && dst_dtype == ICAP_F32) GO(bf16, float);
@@ -290,10 +307,10 @@ extern "C" int icap_rows_gather_add(int dtype, const void* src, int64_t src_ld, 
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned g = grid_for(rows * cols / 4, 256);
   if (dtype == ICAP_F32)
-    rows_gather_add_kernel<float><<<g, 256, 0, st>>>((const float*)src, src_ld, (const float*)base, base_ld, (float*)dst,
+    icap_launch(rows_gather_add_kernel<float>, g, 256, 0, st, (const float*)src, src_ld, (const float*)base, base_ld, (float*)dst,
                                                      dst_ld, rows, (int)cols, (int)div, (int)mul, (int)off);
   else
-    rows_gather_add_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)src, src_ld, (const bf16*)base, base_ld, (bf16*)dst,
+    icap_launch(rows_gather_add_kernel<bf16>, g, 256, 0, st, (const bf16*)src, src_ld, (const bf16*)base, base_ld, (bf16*)dst,
                                                     dst_ld, rows, (int)cols, (int)div, (int)mul, (int)off);
   ICAP_LAUNCH_CHECK("icap_rows_gather_add");
   return 0;
@@ -305,10 +322,10 @@ extern "C" int icap_rows_segsum_add(int dtype, const void* src, int64_t src_ld, 
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned g = grid_for(nseg * cols, 256);
   if (dtype == ICAP_F32)
-    rows_segsum_add_kernel<float><<<g, 256, 0, st>>>((const float*)src, src_ld, (float*)dst, dst_ld, nseg, (int)seg_len,
+    icap_launch(rows_segsum_add_kernel<float>, g, 256, 0, st, (const float*)src, src_ld, (float*)dst, dst_ld, nseg, (int)seg_len,
                                                      (int)cols, (int)mul, (int)off);
   else
-    rows_segsum_add_kernel<bf16><<<g, 256, 0, st>>>((const bf16*)src, src_ld, (bf16*)dst, dst_ld, nseg, (int)seg_len,
+    icap_launch(rows_segsum_add_kernel<bf16>, g, 256, 0, st, (const bf16*)src, src_ld, (bf16*)dst, dst_ld, nseg, (int)seg_len,
                                                     (int)cols, (int)mul, (int)off);
   ICAP_LAUNCH_CHECK("icap_rows_segsum_add");
   return 0;
@@ -317,7 +334,7 @@ extern "C" int icap_rows_segsum_add(int dtype, const void* src, int64_t src_ld, 
 extern "C" int icap_region_valid(const float* pos, int64_t M, int64_t Dp, uint8_t* kvalid, float* rowscale,
                                  void* stream) {
   ICAP_ARG(pos && M > 0 && Dp > 0, "icap_region_valid: null/empty argument");
-  region_valid_kernel<<<(unsigned)ceil_div64(M, 8), 256, 0, (cudaStream_t)stream>>>(pos, M, (int)Dp, kvalid, rowscale);
+  icap_launch(region_valid_kernel, (unsigned)ceil_div64(M, 8), 256, 0, (cudaStream_t)stream, pos, M, (int)Dp, kvalid, rowscale);
   ICAP_LAUNCH_CHECK("icap_region_valid");
   return 0;
 }
@@ -331,12 +348,12 @@ extern "C" int icap_caption_prep(const void* captions, int cap_is_int64, int64_t
   ICAP_CUDA(cudaMemsetAsync(count_i, 0, sizeof(int), st));
   const unsigned g = grid_for(B * (L - 1), 256);
   if (cap_is_int64)
-    caption_prep_kernel<long long><<<g, 256, 0, st>>>((const long long*)captions, (int)B, (int)L, pad_idx, inp, tgt,
+    icap_launch(caption_prep_kernel<long long>, g, 256, 0, st, (const long long*)captions, (int)B, (int)L, pad_idx, inp, tgt,
                                                       tok_valid, rowscale, count_i);
   else
-    caption_prep_kernel<int><<<g, 256, 0, st>>>((const int*)captions, (int)B, (int)L, pad_idx, inp, tgt, tok_valid,
+    icap_launch(caption_prep_kernel<int>, g, 256, 0, st, (const int*)captions, (int)B, (int)L, pad_idx, inp, tgt, tok_valid,
                                                 rowscale, count_i);
-  count_finish_kernel<<<1, 1, 0, st>>>(count_i, count_f2);
+  icap_launch(count_finish_kernel, 1, 1, 0, st, count_i, count_f2);
   ICAP_LAUNCH_CHECK("icap_caption_prep");
   return 0;
 }
@@ -347,11 +364,11 @@ extern "C" int icap_embed_fwd(int table_dtype, int out_dtype, const int* tokens,
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned g = grid_for(M * E / 4, 256);
   if (table_dtype == ICAP_F32 && out_dtype == ICAP_F32)
-    embed_fwd_kernel<float, float><<<g, 256, 0, st>>>(tokens, tok_stride, M, (int)E, (const float*)table, (float*)out, rowscale, pad_idx);
+    icap_launch(embed_fwd_kernel<float, float>, g, 256, 0, st, tokens, tok_stride, M, (int)E, (const float*)table, (float*)out, rowscale, pad_idx);
   else if (table_dtype == ICAP_BF16 && out_dtype == ICAP_BF16)
-    embed_fwd_kernel<bf16, bf16><<<g, 256, 0, st>>>(tokens, tok_stride, M, (int)E, (const bf16*)table, (bf16*)out, rowscale, pad_idx);
+    icap_launch(embed_fwd_kernel<bf16, bf16>, g, 256, 0, st, tokens, tok_stride, M, (int)E, (const bf16*)table, (bf16*)out, rowscale, pad_idx);
   else if (table_dtype == ICAP_F32 && out_dtype == ICAP_BF16)
-    embed_fwd_kernel<float, bf16><<<g, 256, 0, st>>>(tokens, tok_stride, M, (int)E, (const float*)table, (bf16*)out, rowscale, pad_idx);
+    icap_launch(embed_fwd_kernel<float, bf16>, g, 256, 0, st, tokens, tok_stride, M, (int)E, (const float*)table, (bf16*)out, rowscale, pad_idx);
   else ICAP_ARG(false, "icap_embed_fwd: unsupported dtype combination");
   ICAP_LAUNCH_CHECK("icap_embed_fwd");
   return 0;
@@ -362,8 +379,8 @@ extern "C" int icap_embed_bwd(int dtype, const int* tokens, int64_t M, int64_t E
   ICAP_ARG(tokens && dout && dtable && M > 0 && E > 0, "icap_embed_bwd: null/empty argument");
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned g = grid_for(M * E, 256);
-  if (dtype == ICAP_F32) embed_bwd_kernel<float><<<g, 256, 0, st>>>(tokens, M, (int)E, pad_idx, (const float*)dout, dtable);
-  else embed_bwd_kernel<bf16><<<g, 256, 0, st>>>(tokens, M, (int)E, pad_idx, (const bf16*)dout, dtable);
+  if (dtype == ICAP_F32) icap_launch(embed_bwd_kernel<float>, g, 256, 0, st, tokens, M, (int)E, pad_idx, (const float*)dout, dtable);
+  else icap_launch(embed_bwd_kernel<bf16>, g, 256, 0, st, tokens, M, (int)E, pad_idx, (const bf16*)dout, dtable);
   ICAP_LAUNCH_CHECK("icap_embed_bwd");
   return 0;
 }
@@ -378,8 +395,8 @@ extern "C" int icap_colsum(int dtype, int64_t M, int64_t N, const void* x, int64
     if (splits < 1) splits = 1;
     const int rpb = (int)ceil_div64(M, splits);
     dim3 grid8((unsigned)cb, (unsigned)ceil_div64(M, rpb)), block8(32, 8);
-    if (dtype == ICAP_F32) colsum8_kernel<float><<<grid8, block8, 0, st>>>((const float*)x, ld, M, N, out, rpb);
-    else colsum8_kernel<bf16><<<grid8, block8, 0, st>>>((const bf16*)x, ld, M, N, out, rpb);
+    if (dtype == ICAP_F32) icap_launch(colsum8_kernel<float>, grid8, block8, 0, st, (const float*)x, ld, M, N, out, rpb);
+    else icap_launch(colsum8_kernel<bf16>, grid8, block8, 0, st, (const bf16*)x, ld, M, N, out, rpb);
     ICAP_LAUNCH_CHECK("icap_colsum");
     return 0;
   }
@@ -389,8 +406,8 @@ extern "C" int icap_colsum(int dtype, int64_t M, int64_t N, const void* x, int64
   if (row_splits < 1) row_splits = 1;
   const int rows_per_block = (int)ceil_div64(M, row_splits);
   dim3 grid((unsigned)col_blocks, (unsigned)ceil_div64(M, rows_per_block)), block(32, 8);
-  if (dtype == ICAP_F32) colsum_kernel<float><<<grid, block, 0, st>>>((const float*)x, ld, M, N, out, rows_per_block);
-  else colsum_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)x, ld, M, N, out, rows_per_block);
+  if (dtype == ICAP_F32) icap_launch(colsum_kernel<float>, grid, block, 0, st, (const float*)x, ld, M, N, out, rows_per_block);
+  else icap_launch(colsum_kernel<bf16>, grid, block, 0, st, (const bf16*)x, ld, M, N, out, rows_per_block);
   ICAP_LAUNCH_CHECK("icap_colsum");
   return 0;
 }
@@ -400,8 +417,8 @@ extern "C" int icap_adam_step(int64_t n, float* p, const float* g, float* m, flo
                               float gscale, void* stream) {
   ICAP_ARG(n > 0 && n % 4 == 0 && p && g && m && v && step_dev, "icap_adam_step: bad argument (n must be a multiple of 4)");
   cudaStream_t st = (cudaStream_t)stream;
-  if (tick) step_tick_kernel<<<1, 1, 0, st>>>(step_dev);
-  adam_kernel<<<grid_for(n / 4, 256), 256, 0, st>>>(n, p, g, m, v, (bf16*)shadow_bf16, lr, beta1, beta2, eps, step_dev,
+  if (tick) icap_launch(step_tick_kernel, 1, 1, 0, st, step_dev);
+  icap_launch(adam_kernel, grid_for(n / 4, 256), 256, 0, st, n, p, g, m, v, (bf16*)shadow_bf16, lr, beta1, beta2, eps, step_dev,
                                                     gscale_dev, gscale);
   ICAP_LAUNCH_CHECK("icap_adam_step");
   return 0;
@@ -409,14 +426,14 @@ extern "C" int icap_adam_step(int64_t n, float* p, const float* g, float* m, flo
 
 extern "C" int icap_reciprocal(const float* x, float* out, float numerator, void* stream) {
   ICAP_ARG(x && out, "icap_reciprocal: null argument");
-  reciprocal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(x, out, numerator);
+  icap_launch(reciprocal_kernel, 1, 1, 0, (cudaStream_t)stream, x, out, numerator);
   ICAP_LAUNCH_CHECK("icap_reciprocal");
   return 0;
 }
 
 extern "C" int icap_scale(float* x, int64_t n, const float* s_dev, float s, void* stream) {
   ICAP_ARG(x && n > 0, "icap_scale: null/empty argument");
-  scale_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, s_dev, s);
+  icap_launch(scale_kernel, grid_for(n, 256), 256, 0, (cudaStream_t)stream, x, n, s_dev, s);
   ICAP_LAUNCH_CHECK("icap_scale");
   return 0;
 }

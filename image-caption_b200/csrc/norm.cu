@@ -20,6 +20,7 @@ add_ln_fwd_kernel(int M, int d, TA* __restrict__ a, const TR* __restrict__ res, 
                   const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ rowscale,
                   TY* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int write_sum,
                   float p_drop, uint32_t thresh, uint64_t seed, const int* __restrict__ seed_dev, float eps) {
+  pdl_prologue();
   if (seed_dev) seed += (uint64_t)(*seed_dev) * 0x9E3779B97F4A7C15ull;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -93,6 +94,7 @@ add_ln_bwd_rows_kernel(int M, int d, const T* __restrict__ dy1, const T* __restr
                        const float* __restrict__ gamma, const float* __restrict__ rowscale, T* __restrict__ ds,
                        T* __restrict__ da, float p_drop, uint32_t thresh, uint64_t seed,
                        const int* __restrict__ seed_dev) {
+  pdl_prologue();
   if (seed_dev) seed += (uint64_t)(*seed_dev) * 0x9E3779B97F4A7C15ull;
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -166,6 +168,7 @@ add_ln_bwd_cols_kernel(int M, int d, const T* __restrict__ dy1, const T* __restr
                        const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                        const float* __restrict__ rowscale, const T* __restrict__ dab, float* __restrict__ dgamma,
                        float* __restrict__ dbeta, float* __restrict__ dbias2, int rows_per_block) {
+  pdl_prologue();
   __shared__ float red[3][8][64];
   const int c = blockIdx.x * 64 + threadIdx.x * 2;
   const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
@@ -254,6 +257,7 @@ add_ln_fwd8_kernel(int M, int d, TA* __restrict__ a, const TR* __restrict__ res,
                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ rowscale,
                    TY* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int write_sum,
                    float p_drop, uint32_t thresh, uint64_t seed, const int* __restrict__ seed_dev, float eps) {
+  pdl_prologue();
   if (seed_dev) seed += (uint64_t)(*seed_dev) * 0x9E3779B97F4A7C15ull;
   const uint32_t sf = seed_fold(seed);
   const int lane = threadIdx.x & 31;
@@ -343,6 +347,7 @@ add_ln_bwd_rows8_kernel(int M, int d, const T* __restrict__ dy1, const T* __rest
                         const float* __restrict__ gamma, const float* __restrict__ rowscale, T* __restrict__ ds,
                         T* __restrict__ da, float p_drop, uint32_t thresh, uint64_t seed,
                         const int* __restrict__ seed_dev) {
+  pdl_prologue();
   if (seed_dev) seed += (uint64_t)(*seed_dev) * 0x9E3779B97F4A7C15ull;
   const uint32_t sf = seed_fold(seed);
   const int lane = threadIdx.x & 31;
@@ -427,6 +432,7 @@ add_ln_bwd_cols8_kernel(int M, int d, const T* __restrict__ dy1, const T* __rest
                         const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                         const float* __restrict__ rowscale, const T* __restrict__ dab, float* __restrict__ dgamma,
                         float* __restrict__ dbeta, float* __restrict__ dbias2, int rows_per_block) {
+  pdl_prologue();
   __shared__ float red[3][8][256 + 8];
   const int c = blockIdx.x * 256 + threadIdx.x * 8;
   const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
@@ -501,7 +507,7 @@ extern "C" int icap_add_ln_fwd(int a_dtype, int act_dtype, int64_t M, int64_t d,
       !getenv("ICAP_LN_NARROW")) {
     dim3 grid8((unsigned)ceil_div64(M, 8 * RPW));
 #define GO8(NIT, TA, TR, TY)                                                                                      \
-  add_ln_fwd8_kernel<NIT, TA, TR, TY><<<grid8, 256, 0, st>>>((int)M, (int)d, (TA*)a, (const TR*)res,             \
+  icap_launch(add_ln_fwd8_kernel<NIT, TA, TR, TY>, grid8, 256, 0, st, (int)M, (int)d, (TA*)a, (const TR*)res,             \
                                                              (int)res_rows, gamma, beta, rowscale, (TY*)y,       \
                                                              mean_out, rstd_out, write_sum, p_drop, th, seed, seed_dev, eps)
 #define GOT8(TA, TR, TY)                                                                                          \
@@ -520,7 +526,7 @@ extern "C" int icap_add_ln_fwd(int a_dtype, int act_dtype, int64_t M, int64_t d,
     return 0;
   }
 #define GO1(NIT, TA, TR, TY)                                                                                      \
-  add_ln_fwd_kernel<NIT, TA, TR, TY><<<grid, 256, 0, st>>>((int)M, (int)d, (TA*)a, (const TR*)res,               \
+  icap_launch(add_ln_fwd_kernel<NIT, TA, TR, TY>, grid, 256, 0, st, (int)M, (int)d, (TA*)a, (const TR*)res,               \
                                                             (int)res_rows, gamma, beta, rowscale, (TY*)y,        \
                                                             mean_out, rstd_out, write_sum, p_drop, th, seed, seed_dev, eps)
 #define GO(TA, TR, TY)                                                                                            \
@@ -566,7 +572,7 @@ extern "C" int icap_add_ln_bwd(int act_dtype, int64_t M, int64_t d, const void* 
     const int rpb8 = (int)ceil_div64(M, splits8);
     dim3 cgrid8((unsigned)col_blocks8, (unsigned)ceil_div64(M, rpb8));
 #define GOB8(NIT, T)                                                                                              \
-  add_ln_bwd_rows8_kernel<NIT, T><<<row_blocks8, 256, 0, st>>>((int)M, (int)d, (const T*)dy1, (const T*)dy2,      \
+  icap_launch(add_ln_bwd_rows8_kernel<NIT, T>, row_blocks8, 256, 0, st, (int)M, (int)d, (const T*)dy1, (const T*)dy2,      \
                                                                (const T*)s, mean, rstd, gamma, rowscale, (T*)ds, \
                                                                (T*)da, p_drop, th, seed, seed_dev)
 #define GOBT8(T)                                                                                                  \
@@ -577,7 +583,7 @@ extern "C" int icap_add_ln_bwd(int act_dtype, int64_t M, int64_t d, const void* 
       else GOB8(4, T);                                                                                            \
     }                                                                                                             \
     if (dgamma || dbeta || dbias2)                                                                                \
-      add_ln_bwd_cols8_kernel<T><<<cgrid8, cblock, 0, st>>>((int)M, (int)d, (const T*)dy1, (const T*)dy2,         \
+      icap_launch(add_ln_bwd_cols8_kernel<T>, cgrid8, cblock, 0, st, (int)M, (int)d, (const T*)dy1, (const T*)dy2,         \
                                                             (const T*)s, mean, rstd, rowscale, (const T*)dab,    \
                                                             dgamma, dbeta, dbias2, rpb8);                        \
   } while (0)
@@ -589,7 +595,7 @@ extern "C" int icap_add_ln_bwd(int act_dtype, int64_t M, int64_t d, const void* 
     return 0;
   }
 #define GOB(NIT, T)                                                                                               \
-  add_ln_bwd_rows_kernel<NIT, T><<<row_blocks, 256, 0, st>>>((int)M, (int)d, (const T*)dy1, (const T*)dy2,        \
+  icap_launch(add_ln_bwd_rows_kernel<NIT, T>, row_blocks, 256, 0, st, (int)M, (int)d, (const T*)dy1, (const T*)dy2,        \
                                                              (const T*)s, mean, rstd, gamma, rowscale, (T*)ds,   \
                                                              (T*)da, p_drop, th, seed, seed_dev)
 #define GOBT(T)                                                                                                   \
@@ -601,7 +607,7 @@ extern "C" int icap_add_ln_bwd(int act_dtype, int64_t M, int64_t d, const void* 
       else GOB(8, T);                                                                                             \
     }                                                                                                             \
     if (dgamma || dbeta || dbias2)                                                                                \
-      add_ln_bwd_cols_kernel<T><<<cgrid, cblock, 0, st>>>((int)M, (int)d, (const T*)dy1, (const T*)dy2,           \
+      icap_launch(add_ln_bwd_cols_kernel<T>, cgrid, cblock, 0, st, (int)M, (int)d, (const T*)dy1, (const T*)dy2,           \
                                                           (const T*)s, mean, rstd, rowscale, (const T*)dab,      \
                                                           dgamma, dbeta, dbias2, rows_per_block);                 \
   } while (0)

@@ -17,6 +17,7 @@ multi-consumer activations are carried as lists and summed inside the fused Laye
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Tuple
 
@@ -162,6 +163,12 @@ class CaptionEngine:
         self.dp_unnormalized = False     # data parallel: dlogits are NOT divided by the local token count
         self._prof = None
         self._gemm_log: Optional[List[tuple]] = None     # bench: argument tuples of every GEMM launch of a step
+        # backward: weight-gradient GEMMs run on a second stream, concurrently with the dgrad / LayerNorm /
+        # attention chain that does not depend on them (joined before the optimizer step)
+        self.wgrad_side_stream = os.environ.get("ICAP_WGRAD_STREAM", "1") != "0"
+        call("icap_set_pdl", 1 if os.environ.get("ICAP_PDL", "1") == "1" else 0)
+        self._side: Optional[torch.cuda.Stream] = None
+        self._bwd_side: Optional[torch.cuda.Stream] = None
         self.p16 = torch.empty(self.n_flat, dtype=torch.bfloat16, device=self.dev) if precision == "bf16" else None
         self.shadow_fresh = False
         self.adam_m: Optional[torch.Tensor] = None
@@ -249,7 +256,7 @@ class CaptionEngine:
 
     def wgrad(self, dy: torch.Tensor, x: torch.Tensor, g_ptr: int, Nout: int, Kin: int, rows: int,
               ld_dy: Optional[int] = None, dy_ptr: Optional[int] = None, ldg: Optional[int] = None,
-              x_ptr: Optional[int] = None, ldx: Optional[int] = None) -> None:
+              x_ptr: Optional[int] = None, ldx: Optional[int] = None, side_ok: bool = True) -> None:
         """dW[Nout,Kin] += dy[rows,Nout]^T x[rows,Kin]  (fp32, split-K over rows so the grid fills the GPU)."""
         ab = BF16 if self.precision == "bf16" else F32
         if ab == BF16:
@@ -263,6 +270,15 @@ class CaptionEngine:
                 F32, None, 0, None, 0, 1, split)
         if self._gemm_log is not None:
             self._gemm_log.append(args)
+        if self._bwd_side is not None and side_ok:
+            # dy and x stay allocated until the end of backward (self.keep), so the side stream may read them late
+            main = torch.cuda.current_stream(self.dev)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self._bwd_side.wait_event(ev)
+            with torch.cuda.stream(self._bwd_side):
+                call("icap_gemm", *args, self._s())
+            return
         ev = self._prof_begin()
         call("icap_gemm", *args, self._s())
         self._prof_end(ev, 2.0 * Nout * Kin * rows)
@@ -511,7 +527,7 @@ class CaptionEngine:
             if rec:
                 def bwd():      # NB: closes over x0 (x is re-bound by the block loop below)
                     ds, _ = self.ln_bwd(x0, e, mean, rstd, "encoder.norm", None, 0.0, 0)
-                    self.wgrad(ds, xcat, dwcat.data_ptr(), d, Kc, M)
+                    self.wgrad(ds, xcat, dwcat.data_ptr(), d, Kc, M, side_ok=False)
                 self.tape.append(bwd)
         for i in range(cfg.encode_num_blocks):
             pre = f"encoder.encoder.{i}"
@@ -551,7 +567,7 @@ class CaptionEngine:
         if rec:
             def bwd_embed2():
                 ds, _ = self.ln_bwd(y2, e2, mean2, rstd2, "encoder.norm", None, 0.0, 0)
-                self.wgrad(ds, x2, dwcat.data_ptr(), d, Kc, 2 * M)
+                self.wgrad(ds, x2, dwcat.data_ptr(), d, Kc, 2 * M, side_ok=False)
             self.tape.append(bwd_embed2)
         pre = "encoder.image_encoder"
         z = self.mha_block(pre + ".multihead_attention", y2, y2, M, 2, 2, H, cfg.encode_q_k_dim, cfg.encode_v_dim,
@@ -569,7 +585,7 @@ class CaptionEngine:
                 ds, _ = self.ln_bwd(x, tok1, mean, rstd, "encoder.norm", None, 0.0, 0)
                 # d position-embedding weights (tail columns of the packed matrix)
                 self.wgrad(ds, xcat, dwcat.data_ptr() + Df * 4, d, Kc - Df, M, x_ptr=xcat.data_ptr() + Df * esz, ldx=Kc,
-                           ldg=Kc)
+                           ldg=Kc, side_ok=False)
                 dz = self.new(2 * M, d, zero=True)
                 call("icap_copy2d", ds.data_ptr(), self.act, d, dz.data_ptr() + d * esz, self.act, 2 * d, M, d, 0, self._s())
                 self.add_grad(z, dz)
@@ -706,10 +722,21 @@ class CaptionEngine:
         assert self.tape is not None, "forward was not recorded"
         if zero_grads:
             self.g32.zero_()
-        for fn in reversed(self.tape):
-            fn()
-            if self.bucket_hook is not None:
-                self.bucket_hook(getattr(fn, "__qualname__", ""))
+        main = torch.cuda.current_stream(self.dev)
+        if self.wgrad_side_stream and self.precision == "bf16" and self._prof is None:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.dev)
+            self._bwd_side = self._side
+            self._bwd_side.wait_stream(main)          # g32 has been zeroed / the forward is complete
+        try:
+            for fn in reversed(self.tape):
+                fn()
+                if self.bucket_hook is not None:
+                    self.bucket_hook(getattr(fn, "__qualname__", ""))
+        finally:
+            if self._bwd_side is not None:
+                main.wait_stream(self._bwd_side)      # every weight gradient has landed in g32
+                self._bwd_side = None
         self.tape = None
         self.gr, self.keep = {}, []
 
