@@ -7,12 +7,12 @@
 // Same operand conventions as gemm_simt.cu (a_kmajor / b_kmajor); MN-major operands are fed to the
 // tensor core directly through the UMMA descriptor major bits, so dgrad / wgrad need no transposes.
 //
-// PERSISTENT, warp-specialised: grid = min(#tiles, #SMs), one CTA per SM (all of TMEM, ~225 KB smem).
+// PERSISTENT, warp-specialised (320 threads): grid = min(#tiles, #SMs), one CTA per SM (all of TMEM, ~226 KB smem).
 //   warp 0      : TMA producer (one lane), 4-stage (BN=256) / 6-stage (BN=128) ring of 64-wide k-blocks
 //   warp 1      : TMEM allocator + single-thread MMA issuer; TWO accumulator stages in TMEM, so the
 //                 main loop of tile i+1 runs while the epilogue warps drain tile i
-//   warps 2..5  : epilogue; each owns the TMEM lane quarter (warp_id % 4) and a double-buffered 2 x 4 KB
-//                 staging slab: TMEM -> registers -> swizzled smem -> TMA store / TMA reduce-add
+//   warps 2..9  : epilogue; two warps per TMEM lane quarter (warp_id % 4), each draining half of the tile's columns
+//                 through its own 4 KB staging box: TMEM -> registers -> swizzled smem -> TMA store / reduce-add
 // The GEMMs of this model are small (2-20 GFLOP, K = 512 mostly): per-CTA setup (barrier init, TMEM
 // allocation, descriptor prefetch) is paid once per launch instead of once per tile, and the kernel is
 // PDL-aware (griddepcontrol) so that setup can overlap the tail of the previous kernel in the stream.
@@ -27,17 +27,21 @@ namespace {
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
 constexpr int A_TILE_BYTES = BM * BK * 2;        // 16 KB per stage
-constexpr int NTHREADS = 192;
-constexpr int EPI_WARPS = 4;
+constexpr int NTHREADS = 320;
+constexpr int EPI_WARPS = 8;                     // two per TMEM lane quarter: each takes half of the tile's columns
 constexpr int EPI_BOX_BYTES = 4096;              // 32 rows x 128 B: one TMA store box
-constexpr int EPI_BYTES = EPI_WARPS * 2 * EPI_BOX_BYTES;
+constexpr int EPI_BYTES = EPI_WARPS * EPI_BOX_BYTES;
 
-template <int BN> struct Cfg {
-  static constexpr int STAGES = BN == 256 ? 4 : 6;
-  static constexpr int B_TILE_BYTES = BN * BK * 2;
+// TWO = cta_group::2: a cluster of two CTAs (one TPC) computes a 256 x 256 tile; each CTA owns 128 rows of A and
+// HALF of the B tile (128 of the 256 columns), the pair's tensor cores read both halves.  Per CTA and k-block that
+// is 32 KB of operands from L2 instead of 48 KB for the same 128 x 256 x 64 MACs.
+template <int BN, bool TWO> struct Cfg {
+  static constexpr int B_ROWS = TWO ? BN / 2 : BN;           // B rows (n) staged per CTA
+  static constexpr int B_TILE_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int TMEM_COLS = 2 * BN;       // two accumulator stages
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/ + 512 /*bias staging*/ +
+  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;  // 4 (128x256), 6 (128x128 and 2-CTA)
+  static constexpr int TMEM_COLS = 2 * BN;                   // two accumulator stages
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 /*barriers*/ + 1024 /*bias staging*/ +
                                     1024 /*align slack*/;
 };
 
@@ -63,6 +67,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
   } while (!done);
+}
+// spin on test_wait: barriers that are completed from the PEER CTA (remote arrive / multicast commit / cta_group::2
+// TMA) do not promptly wake a thread suspended in try_wait -- it sleeps out its time limit (measured: ~1 us per k-block)
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+template <bool SPIN>
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity) {
+  if constexpr (SPIN) mbar_wait_spin(bar, parity); else mbar_wait(bar, parity);
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
   asm volatile(
@@ -146,6 +170,44 @@ template <> struct OutVec<bf16> {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// ---- cta_group::2 (CTA pair) helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {      // shared::cluster address
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion is signalled on an mbarrier of the LEADER CTA of the pair (cluster address)
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar_cluster) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar_cluster)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {      // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
 
 // 32 consecutive elements of the ReLU-mask operand (aux) of one row, as raw 16-byte words
 template <typename TO> struct AuxRow { uint4 w[32 * sizeof(TO) / 16]; };
@@ -179,96 +241,129 @@ struct GemmArgs {
   int accumulate;      // 0 store, 1 C += (load/add/store or TMA reduce), 2 atomics (split-K on the direct path)
   int kb_per_split, splits, tiles_m, tiles_n;
   int vec_ok, store_mode;   // store_mode: 0 direct global stores, 1 TMA store, 2 TMA reduce-add
+  int debug;                // timing experiments only (ICAP_GEMM_DEBUG): 1 = no TMA loads, 2 = no MMAs, 3 = no epilogue stores
 };
 
-template <int BN, bool A_KMAJOR, bool B_KMAJOR, typename TO>
+template <int BN, bool TWO, bool A_KMAJOR, bool B_KMAJOR, typename TO>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
-  using CF = Cfg<BN>;
+  using CF = Cfg<BN, TWO>;
   constexpr int STAGES = CF::STAGES;
+  constexpr int NCTA = TWO ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base, sB = sA + STAGES * A_TILE_BYTES, sE = sB + STAGES * CF::B_TILE_BYTES;
   const uint32_t bars = sE + EPI_BYTES;                  // full[S], empty[S], tfull[2], tempty[2], tmem slot
   const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES, tfull_bar = bars + 16 * STAGES;
   const uint32_t tempty_bar = tfull_bar + 16, slot_addr = tempty_bar + 16;
-  const uint32_t sBias = bars + 256;                     // 4 x 128 B: one 32-float bias row per epilogue warp
+  const uint32_t sBias = bars + 256;                     // 8 x 128 B: one 32-float bias row per epilogue warp
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + (slot_addr - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = g.M, N = g.N;
   const int nkb_total = (g.K + BK - 1) / BK;
-  const int total_tiles = g.tiles_m * g.tiles_n * g.splits;
+  const int total_tiles = g.tiles_m * g.tiles_n * g.splits;      // tiles of (NCTA*128) x BN
+  const uint32_t rank = TWO ? cluster_ctarank() : 0u;            // 0 = leader of the pair
+  const int worker = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int nworkers = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     if (g.store_mode) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(full_bar + 8 * i, 1);
+      mbar_init(full_bar + 8 * i, 1);                    // pair: only the leader arrives (expect_tx of BOTH CTAs' bytes)
       mbar_init(empty_bar + 8 * i, 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar + 8 * i, 1);
-      mbar_init(tempty_bar + 8 * i, EPI_WARPS);
+      mbar_init(tempty_bar + 8 * i, EPI_WARPS * NCTA);   // pair: the peer's epilogue warps arrive remotely
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_addr), "n"(CF::TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (TWO) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_addr), "n"(CF::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_addr), "n"(CF::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if constexpr (TWO) cluster_sync_all(); else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   pdl_prologue();    // everything above overlaps the previous kernel's tail when launched with PDL
 
   if (warp == 0) {
     if (lane == 0) {
-      // ------------------------------------------------------------ TMA producer
+      // ------------------------------------------------------------ TMA producer (one per CTA)
+      const uint32_t full_leader = TWO ? map_to_cta(full_bar, 0) : full_bar;
       int s = 0, ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n0 = (tile % g.tiles_n) * BN, m0 = ((tile / g.tiles_n) % g.tiles_m) * BM;
+      for (int tile = worker; tile < total_tiles; tile += nworkers) {
+        const int n0 = (tile % g.tiles_n) * BN + (int)rank * CF::B_ROWS;       // this CTA's share of the B tile
+        const int m0 = ((tile / g.tiles_n) % g.tiles_m) * (BM * NCTA) + (int)rank * BM;
         const int kb0 = (tile / (g.tiles_n * g.tiles_m)) * g.kb_per_split;
         const int nkb = min(g.kb_per_split, nkb_total - kb0);
         for (int i = 0; i < nkb; ++i) {
-          mbar_wait(empty_bar + 8 * s, ph ^ 1);
-          mbar_expect_tx(full_bar + 8 * s, CF::STAGE_BYTES);
+          mbar_wait_t<TWO>(empty_bar + 8 * s, ph ^ 1);
           const int k0 = (kb0 + i) * BK;
           const uint32_t dA = sA + s * A_TILE_BYTES, dB = sB + s * CF::B_TILE_BYTES;
-          if (A_KMAJOR) tma_load_2d(dA, &tmA, k0, m0, full_bar + 8 * s);          // box {64 k, 128 m}
-          else {                                                                   // 2 boxes {64 m, 64 k}
+          if ((g.debug & 7) == 1) {                    // timing experiment: barriers only, operands are garbage
+            if (rank == 0) mbar_arrive(full_bar + 8 * s);
+          } else if constexpr (TWO) {
+            const uint32_t fb = full_leader + 8 * s;
+            // Both CTAs' TMA bytes complete on the leader's barrier.  The peer does NOT arrive on it: a remote
+            // mbarrier.arrive.release.cluster per k-block cost ~0.5 us each (measured, tools/gemm_bench.py).
+            if (rank == 0) mbar_expect_tx(full_bar + 8 * s, 2 * CF::STAGE_BYTES);
+            if (A_KMAJOR) tma_load_2d_2sm(dA, &tmA, k0, m0, fb);
+            else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(dA + j * 8192, &tmA, m0 + 64 * j, k0, full_bar + 8 * s);
-          }
-          if (B_KMAJOR) tma_load_2d(dB, &tmB, k0, n0, full_bar + 8 * s);          // box {64 k, BN n}
-          else {
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d_2sm(dA + j * 8192, &tmA, m0 + 64 * j, k0, fb);
+            }
+            if (B_KMAJOR) tma_load_2d_2sm(dB, &tmB, k0, n0, fb);                    // box {64 k, 128 n}
+            else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(dB + j * 8192, &tmB, n0 + 64 * j, k0, full_bar + 8 * s);
+              for (int j = 0; j < CF::B_ROWS / 64; ++j) tma_load_2d_2sm(dB + j * 8192, &tmB, n0 + 64 * j, k0, fb);
+            }
+          } else {
+            mbar_expect_tx(full_bar + 8 * s, CF::STAGE_BYTES);
+            if (A_KMAJOR) tma_load_2d(dA, &tmA, k0, m0, full_bar + 8 * s);          // box {64 k, 128 m}
+            else {                                                                   // 2 boxes {64 m, 64 k}
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d(dA + j * 8192, &tmA, m0 + 64 * j, k0, full_bar + 8 * s);
+            }
+            if (B_KMAJOR) tma_load_2d(dB, &tmB, k0, n0, full_bar + 8 * s);          // box {64 k, BN n}
+            else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(dB + j * 8192, &tmB, n0 + 64 * j, k0, full_bar + 8 * s);
+            }
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ MMA issuer (one thread)
-      // instruction descriptor: D=f32, A=B=bf16, majors, N>>3, M>>4
+    if (lane == 0 && rank == 0) {
+      // ------------------------------------------------------------ MMA issuer (one thread; pair: leader CTA only)
+      // instruction descriptor: D=f32, A=B=bf16, majors, N>>3, M>>4   (pair: M = 256 across the two CTAs)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_KMAJOR ? 0u : 1u) << 15) |
-                             ((B_KMAJOR ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                             ((B_KMAJOR ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)((BM * NCTA) >> 4) << 24);
       int s = 0, ph = 0, it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = worker; tile < total_tiles; tile += nworkers, ++it) {
         const int kb0 = (tile / (g.tiles_n * g.tiles_m)) * g.kb_per_split;
         const int nkb = min(g.kb_per_split, nkb_total - kb0);
         const int as = it & 1, aph = (it >> 1) & 1;
-        mbar_wait(tempty_bar + 8 * as, aph ^ 1);          // epilogue has drained this accumulator stage
+        mbar_wait_t<TWO>(tempty_bar + 8 * as, aph ^ 1);          // epilogue has drained this accumulator stage
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
         for (int i = 0; i < nkb; ++i) {
-          mbar_wait(full_bar + 8 * s, ph);
+          mbar_wait_t<TWO>(full_bar + 8 * s, ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t aS = sA + s * A_TILE_BYTES, bS = sB + s * CF::B_TILE_BYTES;
 #pragma unroll
@@ -277,12 +372,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // MN-major: 64-element MN atoms 8192 B apart (LBO), 8-k groups 1024 B apart (SBO), +2048 B per k step
             const uint64_t ad = A_KMAJOR ? make_sdesc(aS + k * 32, 16, 1024) : make_sdesc(aS + k * 2048, 8192, 1024);
             const uint64_t bd = B_KMAJOR ? make_sdesc(bS + k * 32, 16, 1024) : make_sdesc(bS + k * 2048, 8192, 1024);
-            umma_bf16(tacc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            if ((g.debug & 7) == 2) continue;
+            if constexpr (TWO) umma_bf16_2sm(tacc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            else umma_bf16(tacc, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(empty_bar + 8 * s);      // smem slot free once these MMAs have read it
+          // smem slot free (in both CTAs of a pair) once these MMAs have read it
+          if constexpr (TWO) umma_commit_2sm(empty_bar + 8 * s); else umma_commit(empty_bar + 8 * s);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(tfull_bar + 8 * as);       // accumulator complete
+        // accumulator complete
+        if constexpr (TWO) umma_commit_2sm(tfull_bar + 8 * as); else umma_commit(tfull_bar + 8 * as);
       }
     }
   } else {
@@ -291,27 +390,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int CPB = 128 / ESZ;             // columns per TMA store box (one 128 B swizzle row): 64 bf16 / 32 fp32
     constexpr int CHUNKS_PER_BOX = CPB / 32;   // 32-column TMEM loads per box
     constexpr int NCH = 32 * ESZ / 16;         // 16 B smem chunks per 32 columns: 4 (bf16) / 8 (fp32)
+    // The epilogue is one dependent instruction stream per warp (TMEM load -> math -> convert -> st.shared), i.e.
+    // latency bound: with 4 warps it took ~3.7 us per 128x256 tile, longer than a K=512 main loop (ncu/ablation r1).
+    // Eight warps -- two per TMEM lane quarter, each draining half of the columns -- halve that.
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
-    const uint32_t ebuf = sE + (uint32_t)q * (2 * EPI_BOX_BYTES);
+    const int ew = warp - 2, half = ew >> 2;   // half: which half of the tile's columns
+    const uint32_t ebuf = sE + (uint32_t)ew * EPI_BOX_BYTES;
     const uint32_t sw = (uint32_t)(lane & 7);
     TO* const C = reinterpret_cast<TO*>(g.C);
     const TO* const aux = reinterpret_cast<const TO*>(g.aux);
+    const uint32_t tempty_leader = TWO ? map_to_cta(tempty_bar, 0) : tempty_bar;
     int it = 0, nbox = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int n0 = (tile % g.tiles_n) * BN, m0 = ((tile / g.tiles_n) % g.tiles_m) * BM;
+    for (int tile = worker; tile < total_tiles; tile += nworkers, ++it) {
+      const int n0 = (tile % g.tiles_n) * BN;
+      const int m0 = ((tile / g.tiles_n) % g.tiles_m) * (BM * NCTA) + (int)rank * BM;
       const bool add_bias = (g.bias != nullptr) && (tile < g.tiles_n * g.tiles_m);     // split 0 only
       const int as = it & 1, aph = (it >> 1) & 1;
       const int row0 = m0 + q * 32, row = row0 + lane;
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-      const int nchunks = min(BN / 32, (N - n0 + 31) / 32);       // >= 1
+      const int c_begin = half * (BN / 64);
+      const int nchunks = min((half + 1) * (BN / 64), (N - n0 + 31) / 32);      // this warp: chunks [c_begin, nchunks)
       AuxRow<TO> a_cur, a_nxt;
       const bool aux_vec = g.vec_ok != 0;
-      if (g.epi == 2 && row < M)
-        aux_load(a_cur, aux + (int64_t)row * g.ldaux + n0, aux_vec && n0 + 32 <= N, N - n0);
-      mbar_wait(tfull_bar + 8 * as, aph);
+      if (g.epi == 2 && row < M && c_begin < nchunks)
+        aux_load(a_cur, aux + (int64_t)row * g.ldaux + n0 + c_begin * 32, aux_vec && n0 + c_begin * 32 + 32 <= N,
+                 N - n0 - c_begin * 32);
+      mbar_wait_t<TWO>(tfull_bar + 8 * as, aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (c_begin >= nchunks) {                 // ragged N: nothing to drain, just hand the stage back
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (TWO) mbar_arrive_cluster(tempty_leader + 8 * as); else mbar_arrive(tempty_bar + 8 * as);
+        }
+      }
 #pragma unroll 1
-      for (int c = 0; c < nchunks; ++c) {
+      for (int c = c_begin; c < nchunks; ++c) {
         const int col0 = n0 + c * 32;
         if (g.epi == 2 && row < M && c + 1 < nchunks)
           aux_load(a_nxt, aux + (int64_t)row * g.ldaux + col0 + 32, aux_vec && col0 + 64 <= N, N - col0 - 32);
@@ -322,13 +436,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (c == nchunks - 1) {                 // accumulator fully read: hand the TMEM stage back to the MMA warp
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar + 8 * as);
+          if (lane == 0) {
+            if constexpr (TWO) mbar_arrive_cluster(tempty_leader + 8 * as); else mbar_arrive(tempty_bar + 8 * as);
+          }
         }
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         if (add_bias) {
-          const uint32_t bslot = sBias + (uint32_t)q * 128;
+          const uint32_t bslot = sBias + (uint32_t)ew * 128;
           __syncwarp();                         // previous chunk's reads of the slot are done
           asm volatile("st.shared.f32 [%0], %1;" ::"r"(bslot + (uint32_t)lane * 4), "f"(bias_l) : "memory");
           __syncwarp();
@@ -347,12 +463,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (row < M) aux_mask<TO>(a_cur, v);
           a_cur = a_nxt;
         }
-        if (g.store_mode != 0) {
+        if ((g.debug & 7) == 3) {                     // timing experiment: no stores at all (keep the math alive)
+          float acc = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc += v[j];
+          if (acc == 123.456f) C[0] = from_f32<TO>(acc);
+        } else if (g.store_mode != 0) {
           // ---- staged: registers -> 128B-swizzled smem box (32 rows x 128 B) -> TMA store / reduce-add
           const int cc = c % CHUNKS_PER_BOX;
-          const uint32_t buf = ebuf + (uint32_t)(nbox & 1) * EPI_BOX_BYTES;
+          const uint32_t buf = ebuf;
           if (cc == 0) {                        // the TMA store that last read this buffer must be done
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             __syncwarp();
           }
           const uint32_t my_row = buf + (uint32_t)lane * 128;
@@ -381,7 +502,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (g.store_mode == 2) tma_reduce_add_2d(&tmC, buf, bc0, row0);
                 else tma_store_2d(&tmC, buf, bc0, row0);
               }
-              // one (possibly empty) group per box keeps `wait_group.read 1` == "the other buffer is free"
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
             ++nbox;
@@ -420,9 +540,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (g.store_mode != 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if constexpr (TWO) cluster_sync_all(); else __syncthreads();    // pair: the peer may still signal our barriers / read our smem
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(CF::TMEM_COLS) : "memory");
+    if constexpr (TWO)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(CF::TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(CF::TMEM_COLS) : "memory");
   }
 }
 
@@ -477,27 +600,51 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, bool AK, bool BKM, typename TO>
+template <int BN, bool TWO, bool AK, bool BKM, typename TO>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmArgs& g, cudaStream_t st) {
   static bool attr_done = false;
-  auto kern = gemm_tc_kernel<BN, AK, BKM, TO>;
+  auto kern = gemm_tc_kernel<BN, TWO, AK, BKM, TO>;
+  using CF = Cfg<BN, TWO>;
   if (!attr_done) {
-    ICAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+    ICAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES));
     attr_done = true;
   }
   const int total = g.tiles_m * g.tiles_n * g.splits;
-  ICAP_CUDA(icap_launch(kern, dim3((unsigned)(total < num_sms() ? total : num_sms())), dim3(NTHREADS),
-                        (size_t)Cfg<BN>::SMEM_BYTES, st, ta, tb, tc, g));
+  if (!TWO) {
+    ICAP_CUDA(icap_launch(kern, dim3((unsigned)(total < num_sms() ? total : num_sms())), dim3(NTHREADS),
+                          (size_t)CF::SMEM_BYTES, st, ta, tb, tc, g));
+    return 0;
+  }
+  // CTA pairs: cluster (2,1,1), one pair per TPC, persistent over the 256 x BN tiles
+  const int pairs = num_sms() / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * (total < pairs ? total : pairs)));
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = CF::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = icap_g_pdl ? 2 : 1;
+  ICAP_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, g));
   return 0;
 }
 
-// estimated tensor-pipe clocks of the whole launch for a tile width (persistent: waves x per-tile main loop,
-// plus one exposed epilogue); used to pick BN and the split-K factor
-double est_cost(int64_t tiles, int nkb, int bn, int sms) {
-  const double waves = (double)((tiles + sms - 1) / sms);
-  // 128-wide tiles move 1.5x the operand bytes per flop from L2 (measured ~1.3x slower main loop, tools/gemm_bench.py)
-  const double per_kb = bn == 256 ? 512.0 : 256.0 * 1.35;
-  return waves * (double)nkb * per_kb + 4.0 * bn + 1500.0;
+// Estimated tensor-pipe clocks of the whole launch (persistent: waves x per-tile main loop, plus one exposed
+// epilogue); picks the tile configuration and the split-K factor.  cfg: 0 = 128x128, 1 = 128x256, 2 = CTA pair 256x256.
+// Per-k-block costs are calibrated with tools/gemm_bench.py: the main loop is bound by operand bytes from L2
+// (128x128: 32 KB per 128x128x64 MACs; 128x256: 48 KB per 2x that; pair: 32 KB per CTA per 2x that).
+double est_cost(int64_t tiles, int nkb, int cfg, int sms) {
+  const int workers = cfg == 2 ? sms / 2 : sms;
+  const double waves = (double)((tiles + workers - 1) / workers);
+  const double per_kb = cfg == 0 ? 345.0 : cfg == 1 ? 512.0 : 400.0;
+  const double epi = cfg == 0 ? 512.0 : 1024.0;
+  return waves * (double)nkb * per_kb + epi + (cfg == 2 ? 2200.0 : 1500.0);
 }
 
 }  // namespace
@@ -511,21 +658,26 @@ int icap_gemm_bf16_launch(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int6
   ICAP_ARG(!(a_kmajor == 0 && b_kmajor == 1), "icap_gemm(bf16): (A MN-major, B K-major) is not instantiated");
   const int sms = num_sms();
   const int nkb = (int)ceil_div64(K, BK);
-  const int64_t tiles_m = ceil_div64(M, BM);
   const bool can_split = accumulate != 0 && epi == 0 && c_dtype == ICAP_F32 && bias == nullptr;
-  // ---- tile width and split-K factor: split_k <= 0 = automatic (fill the SMs, >= 4 k-blocks per split)
-  int best_bn = 128, best_split = 1;
+  // ---- tile configuration and split-K factor: split_k <= 0 = automatic (fill the SMs, >= 4 k-blocks per split)
+  int best_cfg = 0, best_split = 1;
   double best_cost = 1e30;
-  const char* force_bn = getenv("ICAP_GEMM_BN");
-  for (int bn = 256; bn >= 128; bn -= 128) {
-    if (force_bn && atoi(force_bn) != bn) continue;
-    if (bn == 256 && N <= 128) continue;
-    const int64_t tiles = tiles_m * ceil_div64(N, bn);
+  const char* force_bn = getenv("ICAP_GEMM_BN");          // "128" | "256" | "pair"
+  for (int c = 2; c >= 0; --c) {
+    if (force_bn) {
+      const int want = force_bn[0] == 'p' ? 2 : (atoi(force_bn) == 256 ? 1 : 0);
+      if (want != c) continue;
+    }
+    const int bn = c == 0 ? 128 : 256, bm = c == 2 ? 256 : 128;
+    if (c >= 1 && N <= 128 && !force_bn) continue;
+    if (c == 2 && !force_bn && (M <= 128 || getenv("ICAP_GEMM_NO_PAIR"))) continue;
+    const int64_t tiles = ceil_div64(M, bm) * ceil_div64(N, bn);
+    const int workers = c == 2 ? sms / 2 : sms;
     int split = split_k;
     if (split <= 0) {
       split = 1;
-      if (can_split && tiles < sms) {
-        split = (int)(sms / tiles);
+      if (can_split && tiles < workers) {
+        split = (int)(workers / tiles);
         if (split > nkb / 4) split = nkb / 4;
         if (split < 1) split = 1;
       }
@@ -534,13 +686,23 @@ int icap_gemm_bf16_launch(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int6
     if (split > 1 && !can_split) split = 1;
     int kb_per = (nkb + split - 1) / split;
     split = (nkb + kb_per - 1) / kb_per;
-    const double cost = est_cost(tiles * split, kb_per, bn, sms);
-    if (cost < best_cost) { best_cost = cost; best_bn = bn; best_split = split; }
+    double cost = est_cost(tiles * split, kb_per, c, sms);
+    if (c == 2 && !force_bn) {
+      // CTA pairs (2/3 of the operand traffic, ~1 us more setup) only pay off for long per-worker k loops, or when
+      // an operand's row pitch is not a multiple of 128 B (every TMA box row then straddles two L2 lines):
+      // measured with tools/gemm_bench.py -- embed / classifier dgrad+wgrad win 12-18 %, K <= 2048 shapes lose ~10 %.
+      const int64_t work = (int64_t)kb_per * ((tiles * split + workers - 1) / workers);
+      const bool ragged_pitch = (lda * 2) % 128 != 0 || (ldb * 2) % 128 != 0;
+      if (!(work >= 80 || (ragged_pitch && work >= 32))) continue;
+      cost = 0.0;                            // eligible: take it
+    }
+    if (cost < best_cost) { best_cost = cost; best_cfg = c; best_split = split; }
   }
   if (split_k > 1)
     ICAP_ARG(can_split, "icap_gemm(bf16): split_k>1 needs fp32 C, accumulate!=0, no bias and no activation epilogue");
   split_k = best_split;
-  const int BN = best_bn;
+  const bool two = best_cfg == 2;
+  const int BN = best_cfg == 0 ? 128 : 256;
   const int kb_per = (nkb + split_k - 1) / split_k;
   if (split_k > 1) accumulate = 2;
   ICAP_ARG(accumulate != 2 || c_dtype == ICAP_F32, "icap_gemm(bf16): atomic accumulate needs fp32 C");
@@ -549,7 +711,7 @@ int icap_gemm_bf16_launch(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int6
   int rc;
   if (a_kmajor) rc = make_tmap(&ta, A, M, K, lda, BM); else rc = make_tmap(&ta, A, K, M, lda, 64);
   if (rc) return rc;
-  if (b_kmajor) rc = make_tmap(&tb, B, N, K, ldb, BN); else rc = make_tmap(&tb, B, K, N, ldb, 64);
+  if (b_kmajor) rc = make_tmap(&tb, B, N, K, ldb, two ? BN / 2 : BN); else rc = make_tmap(&tb, B, K, N, ldb, 64);
   if (rc) return rc;
   const int esz = c_dtype == ICAP_F32 ? 4 : 2;
   int vec_ok = ((uintptr_t)C % 16 == 0) && ((ldc * esz) % 16 == 0);
@@ -562,11 +724,14 @@ int icap_gemm_bf16_launch(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int6
   GemmArgs g;
   g.M = (int)M; g.N = (int)N; g.K = (int)K;
   g.C = C; g.ldc = ldc; g.bias = bias; g.epi = epi; g.aux = aux; g.ldaux = ldaux; g.accumulate = accumulate;
-  g.kb_per_split = kb_per; g.splits = split_k; g.tiles_m = (int)tiles_m; g.tiles_n = (int)ceil_div64(N, BN);
+  g.kb_per_split = kb_per; g.splits = split_k;
+  g.tiles_m = (int)ceil_div64(M, two ? 2 * BM : BM); g.tiles_n = (int)ceil_div64(N, BN);
   g.vec_ok = vec_ok; g.store_mode = store_mode;
-#define GO2(BNV, AK, BKM) \
-  (c_dtype == ICAP_F32 ? launch<BNV, AK, BKM, float>(ta, tb, tc, g, st) : launch<BNV, AK, BKM, bf16>(ta, tb, tc, g, st))
-#define GO(AK, BKM) (BN == 256 ? GO2(256, AK, BKM) : GO2(128, AK, BKM))
+  { const char* e = getenv("ICAP_GEMM_DEBUG"); g.debug = e ? atoi(e) : 0; }
+#define GO2(BNV, TW, AK, BKM)                                                                          \
+  (c_dtype == ICAP_F32 ? launch<BNV, TW, AK, BKM, float>(ta, tb, tc, g, st)                              \
+                       : launch<BNV, TW, AK, BKM, bf16>(ta, tb, tc, g, st))
+#define GO(AK, BKM) (two ? GO2(256, true, AK, BKM) : BN == 256 ? GO2(256, false, AK, BKM) : GO2(128, false, AK, BKM))
   if (a_kmajor && b_kmajor) return GO(true, true);
   if (a_kmajor && !b_kmajor) return GO(true, false);
   return GO(false, false);

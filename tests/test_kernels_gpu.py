@@ -93,10 +93,11 @@ def test_gemm_bf16_tcgen05_epilogues():
     assert _gemm_case(BF16, 0, 0, 512, 512, 9216, accumulate=1, split_k=18) < 1e-5
 
 
-@pytest.mark.parametrize("bn", ["128", "256"])
+@pytest.mark.parametrize("bn", ["128", "256", "pair"])
 def test_gemm_bf16_persistent_multi_tile(bn, monkeypatch):
     """More tiles than SMs: every CTA loops over several tiles (TMEM accumulator double buffering, smem ring
-    phases carried across tiles), both tile widths, every epilogue, automatic split-K."""
+    phases carried across tiles), all tile configurations (128x128, 128x256, cta_group::2 pair 256x256), every
+    epilogue, automatic split-K."""
     monkeypatch.setenv("ICAP_GEMM_BN", bn)
     assert _gemm_case(BF16, 1, 1, 9216, 2048, 512, c_dtype=BF16, bias=True, epi=1) < 6e-3      # FFN1 forward
     assert _gemm_case(BF16, 1, 0, 9216, 2048, 512, c_dtype=BF16, epi=2) < 6e-3                 # FFN2 dgrad + ReLU mask

@@ -48,7 +48,9 @@ SHAPES = [
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=50)
-    ap.add_argument("--bn", default="128,256,auto")
+    ap.add_argument("--bn", default="256,pair,auto")
+    ap.add_argument("--only", default="", help="substring filter on the shape name")
+    ap.add_argument("--eager", action="store_true", help="no CUDA graph (for ncu)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     st = torch.cuda.current_stream().cuda_stream
@@ -56,6 +58,8 @@ def main():
     tot = {}
     print(f"{'shape':24s} {'M':>6s} {'N':>6s} {'K':>6s} " + " ".join(f"{'us@' + b:>10s} {'TF/s':>7s}" for b in args.bn.split(",")))
     for name, ak, bk, M, Nn, K, cdt, bias, epi, acc, split, cnt in SHAPES:
+        if args.only and args.only not in name:
+            continue
         A = torch.randn((M, K) if ak else (K, M), device=dev).bfloat16()
         B = torch.randn((Nn, K) if bk else (K, Nn), device=dev).bfloat16()
         C = torch.zeros(M, Nn, device=dev, dtype=torch.float32 if cdt == F32 else torch.bfloat16)
@@ -75,6 +79,9 @@ def main():
             for _ in range(5):
                 go()
             torch.cuda.synchronize()
+            if args.eager:
+                row += "  (eager: not timed) "
+                continue
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             # CUDA graph of `iters` back-to-back launches: no host launch overhead in the measurement
             gr = torch.cuda.CUDAGraph()
