@@ -30,6 +30,7 @@ SIGNATURES = {
     "icap_beam_select": [I, L, L, L, P, L, P, L, P, P, P, P, I, P],
     "icap_beam_reorder": [L, L, L, L, P, P, P, P, P, P, P],
     "icap_mha_decode": [I, L, L, L, L, L, P, L, P, L, P, L, L, P, L, P, L, P, L, I, P, L, P, P],
+    "icap_mha_decode_self": [I, L, L, L, L, L, P, L, P, P, L, P, L, P, L, L, P, L, P, L, P, L, I, P],
     "icap_copy2d": [P, I, L, P, I, L, L, L, I, P],
     "icap_rows_gather_add": [I, P, L, P, L, P, L, L, L, L, L, L, P],
     "icap_rows_segsum_add": [I, P, L, P, L, L, L, L, L, L, P],

@@ -173,6 +173,7 @@ argmax_kernel(int V, const T* __restrict__ logits, int64_t ldl, int* __restrict_
   }
 }
 
+constexpr int CAND_CAP = 1024;   // fast-path candidate list of beam_select
 constexpr int KMAX = 8;   // beam width limit; lists hold KMAX+1 entries so the k/(k+1) gap can be reported
 
 struct Cand { float s; int i; };
@@ -190,16 +191,42 @@ beam_select_kernel(int kin, int V, const T* __restrict__ logits, int64_t ldl, co
   __shared__ int h_i[NT], h_t[NT];
   const int b = blockIdx.x;
   const bool vec = ((uintptr_t)logits % 16 == 0) && (ldl * sizeof(T)) % 16 == 0;
+  const int L = kout + 1;
+  __shared__ float s_t1[KMAX], s_t2[KMAX];           // two largest logits of every row
+  __shared__ float red2[2][NT / 32];
+  __shared__ float c_s[CAND_CAP];
+  __shared__ int c_i[CAND_CAP];
+  __shared__ int c_n;
+  __shared__ float s_tau;
   for (int r = 0; r < kin; ++r) {
     const T* x = logits + ((int64_t)b * kin + r) * ldl;
-    float mx = -INFINITY;
+    float t1 = -INFINITY, t2 = -INFINITY;             // t1 >= t2: the thread's two largest logits (= max pass)
     for (int j = threadIdx.x * 8; j < V; j += NT * 8) {
       float v[8];
       load_chunk8(x, j, V, vec, v);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) mx = fmaxf(mx, v[i]);
+      for (int i = 0; i < 8; ++i) {
+        const float xv = v[i];
+        if (xv > t1) { t2 = t1; t1 = xv; } else if (xv > t2) t2 = xv;
+      }
     }
-    mx = block_max(mx, red);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {                // merge the sorted pairs across the warp
+      const float o1 = __shfl_xor_sync(0xffffffffu, t1, o), o2 = __shfl_xor_sync(0xffffffffu, t2, o);
+      const float n1 = fmaxf(t1, o1);
+      t2 = fmaxf(fminf(t1, o1), fmaxf(t2, o2));
+      t1 = n1;
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { red2[0][threadIdx.x >> 5] = t1; red2[1][threadIdx.x >> 5] = t2; }
+    __syncthreads();
+    float mx = red2[0][0], m2 = red2[1][0];
+    for (int i = 1; i < NT / 32; ++i) {
+      const float o1 = red2[0][i], o2 = red2[1][i];
+      const float n1 = fmaxf(mx, o1);
+      m2 = fmaxf(fminf(mx, o1), fmaxf(m2, o2));
+      mx = n1;
+    }
     float sum = 0.f;
     for (int j = threadIdx.x * 8; j < V; j += NT * 8) {
       float v[8];
@@ -208,10 +235,89 @@ beam_select_kernel(int kin, int V, const T* __restrict__ logits, int64_t ldl, co
       for (int i = 0; i < 8; ++i) if (i < n) sum += expf(v[i] - mx);
     }
     sum = block_sum(sum, red);
-    if (threadIdx.x == 0) { s_mx[r] = mx; s_den[r] = log_domain ? logf(sum) : sum; }
+    if (threadIdx.x == 0) {
+      s_mx[r] = mx; s_den[r] = log_domain ? logf(sum) : sum;
+      s_t1[r] = mx; s_t2[r] = m2;
+    }
   }
+  if (threadIdx.x == 0) c_n = 0;
   __syncthreads();
-  const int L = kout + 1;
+  // ---- fast path: tau = the L-th largest of the 2*kin scores {score(row r, its top-2 logits)} is a lower bound of
+  // the L-th best candidate overall, so only candidates with score >= tau (a handful) have to be collected and ranked.
+  bool fast = 2 * kin >= L;
+  if (fast) {
+    if (threadIdx.x == 0) {
+      float cs[2 * KMAX];
+      for (int r = 0; r < kin; ++r) {
+        const float pv = prev ? prev[b * kin + r] : 0.f;
+        cs[2 * r] = (log_domain ? (s_t1[r] - s_mx[r] - s_den[r]) : (expf(s_t1[r] - s_mx[r]) / s_den[r])) + pv;
+        cs[2 * r + 1] = (log_domain ? (s_t2[r] - s_mx[r] - s_den[r]) : (expf(s_t2[r] - s_mx[r]) / s_den[r])) + pv;
+      }
+      for (int a = 0; a < L; ++a)                      // partial selection sort: cs[L-1] = L-th largest
+        for (int c = a + 1; c < 2 * kin; ++c)
+          if (cs[c] > cs[a]) { const float t = cs[a]; cs[a] = cs[c]; cs[c] = t; }
+      s_tau = cs[L - 1];
+    }
+    __syncthreads();
+    const float tau = s_tau;
+    for (int r = 0; r < kin; ++r) {
+      const T* x = logits + ((int64_t)b * kin + r) * ldl;
+      const float mx = s_mx[r], den = s_den[r], pv = prev ? prev[b * kin + r] : 0.f;
+      float tl;                                        // logit whose score is tau, minus a safety margin
+      if (log_domain) tl = tau - pv + mx + den;
+      else { const float need = tau - pv; tl = need > 0.f ? mx + logf(need * den) : -INFINITY; }
+      tl -= 1e-3f;
+      for (int j0 = threadIdx.x * 8; j0 < V; j0 += NT * 8) {
+        float v[8];
+        const int n = load_chunk8(x, j0, V, vec, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (i >= n) break;
+          const float xv = v[i];
+          if (!(xv > tl)) continue;
+          const float sc = (log_domain ? (xv - mx - den) : (expf(xv - mx) / den)) + pv;
+          if (sc >= tau) {
+            const int pos = atomicAdd(&c_n, 1);
+            if (pos < CAND_CAP) { c_s[pos] = sc; c_i[pos] = r * V + j0 + i; }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    const int cn = c_n;
+    if (cn <= CAND_CAP) {
+      if (threadIdx.x < 32) {                          // warp 0: L rounds of "best remaining candidate"
+        const int lane = threadIdx.x;
+        float kth = 0.f;
+        for (int round = 0; round < L; ++round) {
+          float bs = -INFINITY;
+          int bi = 0x7fffffff, bp = -1;
+          for (int e = lane; e < cn; e += 32)
+            if (better(c_s[e], c_i[e], bs, bi)) { bs = c_s[e]; bi = c_i[e]; bp = e; }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o), op = __shfl_xor_sync(0xffffffffu, bp, o);
+            if (better(os, oi, bs, bi)) { bs = os; bi = oi; bp = op; }
+          }
+          if (lane == 0) {
+            if (bp >= 0) { c_s[bp] = -INFINITY; c_i[bp] = 0x7fffffff; }
+            if (round < kout) {
+              out_score[b * kout + round] = bs;
+              out_parent[b * kout + round] = bi / V;
+              out_token[b * kout + round] = bi % V;
+              kth = bs;
+            } else if (gap) {
+              gap[b] = kth - bs;
+            }
+          }
+          __syncwarp();
+        }
+      }
+      return;
+    }
+    // more than CAND_CAP candidates tie with tau (degenerate logits): exact but slow path below
+  }
   Cand lst[KMAX + 1];                      // sorted, best first; only static indices (stays in registers)
 #pragma unroll
   for (int t = 0; t <= KMAX; ++t) { lst[t].s = -INFINITY; lst[t].i = 0x7fffffff; }

@@ -116,6 +116,15 @@ int icap_mha_decode(int dtype, int64_t rows, int64_t H, int64_t Lk, int64_t dk, 
                     int64_t ldo, const int* slot, int64_t slot_ld, const int* tokens, int64_t tok_ld, int pad_idx,
                     const uint8_t* kvalid, int64_t rows_per_image, float* attn_mean, void* stream);
 
+/* Self-attention decode step with the KV-cache append fused in: the key / value of position `pos` (rows of k_new /
+ * v_new, leading dimension ld_new) are written to the row's own cache line (kc/vc + (row*kv_rows_per_seq + pos)*ld)
+ * and attended together with the cached positions 0..pos-1 (slot table / pad-token mask as in icap_mha_decode).
+ * Replaces the per-step prefix recomputation of model.py:114-122,169-180 (decoder self-attention, modules.py:190-194). */
+int icap_mha_decode_self(int dtype, int64_t rows, int64_t H, int64_t pos, int64_t dk, int64_t dv, const void* q,
+                         int64_t ldq, const void* k_new, const void* v_new, int64_t ld_new, void* kc, int64_t ldk, void* vc,
+                         int64_t ldv, int64_t kv_rows_per_seq, void* o, int64_t ldo, const int* slot, int64_t slot_ld,
+                         const int* tokens, int64_t tok_ld, int pad_idx, void* stream);
+
 /* dst[r][c] (+)= convert(src[r][c]) : operand packing / dtype casts / gradient unpacking. */
 int icap_copy2d(const void* src, int src_dtype, int64_t src_ld, void* dst, int dst_dtype, int64_t dst_ld, int64_t rows,
                 int64_t cols, int accumulate, void* stream);

@@ -138,6 +138,36 @@ def test_gemm_bf16_vocab_shapes():
     assert rel_err(dW, C.double().t() @ X.double()) < 1e-5
 
 
+def test_mha_decode_self_fused_append():
+    """icap_mha_decode_self (KV-cache append fused into the attention) == explicit append + icap_mha_decode, for the
+    head-dim-64 fast path and the generic path, with beam slot indirection and pad-token masking."""
+    for act, dh in ((BF16, 64), (F32, 64), (F32, 16)):
+        g = torch.Generator(device="cuda").manual_seed(9 + dh)
+        tdt = dt(act)
+        rows, H, T, t = 24, 4, 9, 5
+        d = H * dh
+        q = torch.randn(rows, 3 * d, device=dev(), generator=g).to(tdt)            # packed [q | k_new | v_new]
+        cache = torch.randn(rows, T, 2 * d, device=dev(), generator=g).to(tdt)
+        tok = torch.randint(0, 4, (rows, T + 1), device=dev(), generator=g, dtype=torch.int32)   # id 0 = pad
+        tok[:, 0] = 1
+        slot = torch.randint(0, rows, (rows, T + 1), device=dev(), generator=g, dtype=torch.int32)
+        slot[:, t] = torch.arange(rows, dtype=torch.int32, device=dev())          # newest position: own row
+        esz = q.element_size()
+        ref_cache = cache.clone()
+        ref_cache[:, t, :] = q[:, d:]
+        o_ref = torch.empty(rows, d, device=dev(), dtype=tdt)
+        N.call("icap_mha_decode", act, rows, H, t + 1, dh, dh, q.data_ptr(), 3 * d, ref_cache.data_ptr(), 2 * d,
+               ref_cache.data_ptr() + d * esz, 2 * d, T, o_ref.data_ptr(), d, slot.data_ptr(), T + 1, tok.data_ptr(), T + 1,
+               0, None, 1, None, S())
+        o = torch.empty(rows, d, device=dev(), dtype=tdt)
+        N.call("icap_mha_decode_self", act, rows, H, t, dh, dh, q.data_ptr(), 3 * d, q.data_ptr() + d * esz,
+               q.data_ptr() + 2 * d * esz, 3 * d, cache.data_ptr(), 2 * d, cache.data_ptr() + d * esz, 2 * d, T,
+               o.data_ptr(), d, slot.data_ptr(), T + 1, tok.data_ptr(), T + 1, 0, S())
+        torch.cuda.synchronize()
+        assert torch.equal(cache, ref_cache)
+        assert rel_err(o, o_ref) < (1e-5 if act == F32 else 1e-2)
+
+
 # ------------------------------------------------------------------------------------------ add + LayerNorm
 @pytest.mark.parametrize("act", [F32, BF16])
 @pytest.mark.parametrize("M,d", [(77, 32), (500, 512), (64, 1024), (33, 256)])
