@@ -246,9 +246,11 @@ def run_ours(args):
     e2e_value = world * BATCH * args.steps / (float(t) / 1e3)
 
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
+        # No process-group teardown: destroying the NCCL communicator while CUDA graphs that captured its
+        # collectives are alive can hang; the timed work is done and rank 0 needs no further collective.
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        os._exit(0)
 
     # ---------------- per-kernel roofline: CUDA events around every GEMM launch of one eager step
     if args.ncu_region:       # one eager step bracketed by cudaProfilerStart/Stop for `ncu --profile-from-start off`
@@ -354,8 +356,10 @@ def run_ours(args):
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "extra": extra}
     print(json.dumps(line))
+    sys.stdout.flush()
     if dist is not None:
-        dist.destroy_process_group()
+        torch.cuda.synchronize(dev)
+        os._exit(0)          # see the note at the non-zero ranks' exit above
 
 
 def main():

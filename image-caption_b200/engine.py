@@ -183,7 +183,9 @@ class CaptionEngine:
         self.training = False
         self._site = 0
         self._stream = 0
-        self.bucket_hook: Optional[Callable[[str], None]] = None   # data-parallel: called as grads complete
+        # data parallel: called after every backward closure with the lowest flat offset it wrote (or None);
+        # gradients complete from the END of the flat buffer towards its start (reverse registration order)
+        self.bucket_hook: Optional[Callable[[Optional[int]], None]] = None
         for k in ("encode_q_k_dim", "encode_v_dim", "decode_q_k_dim", "decode_v_dim"):
             assert getattr(cfg, k) % 8 == 0, f"{k} must be a multiple of 8"
         assert cfg.encode_input_size == cfg.decode_input_size, \
@@ -424,6 +426,7 @@ class CaptionEngine:
                         dxkv = self.new(Mk, d)
                         self.gemm(dkv, True, self.w(wk), d, False, Mk, d, dk_tot + dv_tot, dxkv)
                         gl.append(dxkv)
+            bwd.lo = self.offsets[wq]          # lowest flat offset this closure writes gradients to (DP buckets)
             self.tape.append(bwd)
         return y
 
@@ -455,6 +458,7 @@ class CaptionEngine:
                 dx = self.new(M, d)
                 self.gemm(dh, True, self.w(w1), d, False, M, d, hidden, dx)
                 self.add_grad(gin, dx)
+            bwd.lo = self.offsets[w1] if prefix != "decoder" else None     # the move_first tail completes out of order
             self.tape.append(bwd)
         return y
 
@@ -613,6 +617,7 @@ class CaptionEngine:
                 self.gemm(ds, True, self.w("decoder.word_embedding_linear.weight"), E, False, M, E, d, demb)
                 call("icap_embed_bwd", self.act, inp.data_ptr(), M, E, cfg.pad_idx, demb.data_ptr(),
                      self.g("decoder.word_embedding.weight"), self._s())
+            bwd.lo = self.offsets["decoder.word_embedding.weight"]
             self.tape.append(bwd)
         for i in range(cfg.decode_num_blocks):
             pre = f"decoder.decoder.{i}"
@@ -713,6 +718,7 @@ class CaptionEngine:
                 dx = self.new(M, d)
                 self.gemm(logits, True, self.w("classifer.weight"), d, False, M, d, V, dx, lda=ldl)
                 self.add_grad(dec, dx)
+            bwd.lo = self.offsets["classifer.weight"]
             self.tape.append(bwd)
         return out2
 
@@ -732,7 +738,7 @@ class CaptionEngine:
             for fn in reversed(self.tape):
                 fn()
                 if self.bucket_hook is not None:
-                    self.bucket_hook(getattr(fn, "__qualname__", ""))
+                    self.bucket_hook(getattr(fn, "lo", None))
         finally:
             if self._bwd_side is not None:
                 main.wait_stream(self._bwd_side)      # every weight gradient has landed in g32

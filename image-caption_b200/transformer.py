@@ -288,21 +288,56 @@ class Transformer(nn.Module):
         return out2[0]
 
 
+class GradBuckets:
+    """Bucket schedule over the flat gradient buffer.  Gradients complete from the END of the buffer towards its
+    start (reverse registration order); `on_done(lo)` is told, after every backward closure, the lowest offset
+    that closure wrote, and answers with the slice [lo, hi) that may be all-reduced now (or None).  Every element
+    is handed out exactly once; `flush()` returns the remaining prefix."""
+
+    def __init__(self, total_elems: int, bucket_elems: int):
+        self.prev_lo = int(total_elems)
+        self.bucket_elems = int(bucket_elems)
+
+    def on_done(self, lo: Optional[int]):
+        if lo is None or lo >= self.prev_lo or self.prev_lo - lo < self.bucket_elems:
+            return None
+        out = (int(lo), self.prev_lo)
+        self.prev_lo = int(lo)
+        return out
+
+    def flush(self):
+        if self.prev_lo <= 0:
+            return None
+        out = (0, self.prev_lo)
+        self.prev_lo = 0
+        return out
+
+
 class DataParallel:
     """Data parallelism by image: one process per GPU, replicated weights and Adam state.
     Every rank back-propagates the SUM of its token losses (dlogits not divided by the local count); the flat
-    gradient buffer carries the local non-pad token count in its tail slot, so ONE all-reduce(SUM) yields both
+    gradient buffer carries the local non-pad token count in its tail slot, so the all-reduce(SUM) yields both
     the summed gradients and the global count, and Adam divides by it (gscale).  That reproduces the
-    reference's global `mean over non-pad targets` exactly, whatever the per-rank token counts are."""
+    reference's global `mean over non-pad targets` exactly, whatever the per-rank token counts are.
 
-    def __init__(self, model: "Transformer", dist):
+    Overlap: gradients become final from the END of the flat buffer (classifier) towards its start (encoder
+    embeddings) as the backward proceeds, so the buffer is reduced in `bucket_mb` slices, each launched on a
+    communication stream as soon as its slice is complete (engine.bucket_hook) while the backward continues."""
+
+    def __init__(self, model: "Transformer", dist, bucket_mb: float = 48.0, overlap: bool = True):
         self.dist = dist
         self.world = dist.get_world_size()
         eng = model._engine()
         eng.dp_unnormalized = True
         dist.broadcast(eng.p32, src=0)          # identical replicas
         eng.shadow_fresh = False
+        self.eng = eng
         self.inv = torch.zeros(1, dtype=torch.float32, device=eng.dev)
+        self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
+        self.overlap = overlap and os.environ.get("ICAP_DP_OVERLAP", "1") != "0"
+        self.comm: Optional[torch.cuda.Stream] = None
+        self.plan: Optional[GradBuckets] = None
+        self.n_buckets = 0
 
     @staticmethod
     def allreduce_flat(dist, g32: torch.Tensor, n_flat: int) -> torch.Tensor:
@@ -313,10 +348,52 @@ class DataParallel:
     def reduce(self, eng: CaptionEngine) -> None:
         self.allreduce_flat(self.dist, eng.g32, eng.n_flat)
 
+    # ---- bucketed, overlapped with the backward
+    def begin(self, eng: CaptionEngine) -> None:
+        """Call before forward_backward: arms the bucket hook."""
+        if self.comm is None:
+            self.comm = torch.cuda.Stream(device=eng.dev)
+        self.plan = GradBuckets(eng.g32.numel(), self.bucket_elems)     # includes the token-count tail slot
+        self.n_buckets = 0
+        eng.bucket_hook = self._closure_done
+
+    def _fire(self, sl) -> None:
+        if sl is None:
+            return
+        eng = self.eng
+        main = torch.cuda.current_stream(eng.dev)
+        self.comm.wait_stream(main)
+        if eng._bwd_side is not None:
+            self.comm.wait_stream(eng._bwd_side)  # weight gradients are written by the wgrad side stream
+        with torch.cuda.stream(self.comm):
+            self.dist.all_reduce(eng.g32[sl[0]:sl[1]], op=self.dist.ReduceOp.SUM)
+        self.n_buckets += 1
+
+    def _closure_done(self, lo: Optional[int]) -> None:
+        self._fire(self.plan.on_done(lo))
+
+    def end(self, eng: CaptionEngine) -> None:
+        """Call after forward_backward: reduces what is left and joins the communication stream."""
+        eng.bucket_hook = None
+        self._fire(self.plan.flush())
+        torch.cuda.current_stream(eng.dev).wait_stream(self.comm)
+
     def finish(self, eng: CaptionEngine, lr: float) -> None:
         from ._native import call
         call("icap_reciprocal", eng.g32.data_ptr() + 4 * eng.n_flat, self.inv.data_ptr(), 1.0, eng._s())
         eng.adam_step(lr, gscale_dev=self.inv)
+
+    def step_eager(self, eng: CaptionEngine, feats, pos, cap, lr: float) -> torch.Tensor:
+        """One data-parallel train step without CUDA graphs."""
+        if self.overlap:
+            self.begin(eng)
+            out2 = eng.forward_backward(feats, pos, cap)
+            self.end(eng)
+        else:
+            out2 = eng.forward_backward(feats, pos, cap)
+            self.reduce(eng)
+        self.finish(eng, lr)
+        return out2
 
 
 class GraphedDecode:
@@ -409,6 +486,7 @@ class GraphedTrainStep:
         self.out2: Optional[torch.Tensor] = None
         self.warmup = warmup
         self.launches_per_step = 0
+        self.single_graph_dp = False
 
     def load(self, feats: torch.Tensor, pos: torch.Tensor, cap: torch.Tensor) -> None:
         self.feats.copy_(feats, non_blocking=True)
@@ -428,9 +506,7 @@ class GraphedTrainStep:
                 if self.dp is None:
                     eng.train_step(self.feats, self.pos, self.cap, lr=self.lr)
                 else:
-                    eng.forward_backward(self.feats, self.pos, self.cap)
-                    self.dp.reduce(eng)
-                    self.dp.finish(eng, self.lr)
+                    self.dp.step_eager(eng, self.feats, self.pos, self.cap, self.lr)
         torch.cuda.current_stream(eng.dev).wait_stream(side)
         eng.p32.copy_(p0)
         eng.step_dev.copy_(step0)
@@ -444,7 +520,21 @@ class GraphedTrainStep:
         if self.dp is None:
             with torch.cuda.graph(self.graph):
                 self.out2 = eng.train_step(self.feats, self.pos, self.cap, lr=self.lr)
-        else:     # graph 1: zero_grad/forward/backward ; NCCL all-reduce (eager) ; graph 2: 1/count + Adam
+        elif self.dp.overlap:
+            # ONE graph: forward, backward with the bucketed NCCL all-reduces on the communication stream, Adam
+            try:
+                with torch.cuda.graph(self.graph):
+                    self.out2 = self.dp.step_eager(eng, self.feats, self.pos, self.cap, self.lr)
+                self.single_graph_dp = True
+            except Exception as exc:     # NCCL not capturable in this build: fall back to the split graphs below
+                import warnings
+                warnings.warn(f"capturing NCCL all-reduces failed ({exc!r}); using eager all-reduce between two graphs")
+                eng.bucket_hook = None
+                self.dp.overlap = False
+                torch.cuda.synchronize(eng.dev)
+                self.graph = torch.cuda.CUDAGraph()
+        if self.dp is not None and not self.dp.overlap:
+            # graph 1: zero_grad/forward/backward ; NCCL all-reduce (eager) ; graph 2: 1/count + Adam
             with torch.cuda.graph(self.graph):
                 self.out2 = eng.forward_backward(self.feats, self.pos, self.cap)
             self.graph2 = torch.cuda.CUDAGraph()
@@ -456,7 +546,7 @@ class GraphedTrainStep:
         if self.graph is None:
             self.capture()
         self.graph.replay()
-        if self.dp is not None:
+        if self.graph2 is not None:
             self.dp.reduce(self.eng)
             self.graph2.replay()
         return self.out2[0]

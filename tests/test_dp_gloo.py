@@ -51,6 +51,52 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _bucket_worker(rank, world, port, q):
+    """Bucketed all-reduce in backward-completion order == one all-reduce of the whole buffer."""
+    sys.path.insert(0, ROOT)
+    import icap_loader
+    pkg = icap_loader.load()
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(100 + rank)
+    n = 10_000 + 8
+    flat = torch.randn(n, generator=g)
+    whole = flat.clone()
+    dist.all_reduce(whole)
+    plan = pkg.GradBuckets(n, 1500)
+    fired = []
+    # closures finish with descending (and a few out-of-order / None) lowest offsets
+    for lo in [9500, None, 9000, 9700, 8400, 8399, 6000, 6100, None, 3000, 2999, 100]:
+        sl = plan.on_done(lo)
+        if sl is not None:
+            dist.all_reduce(flat[sl[0]:sl[1]])
+            fired.append(sl)
+    sl = plan.flush()
+    dist.all_reduce(flat[sl[0]:sl[1]])
+    fired.append(sl)
+    assert plan.flush() is None
+    covered = sorted(fired)
+    ok_cover = covered[0][0] == 0 and covered[-1][1] == n and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+    if rank == 0:
+        q.put((bool(torch.equal(flat, whole)), ok_cover, len(fired)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dp_bucketed_allreduce_equals_whole_buffer():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 200
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    same, cover, nb = q.get(timeout=120)
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert same and cover and nb >= 3
+
+
 def test_dp_allreduce_reproduces_global_mean_gradient():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
