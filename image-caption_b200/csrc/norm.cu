@@ -546,10 +546,11 @@ extern "C" int icap_add_ln_fwd(int a_dtype, int act_dtype, int64_t M, int64_t d,
   return 0;
 }
 
-extern "C" int icap_add_ln_bwd(int act_dtype, int64_t M, int64_t d, const void* dy1, const void* dy2, const void* s,
-                               const float* mean, const float* rstd, const float* gamma, const float* rowscale,
-                               void* ds, void* da, float* dgamma, float* dbeta, float* dbias2, float p_drop,
-                               uint64_t seed, const int* seed_dev, void* stream) {
+// which: bit 0 = row kernel (ds / da), bit 1 = column kernel (dgamma / dbeta / dbias2)
+static int add_ln_bwd_impl(int which, int act_dtype, int64_t M, int64_t d, const void* dy1, const void* dy2, const void* s,
+                           const float* mean, const float* rstd, const float* gamma, const float* rowscale,
+                           void* ds, void* da, float* dgamma, float* dbeta, float* dbias2, float p_drop,
+                           uint64_t seed, const int* seed_dev, void* stream) {
   ICAP_ARG(d % 4 == 0 && d <= MAX_IT * 128, "icap_add_ln_bwd: d=%lld must be a multiple of 4 and <= %d", (long long)d,
            MAX_IT * 128);
   ICAP_ARG(M > 0 && dy1 && s && mean && rstd && gamma, "icap_add_ln_bwd: null argument");
@@ -577,7 +578,7 @@ extern "C" int icap_add_ln_bwd(int act_dtype, int64_t M, int64_t d, const void* 
                                                                (T*)da, p_drop, th, seed, seed_dev)
 #define GOBT8(T)                                                                                                  \
   do {                                                                                                            \
-    if (ds || da) {                                                                                               \
+    if ((ds || da) && (which & 1)) {                                                                              \
       if (d <= 256) GOB8(1, T);                                                                                   \
       else if (d <= 512) GOB8(2, T);                                                                              \
       else GOB8(4, T);                                                                                            \
@@ -600,13 +601,13 @@ extern "C" int icap_add_ln_bwd(int act_dtype, int64_t M, int64_t d, const void* 
                                                              (T*)da, p_drop, th, seed, seed_dev)
 #define GOBT(T)                                                                                                   \
   do {                                                                                                            \
-    if (ds || da) {                                                                                               \
+    if ((ds || da) && (which & 1)) {                                                                              \
       if (d <= 128) GOB(1, T);                                                                                    \
       else if (d <= 256) GOB(2, T);                                                                               \
       else if (d <= 512) GOB(4, T);                                                                               \
       else GOB(8, T);                                                                                             \
     }                                                                                                             \
-    if (dgamma || dbeta || dbias2)                                                                                \
+    if ((dgamma || dbeta || dbias2) && (which & 2))                                                               \
       icap_launch(add_ln_bwd_cols_kernel<T>, cgrid, cblock, 0, st, (int)M, (int)d, (const T*)dy1, (const T*)dy2,           \
                                                           (const T*)s, mean, rstd, rowscale, (const T*)dab,      \
                                                           dgamma, dbeta, dbias2, rows_per_block);                 \
@@ -617,4 +618,27 @@ extern "C" int icap_add_ln_bwd(int act_dtype, int64_t M, int64_t d, const void* 
 #undef GOB
   ICAP_LAUNCH_CHECK("icap_add_ln_bwd");
   return 0;
+}
+
+extern "C" int icap_add_ln_bwd(int act_dtype, int64_t M, int64_t d, const void* dy1, const void* dy2, const void* s,
+                               const float* mean, const float* rstd, const float* gamma, const float* rowscale,
+                               void* ds, void* da, float* dgamma, float* dbeta, float* dbias2, float p_drop,
+                               uint64_t seed, const int* seed_dev, void* stream) {
+  return add_ln_bwd_impl(3, act_dtype, M, d, dy1, dy2, s, mean, rstd, gamma, rowscale, ds, da, dgamma, dbeta, dbias2,
+                         p_drop, seed, seed_dev, stream);
+}
+// The two halves of icap_add_ln_bwd separately: the parameter-gradient sums (dgamma / dbeta / dbias2) are not on the
+// critical path of the backward and may run on another stream AFTER the row kernel has produced ds / da.
+extern "C" int icap_add_ln_bwd_rows(int act_dtype, int64_t M, int64_t d, const void* dy1, const void* dy2, const void* s,
+                                    const float* mean, const float* rstd, const float* gamma, const float* rowscale,
+                                    void* ds, void* da, float p_drop, uint64_t seed, const int* seed_dev, void* stream) {
+  return add_ln_bwd_impl(1, act_dtype, M, d, dy1, dy2, s, mean, rstd, gamma, rowscale, ds, da, nullptr, nullptr, nullptr,
+                         p_drop, seed, seed_dev, stream);
+}
+extern "C" int icap_add_ln_bwd_params(int act_dtype, int64_t M, int64_t d, const void* dy1, const void* dy2, const void* s,
+                                      const float* mean, const float* rstd, const float* rowscale, const void* ds,
+                                      const void* da, float* dgamma, float* dbeta, float* dbias2, void* stream) {
+  alignas(16) static const float dummy_gamma[4] = {0.f, 0.f, 0.f, 0.f};     // not read by the column kernel, only null-checked
+  return add_ln_bwd_impl(2, act_dtype, M, d, dy1, dy2, s, mean, rstd, dummy_gamma, rowscale, const_cast<void*>(ds),
+                         const_cast<void*>(da), dgamma, dbeta, dbias2, 0.f, 0, nullptr, stream);
 }

@@ -274,12 +274,7 @@ class CaptionEngine:
             self._gemm_log.append(args)
         if self._bwd_side is not None and side_ok:
             # dy and x stay allocated until the end of backward (self.keep), so the side stream may read them late
-            main = torch.cuda.current_stream(self.dev)
-            ev = torch.cuda.Event()
-            ev.record(main)
-            self._bwd_side.wait_event(ev)
-            with torch.cuda.stream(self._bwd_side):
-                call("icap_gemm", *args, self._s())
+            self.side_call("icap_gemm", *args)
             return
         ev = self._prof_begin()
         call("icap_gemm", *args, self._s())
@@ -347,10 +342,34 @@ class CaptionEngine:
         M, d = s.shape
         ds = self.new(M, d)
         da = self.new(M, d) if p > 0 else None
-        call("icap_add_ln_bwd", self.act, M, d, gs[0].data_ptr(), _ptr(gs[1]) if len(gs) > 1 else None, s.data_ptr(),
-             mean.data_ptr(), rstd.data_ptr(), self.p(norm + ".weight"), _ptr(rowscale), ds.data_ptr(), _ptr(da),
-             self.g(norm + ".weight"), self.g(norm + ".bias"), dbias2, p, seed, self.step_dev.data_ptr(), self._s())
+        dy2 = _ptr(gs[1]) if len(gs) > 1 else None
+        if self._bwd_side is None:
+            call("icap_add_ln_bwd", self.act, M, d, gs[0].data_ptr(), dy2, s.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                 self.p(norm + ".weight"), _ptr(rowscale), ds.data_ptr(), _ptr(da), self.g(norm + ".weight"),
+                 self.g(norm + ".bias"), dbias2, p, seed, self.step_dev.data_ptr(), self._s())
+        else:
+            # ds / da on the main stream (the dgrad chain waits for them); the parameter-gradient column sums
+            # (dgamma, dbeta, bias of the producing GEMM) only feed the optimizer: side stream
+            call("icap_add_ln_bwd_rows", self.act, M, d, gs[0].data_ptr(), dy2, s.data_ptr(), mean.data_ptr(),
+                 rstd.data_ptr(), self.p(norm + ".weight"), _ptr(rowscale), ds.data_ptr(), _ptr(da), p, seed,
+                 self.step_dev.data_ptr(), self._s())
+            self.side_call("icap_add_ln_bwd_params", self.act, M, d, gs[0].data_ptr(), dy2, s.data_ptr(), mean.data_ptr(),
+                           rstd.data_ptr(), _ptr(rowscale), ds.data_ptr(), _ptr(da), self.g(norm + ".weight"),
+                           self.g(norm + ".bias"), dbias2)
         return ds, (da if da is not None else ds)
+
+    def side_call(self, name: str, *args) -> None:
+        """Launch a kernel whose results only feed the optimizer on the backward side stream (after everything
+        enqueued on the main stream so far); same stream when the side stream is off.  The stream is appended."""
+        if self._bwd_side is None:
+            call(name, *args, self._s())
+            return
+        main = torch.cuda.current_stream(self.dev)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._bwd_side.wait_event(ev)
+        with torch.cuda.stream(self._bwd_side):
+            call(name, *args, self._s())
 
     # ------------------------------------------------------------------ blocks
     def mha_block(self, prefix: str, xq: torch.Tensor, xkv: torch.Tensor, B: int, Lq: int, Lk: int, H: int,
@@ -453,7 +472,7 @@ class CaptionEngine:
                 self.wgrad(da, h, self.g(w2), d, hidden, M)
                 dh = self.new(M, hidden)
                 self.gemm(da, True, self.w(w2), hidden, False, M, hidden, d, dh, epi=N.EPI_RELU_MASK, aux=h)
-                call("icap_colsum", self.act, M, hidden, dh.data_ptr(), hidden, self.g(b1), self._s())
+                self.side_call("icap_colsum", self.act, M, hidden, dh.data_ptr(), hidden, self.g(b1))
                 self.wgrad(dh, gin, self.g(w1), hidden, d, M)
                 dx = self.new(M, d)
                 self.gemm(dh, True, self.w(w1), d, False, M, d, hidden, dx)
@@ -714,7 +733,7 @@ class CaptionEngine:
         if record:
             def bwd():
                 self.wgrad(logits, dec, self.g("classifer.weight"), V, d, M, ld_dy=ldl)
-                call("icap_colsum", self.act, M, V, logits.data_ptr(), ldl, self.g("classifer.bias"), self._s())
+                self.side_call("icap_colsum", self.act, M, V, logits.data_ptr(), ldl, self.g("classifer.bias"))
                 dx = self.new(M, d)
                 self.gemm(logits, True, self.w("classifer.weight"), d, False, M, d, V, dx, lda=ldl)
                 self.add_grad(dec, dx)

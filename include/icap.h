@@ -82,6 +82,16 @@ int icap_add_ln_bwd(int act_dtype, int64_t M, int64_t d, const void* dy1, const 
                     float* dgamma, float* dbeta, float* dbias2, float p_drop, uint64_t seed, const int* seed_dev,
                     void* stream);
 
+/* The two halves of icap_add_ln_bwd as separate launches: _rows writes ds / da (critical path of the backward),
+ * _params accumulates dgamma / dbeta / dbias2 from the same inputs plus the ds / da written by _rows (may run later,
+ * on another stream). */
+int icap_add_ln_bwd_rows(int act_dtype, int64_t M, int64_t d, const void* dy1, const void* dy2, const void* s,
+                         const float* mean, const float* rstd, const float* gamma, const float* rowscale, void* ds, void* da,
+                         float p_drop, uint64_t seed, const int* seed_dev, void* stream);
+int icap_add_ln_bwd_params(int act_dtype, int64_t M, int64_t d, const void* dy1, const void* dy2, const void* s,
+                           const float* mean, const float* rstd, const float* rowscale, const void* ds, const void* da,
+                           float* dgamma, float* dbeta, float* dbias2, void* stream);
+
 /* Fused log-softmax + NLL per row; with write_grad=1 the logits are overwritten IN PLACE by
  * (softmax - onehot) * inv_count[0] (zero rows for ignored targets).  row_loss: fp32 [M].
  * Replaces CrossEntropyLoss(ignore_index=pad_idx, 'mean'), model.py:76,93-96. */
