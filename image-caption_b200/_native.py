@@ -42,6 +42,7 @@ SIGNATURES = {
     "icap_embed_bwd": [I, P, L, L, I, P, P, P],
     "icap_colsum": [I, L, L, P, L, P, P],
     "icap_adam_step": [L, P, P, P, P, P, F, F, F, F, P, I, P, F, P],
+    "icap_step_tick": [P, P],
     "icap_scale": [P, L, P, F, P],
     "icap_reciprocal": [P, P, F, P],
 }

@@ -198,9 +198,10 @@ colsum8_kernel(const T* __restrict__ x, int64_t ld, int64_t M, int64_t N, float*
 // (+2 for the shadow).  step lives on the device so a captured CUDA graph can be replayed.
 __global__ void adam_kernel(int64_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, bf16* __restrict__ shadow, float lr, float b1, float b2, float eps,
-                            const int* __restrict__ step_ptr, const float* __restrict__ gscale_ptr, float gscale) {
+                            const int* __restrict__ step_ptr, const float* __restrict__ gscale_ptr, float gscale,
+                            int step_bias) {
   pdl_prologue();
-  const int step = *step_ptr;
+  const int step = *step_ptr + step_bias;
   const float bc1 = 1.f - powf(b1, (float)step);
   const float bc2 = 1.f - powf(b2, (float)step);
   const float step_size = lr / bc1, sqrt_bc2 = sqrtf(bc2);
@@ -417,10 +418,18 @@ extern "C" int icap_adam_step(int64_t n, float* p, const float* g, float* m, flo
                               float gscale, void* stream) {
   ICAP_ARG(n > 0 && n % 4 == 0 && p && g && m && v && step_dev, "icap_adam_step: bad argument (n must be a multiple of 4)");
   cudaStream_t st = (cudaStream_t)stream;
-  if (tick) icap_launch(step_tick_kernel, 1, 1, 0, st, step_dev);
+  ICAP_ARG(tick >= 0 && tick <= 2, "icap_adam_step: tick must be 0, 1 or 2");
+  if (tick == 1) icap_launch(step_tick_kernel, 1, 1, 0, st, step_dev);
   icap_launch(adam_kernel, grid_for(n / 4, 256), 256, 0, st, n, p, g, m, v, (bf16*)shadow_bf16, lr, beta1, beta2, eps, step_dev,
-                                                    gscale_dev, gscale);
+                                                    gscale_dev, gscale, tick == 2 ? 1 : 0);
   ICAP_LAUNCH_CHECK("icap_adam_step");
+  return 0;
+}
+
+extern "C" int icap_step_tick(int* step_dev, void* stream) {
+  ICAP_ARG(step_dev, "icap_step_tick: null argument");
+  icap_launch(step_tick_kernel, 1, 1, 0, (cudaStream_t)stream, step_dev);
+  ICAP_LAUNCH_CHECK("icap_step_tick");
   return 0;
 }
 

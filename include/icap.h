@@ -162,12 +162,15 @@ int icap_embed_bwd(int dtype, const int* tokens, int64_t M, int64_t E, int pad_i
                    void* stream);
 /* out[c] += sum_r x[r][c]  (bias gradients). */
 int icap_colsum(int dtype, int64_t M, int64_t N, const void* x, int64_t ld, float* out, void* stream);
-/* torch.optim.Adam step over flat fp32 buffers (+ bf16 shadow refresh); step counter on the device
- * (tick=1 increments it first); gradients are pre-multiplied by gscale * gscale_dev[0].
+/* torch.optim.Adam step over flat fp32 buffers (+ bf16 shadow refresh); step counter on the device: tick=1
+ * increments it first, tick=0 uses it as is, tick=2 uses step+1 WITHOUT incrementing (slices of the parameter
+ * buffer updated during the backward, while the dropout seeds of the step still read the old counter; finish with
+ * icap_step_tick); gradients are pre-multiplied by gscale * gscale_dev[0].
  * Replaces optimizer.step(), core/models.py:111-113,126. */
 int icap_adam_step(int64_t n, float* p, const float* g, float* m, float* v, void* shadow_bf16, float lr, float beta1,
                    float beta2, float eps, int* step_dev, int tick, const float* gscale_dev, float gscale,
                    void* stream);
+int icap_step_tick(int* step_dev, void* stream);
 int icap_scale(float* x, int64_t n, const float* s_dev, float s, void* stream);
 /* out[0] = numerator / x[0]  (data parallel: 1 / all-reduced token count, consumed by icap_adam_step as gscale_dev). */
 int icap_reciprocal(const float* x, float* out, float numerator, void* stream);

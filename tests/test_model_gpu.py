@@ -322,6 +322,30 @@ def test_full_size_train_step_properties_bf16():
     assert gs.launches_per_step > 100
 
 
+def test_adam_sliced_into_backward_equals_adam_after_backward():
+    """bf16 fused step: Adam applied in slices on the side stream while the backward is still running must give the
+    same parameters as one Adam launch after the backward (split-K reduction order is the only nondeterminism)."""
+    kw = model_a_cfg(encode_num_blocks=2, decode_num_blocks=2)
+    f, p, c = O.synthetic_batch(64, 36, 2048, 84, 22, 10000, seed=3)
+    f, p, c = f.to(DEV), p.to(DEV), c.to(DEV)
+    flats, losses = [], []
+    for sliced in (True, False):
+        torch.manual_seed(0)
+        m = pkg.Transformer(device=DEV, **kw).to(DEV).train()
+        eng = m._engine()
+        eng.adam_in_backward = sliced
+        eng.ADAM_SLICE_ELEMS = 1 << 20          # several slices even for this 4-block model
+        ls = [float(eng.train_step(f, p, c, lr=5e-4, train_mode=False)[0]) for _ in range(3)]
+        torch.cuda.synchronize()
+        flats.append(eng.p32.clone())
+        losses.append(ls)
+        assert int(eng.step_dev) == 3
+    np.testing.assert_allclose(losses[0], losses[1], rtol=2e-3)
+    diff = (flats[0] - flats[1]).abs()
+    assert float((diff > 2e-4).float().mean()) < 0.01, float((diff > 2e-4).float().mean())
+    assert float(diff.max()) <= 3.1e-3          # at most a couple of lr-sized steps apart (sign flips of ~0 gradients)
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     N = pkg._native
     monkeypatch.setattr(N, "_lib", None)
