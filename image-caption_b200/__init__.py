@@ -6,7 +6,7 @@ The directory name contains a hyphen, so import it through `icap_loader.load()` 
 drop-in tree `core.TRANSFORMER.model` / `core.models` exactly like the reference's.
 """
 from .engine import ModelConfig, CaptionEngine, param_layout, flat_offsets   # noqa: F401
-from .transformer import Transformer, GraphedTrainStep, GraphedDecode, DataParallel, GradBuckets                       # noqa: F401
+from .transformer import Transformer, PolicyNetwork, GraphedTrainStep, GraphedDecode, DataParallel, GradBuckets                       # noqa: F401
 from . import _native                                                        # noqa: F401
 
-__all__ = ["Transformer", "GraphedTrainStep", "GraphedDecode", "DataParallel", "GradBuckets", "ModelConfig", "CaptionEngine", "param_layout", "flat_offsets"]
+__all__ = ["Transformer", "PolicyNetwork", "GraphedTrainStep", "GraphedDecode", "DataParallel", "GradBuckets", "ModelConfig", "CaptionEngine", "param_layout", "flat_offsets"]

@@ -736,15 +736,31 @@ class CaptionEngine:
         call("icap_xent_finalize", M, row_loss.data_ptr(), inv_count.data_ptr(), int(cfg.focal), out2.data_ptr(),
              self._s())
         if record:
-            def bwd():
-                self.wgrad(logits, dec, self.g("classifer.weight"), V, d, M, ld_dy=ldl)
-                self.side_call("icap_colsum", self.act, M, V, logits.data_ptr(), ldl, self.g("classifer.bias"))
-                dx = self.new(M, d)
-                self.gemm(logits, True, self.w("classifer.weight"), d, False, M, d, V, dx, lda=ldl)
-                self.add_grad(dec, dx)
-            bwd.lo = self.offsets["classifer.weight"]
-            self.tape.append(bwd)
+            self._append_classifier_bwd(logits, dec)
         return out2
+
+    def _append_classifier_bwd(self, logits: torch.Tensor, dec: torch.Tensor) -> None:
+        """Backward of `classifer` (model.py:68,93): by the time it runs, `logits` holds d loss / d logits."""
+        cfg = self.cfg
+        M, ldl = logits.shape
+        V, d = cfg.num_vocab, cfg.decode_input_size
+
+        def bwd():
+            self.wgrad(logits, dec, self.g("classifer.weight"), V, d, M, ld_dy=ldl)
+            self.side_call("icap_colsum", self.act, M, V, logits.data_ptr(), ldl, self.g("classifer.bias"))
+            dx = self.new(M, d)
+            self.gemm(logits, True, self.w("classifer.weight"), d, False, M, d, V, dx, lda=ldl)
+            self.add_grad(dec, dx)
+        bwd.lo = self.offsets["classifer.weight"]
+        self.tape.append(bwd)
+
+    def set_dlogits(self, logits: torch.Tensor, grad: torch.Tensor) -> None:
+        """Overwrite the recorded logits buffer [M, ldl] with an externally computed d loss / d logits [M, V] (fp32):
+        the PolicyNetwork path, where the loss lives in user code (model_RL.py:75-90, loss.py:31-219)."""
+        M, ldl = logits.shape
+        V = self.cfg.num_vocab
+        grad = grad.reshape(M, V).to(torch.float32).contiguous()
+        call("icap_copy2d", grad.data_ptr(), F32, V, logits.data_ptr(), self.act, ldl, M, V, 0, self._s())
 
     def backward(self, zero_grads: bool = True) -> None:
         """Run the tape in reverse: fills g32 with d(mean CE)/d(param); focal scaling is applied by

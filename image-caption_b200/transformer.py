@@ -80,6 +80,40 @@ class _LossFn(torch.autograd.Function):
         return (None,) * (5 + len(params))
 
 
+class _LogitsFn(torch.autograd.Function):
+    """Differentiable teacher-forced logits (PolicyNetwork.forward, model_RL.py:75-90): the loss is computed by the
+    caller in PyTorch, its gradient w.r.t. the logits re-enters the engine's explicit backward here."""
+
+    @staticmethod
+    def forward(ctx, model, record, feats, pos, captions, *params):
+        eng = model._engine()
+        eng.training = model.training
+        eng.shadow_fresh = False
+        f, p, c = eng.prepare_inputs(feats, pos, captions)
+        logits, tgt, count2, dec = eng.forward_logits(f, p, c, record=record)
+        if record:
+            eng._append_classifier_bwd(logits, dec)
+        ctx.model, ctx.logits, ctx.recorded = model, logits, record
+        B, T = c.shape[0], c.shape[1] - 1
+        ctx.shape = (B, T, model.num_vocab)
+        # a copy: the engine overwrites its logits buffer with d loss / d logits in the backward
+        return logits[:, :model.num_vocab].to(torch.float32, copy=True).reshape(B, T, model.num_vocab)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        model, eng = ctx.model, ctx.model._engine()
+        if not ctx.recorded:
+            raise IcapError("backward() called on a forward that did not record (no_grad / frozen parameters)")
+        params = [q for _, q in model.named_parameters()]
+        fresh = all(q.grad is None for q in params)
+        eng.set_dlogits(ctx.logits, grad_out)
+        eng.backward(zero_grads=fresh)
+        for name, q in model.named_parameters():
+            off = eng.offsets[name]
+            q.grad = eng.g32[off:off + q.numel()].view_as(q)
+        return (None,) * (5 + len(params))
+
+
 class Transformer(nn.Module):
     """Reference signature: model.py:10-36."""
 
@@ -286,6 +320,42 @@ class Transformer(nn.Module):
         f, p, c = eng.prepare_inputs(object_features, position_features, target_caption)
         out2 = eng.train_step(f, p, c, lr=lr, train_mode=self.training if train_mode is None else train_mode)
         return out2[0]
+
+
+class PolicyNetwork(Transformer):
+    """Drop-in for core/TRANSFORMER/model_RL.py::PolicyNetwork (the repo's shipped default CAPTION_MODEL,
+    core/config.py:14): same Encoder / Decoder / classifer parameters, but `forward` returns the teacher-forced
+    LOGITS [B, T, V] (differentiable: any PyTorch loss on top back-propagates through the CUDA path), `sample`
+    is the argmax "sampler" of model_RL.py:93-97 and beam search scores with LogSoftmax (model_RL.py:72,157,182).
+    The reward computation of SelfCriticNetwork (CIDEr / BLEU on CPU strings) stays in user code."""
+
+    def __init__(self, num_vocab, max_length, encode_dim_positions, encode_dim_features, device, pad_idx=0, dropout=0.2,
+                 encode_mask=False, encode_input_size=512, encode_q_k_dim=512, encode_v_dim=512, encode_hidden_size=2048,
+                 encode_num_blocks=6, encode_num_heads=8, dim_word_embedding=512, decode_input_size=512,
+                 decode_q_k_dim=512, decode_v_dim=512, decode_hidden_size=2048, decode_num_blocks=6, decode_num_heads=8,
+                 move_first_image_feature=False, split_position=False, split_image_objects=False):
+        super().__init__(num_vocab, max_length, encode_dim_positions, encode_dim_features, device, "RL_Transformer",
+                         encode_mask=encode_mask, pad_idx=pad_idx, dropout=dropout, encode_input_size=encode_input_size,
+                         encode_q_k_dim=encode_q_k_dim, encode_v_dim=encode_v_dim, encode_hidden_size=encode_hidden_size,
+                         encode_num_blocks=encode_num_blocks, encode_num_heads=encode_num_heads,
+                         dim_word_embedding=dim_word_embedding, decode_input_size=decode_input_size,
+                         decode_q_k_dim=decode_q_k_dim, decode_v_dim=decode_v_dim, decode_hidden_size=decode_hidden_size,
+                         decode_num_blocks=decode_num_blocks, decode_num_heads=decode_num_heads,
+                         move_first_image_feature=move_first_image_feature, split_position=split_position,
+                         split_image_objects=split_image_objects)
+        self.log_domain_beam = True
+
+    def forward(self, object_features, position_features, target_caption):
+        """model_RL.py:75-90 -> logits [B, T, V] (fp32)."""
+        params = [q for _, q in self.named_parameters()]
+        record = torch.is_grad_enabled() and any(q.requires_grad for q in params)
+        return _LogitsFn.apply(self, record, object_features, position_features, target_caption, *params)
+
+    @staticmethod
+    def sample(output):
+        """model_RL.py:93-97."""
+        log_probs = torch.nn.functional.log_softmax(output, dim=2)
+        return torch.argmax(log_probs, dim=2), log_probs
 
 
 class GradBuckets:

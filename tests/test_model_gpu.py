@@ -322,6 +322,37 @@ def test_full_size_train_step_properties_bf16():
     assert gs.launches_per_step > 100
 
 
+def test_policy_network_logits_and_external_loss_gradients():
+    """PolicyNetwork.forward returns differentiable logits (model_RL.py:75-90).  A PyTorch
+    cross-entropy on top of them must reproduce the oracle's loss and every parameter gradient (fp32 mode), and the
+    log-domain beam search must match the oracle's PolicyNetwork beam."""
+    kw = model_a_cfg(encode_num_blocks=2, decode_num_blocks=2, max_length=12, num_vocab=1000)
+    cfg = O.OracleConfig(**kw)
+    sd = O.init_state_dict(cfg, seed=4)
+    f, p, c = O.synthetic_batch(5, 36, 2048, 84, 12, 1000, seed=8)
+    pk = {k: v for k, v in kw.items() if k != "output_name"}
+    m = pkg.PolicyNetwork(device=DEV, **pk)
+    m.load_state_dict(sd)
+    m = m.to(DEV).eval()
+    m.set_precision("fp32")
+    logits = m(f, p, c)
+    assert logits.shape == (5, 11, 1000) and logits.requires_grad
+    assert rel(logits.detach(), O.logits_forward(sd, cfg, f, p, c)) < 1e-4
+    tgt = c[:, 1:].long().to(DEV)
+    loss = torch.nn.functional.cross_entropy(logits.reshape(-1, 1000), tgt.reshape(-1), ignore_index=0)
+    ref_loss, ref_grads = O.loss_and_grads(sd, cfg, f, p, c)
+    assert abs(float(loss) - float(ref_loss)) / float(ref_loss) < 1e-5
+    loss.backward()
+    for name, q in m.named_parameters():
+        r = ref_grads[name]
+        assert float((q.grad.cpu() - r).norm() / (r.norm() + 1e-12)) < 5e-4, name
+    seq, logp = m.sample(logits.detach())
+    assert seq.shape == (5, 11) and logp.shape == (5, 11, 1000)
+    ref = O.beam_search(sd, cfg, f, p, beam_size=3, log_domain=True)
+    out = m.beam_search(f, p, beam_size=3)
+    assert not ids_match_except_near_ties(out, ref, m.last_gaps, tol=1e-6)
+
+
 def test_adam_sliced_into_backward_equals_adam_after_backward():
     """bf16 fused step: Adam applied in slices on the side stream while the backward is still running must give the
     same parameters as one Adam launch after the backward (split-K reduction order is the only nondeterminism)."""
