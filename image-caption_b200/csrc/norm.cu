@@ -249,9 +249,8 @@ __device__ __forceinline__ uint32_t dropout_keep8(uint32_t sf, uint64_t e8, uint
          (dropout_keep2(sf, 4 * e8 + 2, thresh) << 4) | (dropout_keep2(sf, 4 * e8 + 3, thresh) << 6);
 }
 
-constexpr int RPW = 2;      // rows per warp
 
-template <int NIT, typename TA, typename TR, typename TY>
+template <int NIT, int RPW, typename TA, typename TR, typename TY>
 __global__ void __launch_bounds__(256)
 add_ln_fwd8_kernel(int M, int d, TA* __restrict__ a, const TR* __restrict__ res, int res_rows,
                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ rowscale,
@@ -340,7 +339,7 @@ add_ln_fwd8_kernel(int M, int d, TA* __restrict__ a, const TR* __restrict__ res,
   }
 }
 
-template <int NIT, typename T>
+template <int NIT, int RPW, typename T>
 __global__ void __launch_bounds__(256)
 add_ln_bwd_rows8_kernel(int M, int d, const T* __restrict__ dy1, const T* __restrict__ dy2, const T* __restrict__ s,
                         const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
@@ -505,11 +504,16 @@ extern "C" int icap_add_ln_fwd(int a_dtype, int act_dtype, int64_t M, int64_t d,
   const uint32_t th = dropout_threshold(p_drop);
   if (d % 8 == 0 && aligned16(a) && aligned16(res) && aligned16(y) && aligned16(gamma) && aligned16(beta) &&
       !getenv("ICAP_LN_NARROW")) {
-    dim3 grid8((unsigned)ceil_div64(M, 8 * RPW));
-#define GO8(NIT, TA, TR, TY)                                                                                      \
-  icap_launch(add_ln_fwd8_kernel<NIT, TA, TR, TY>, grid8, 256, 0, st, (int)M, (int)d, (TA*)a, (const TR*)res,             \
+    static const int rpw = getenv("ICAP_LN_RPW") ? atoi(getenv("ICAP_LN_RPW")) : 1;     // rows per warp (1 or 2)
+    dim3 grid8((unsigned)ceil_div64(M, 8 * (rpw == 1 ? 1 : 2)));
+#define GO8R(NIT, R, TA, TR, TY)                                                                                  \
+  icap_launch(add_ln_fwd8_kernel<NIT, R, TA, TR, TY>, grid8, 256, 0, st, (int)M, (int)d, (TA*)a, (const TR*)res, \
                                                              (int)res_rows, gamma, beta, rowscale, (TY*)y,       \
                                                              mean_out, rstd_out, write_sum, p_drop, th, seed, seed_dev, eps)
+#define GO8(NIT, TA, TR, TY)                                                                                      \
+  do {                                                                                                            \
+    if (rpw == 1) GO8R(NIT, 1, TA, TR, TY); else GO8R(NIT, 2, TA, TR, TY);                                        \
+  } while (0)
 #define GOT8(TA, TR, TY)                                                                                          \
   do {                                                                                                            \
     if (d <= 256) GO8(1, TA, TR, TY);                                                                             \
@@ -520,6 +524,7 @@ extern "C" int icap_add_ln_fwd(int a_dtype, int act_dtype, int64_t M, int64_t d,
     else if (a_dtype == ICAP_BF16 && act_dtype == ICAP_BF16) GOT8(bf16, bf16, bf16);
     else if (a_dtype == ICAP_F32 && act_dtype == ICAP_BF16) GOT8(float, bf16, bf16);
     else ICAP_ARG(false, "icap_add_ln_fwd: unsupported dtype combination a=%d act=%d", a_dtype, act_dtype);
+#undef GO8R
 #undef GOT8
 #undef GO8
     ICAP_LAUNCH_CHECK("icap_add_ln_fwd");
@@ -566,16 +571,20 @@ static int add_ln_bwd_impl(int which, int act_dtype, int64_t M, int64_t d, const
   ICAP_ARG(dbias2 == nullptr || dab != nullptr, "icap_add_ln_bwd: dbias2 needs ds or da");
   if (d % 8 == 0 && aligned16(dy1) && aligned16(dy2) && aligned16(s) && aligned16(ds) && aligned16(da) &&
       aligned16(gamma) && !getenv("ICAP_LN_NARROW")) {
-    const unsigned row_blocks8 = (unsigned)ceil_div64(M, 8 * RPW);
+    static const int rpw = getenv("ICAP_LN_RPW") ? atoi(getenv("ICAP_LN_RPW")) : 1;     // rows per warp (1 or 2)
+    const unsigned row_blocks8 = (unsigned)ceil_div64(M, 8 * (rpw == 1 ? 1 : 2));
     const int64_t col_blocks8 = ceil_div64(d, 256);
     int64_t splits8 = ceil_div64(148 * 3, col_blocks8);
     if (splits8 > ceil_div64(M, 16)) splits8 = ceil_div64(M, 16);
     const int rpb8 = (int)ceil_div64(M, splits8);
     dim3 cgrid8((unsigned)col_blocks8, (unsigned)ceil_div64(M, rpb8));
+#define GOB8R(NIT, R, T)                                                                                          \
+  icap_launch(add_ln_bwd_rows8_kernel<NIT, R, T>, row_blocks8, 256, 0, st, (int)M, (int)d, (const T*)dy1,         \
+              (const T*)dy2, (const T*)s, mean, rstd, gamma, rowscale, (T*)ds, (T*)da, p_drop, th, seed, seed_dev)
 #define GOB8(NIT, T)                                                                                              \
-  icap_launch(add_ln_bwd_rows8_kernel<NIT, T>, row_blocks8, 256, 0, st, (int)M, (int)d, (const T*)dy1, (const T*)dy2,      \
-                                                               (const T*)s, mean, rstd, gamma, rowscale, (T*)ds, \
-                                                               (T*)da, p_drop, th, seed, seed_dev)
+  do {                                                                                                            \
+    if (rpw == 1) GOB8R(NIT, 1, T); else GOB8R(NIT, 2, T);                                                        \
+  } while (0)
 #define GOBT8(T)                                                                                                  \
   do {                                                                                                            \
     if ((ds || da) && (which & 1)) {                                                                              \
@@ -592,6 +601,7 @@ static int add_ln_bwd_impl(int which, int act_dtype, int64_t M, int64_t d, const
     else GOBT8(bf16);
 #undef GOBT8
 #undef GOB8
+#undef GOB8R
     ICAP_LAUNCH_CHECK("icap_add_ln_bwd");
     return 0;
   }

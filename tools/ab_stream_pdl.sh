@@ -1,10 +1,10 @@
-for fa in 0 1; do
-echo "== ICAP_DECODE_FUSED_APPEND=$fa"
-ICAP_DECODE_STREAMS=1 ICAP_DECODE_FUSED_APPEND=$fa timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>&1 | python -c "
+for r in 1 2; do
+echo "== ICAP_LN_RPW=$r"
+ICAP_LN_RPW=$r timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-decode 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
     if l.startswith('{'):
-        d=json.loads(l); print({k:round(v,1) for k,v in d['extra'].items() if 'ms_per' in k})
+        d=json.loads(l); print('ms_per_step', d['ms_per_step'], 'value', d['value'])
     else: print(l.rstrip()[-300:])
 "
 done
