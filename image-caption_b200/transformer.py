@@ -394,7 +394,7 @@ class DataParallel:
     embeddings) as the backward proceeds, so the buffer is reduced in `bucket_mb` slices, each launched on a
     communication stream as soon as its slice is complete (engine.bucket_hook) while the backward continues."""
 
-    def __init__(self, model: "Transformer", dist, bucket_mb: float = 48.0, overlap: bool = True):
+    def __init__(self, model: "Transformer", dist, bucket_mb: Optional[float] = None, overlap: bool = True):
         self.dist = dist
         self.world = dist.get_world_size()
         eng = model._engine()
@@ -403,6 +403,8 @@ class DataParallel:
         eng.shadow_fresh = False
         self.eng = eng
         self.inv = torch.zeros(1, dtype=torch.float32, device=eng.dev)
+        if bucket_mb is None:
+            bucket_mb = float(os.environ.get("ICAP_DP_BUCKET_MB", "48"))
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
         self.overlap = overlap and os.environ.get("ICAP_DP_OVERLAP", "1") != "0"
         self.comm: Optional[torch.cuda.Stream] = None
