@@ -575,6 +575,169 @@ mha_decode64_kernel(int groups, int H, int Lk, const T* __restrict__ q, int64_t 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Self-attention decode step, "row per warp" mapping (head dim 64, width H*64 = WPR * 32 * EPL, at most 32 cached
+// positions).  The warp-per-(row, head) kernel above spends ~700 instructions of fixed overhead per 64-wide head for
+// <= 21 keys and was issue bound (ncu r1: 39 us per launch).  Here one warp owns EPL contiguous elements per lane of
+// a row's K / V line (all or half of the heads at once): one fully coalesced 16/32-byte load per lane fetches a
+// cached position for every head, the per-head dot product is reduced over the 64/EPL lanes of a head with xor
+// shuffles, the softmax is online (running max / sum per head, kept redundantly in the head's lanes), and the new
+// K / V of position pos_new are appended to the row's own cache line from registers.
+template <typename T, int EPL> struct RawVec;                       // EPL elements as 16-byte words
+template <int EPL> struct RawVec<bf16, EPL> { uint4 w[EPL / 8]; };
+template <int EPL> struct RawVec<float, EPL> { uint4 w[EPL / 4]; };
+template <typename T, int EPL>
+__device__ __forceinline__ void raw_load(RawVec<T, EPL>& r, const T* p) {
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(r.w) / 16); ++i) r.w[i] = __ldg(reinterpret_cast<const uint4*>(p) + i);
+}
+template <typename T, int EPL>
+__device__ __forceinline__ void raw_zero(RawVec<T, EPL>& r) {
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(r.w) / 16); ++i) r.w[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+template <int EPL>
+__device__ __forceinline__ void raw_unpack(const RawVec<bf16, EPL>& r, float (&v)[EPL]) {
+#pragma unroll
+  for (int i = 0; i < EPL / 8; ++i) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r.w[i]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { v[i * 8 + 2 * e] = __low2float(h[e]); v[i * 8 + 2 * e + 1] = __high2float(h[e]); }
+  }
+}
+template <int EPL>
+__device__ __forceinline__ void raw_unpack(const RawVec<float, EPL>& r, float (&v)[EPL]) {
+#pragma unroll
+  for (int i = 0; i < EPL / 4; ++i) {
+    v[i * 4] = __uint_as_float(r.w[i].x); v[i * 4 + 1] = __uint_as_float(r.w[i].y);
+    v[i * 4 + 2] = __uint_as_float(r.w[i].z); v[i * 4 + 3] = __uint_as_float(r.w[i].w);
+  }
+}
+template <int EPL>
+__device__ __forceinline__ void raw_pack_store(bf16* p, const float (&v)[EPL]) {
+#pragma unroll
+  for (int i = 0; i < EPL / 8; ++i) {
+    uint4 t;
+    __nv_bfloat162 h;
+    h = __floats2bfloat162_rn(v[i * 8 + 0], v[i * 8 + 1]); t.x = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(v[i * 8 + 2], v[i * 8 + 3]); t.y = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(v[i * 8 + 4], v[i * 8 + 5]); t.z = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(v[i * 8 + 6], v[i * 8 + 7]); t.w = *reinterpret_cast<uint32_t*>(&h);
+    reinterpret_cast<uint4*>(p)[i] = t;
+  }
+}
+template <int EPL>
+__device__ __forceinline__ void raw_pack_store(float* p, const float (&v)[EPL]) {
+#pragma unroll
+  for (int i = 0; i < EPL / 4; ++i) reinterpret_cast<float4*>(p)[i] = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+}
+
+
+template <typename T, int EPL, int ROW_UB>      // ROW_UB: cached positions fetched per batch (loads in flight per lane)
+__global__ void __launch_bounds__(256)
+mha_decode_row_kernel(int rows, int wpr, int Lk, const T* __restrict__ q, int64_t ldq, T* __restrict__ kc, int64_t ldk,
+                      T* __restrict__ vc, int64_t ldv, int kv_rows_per_seq, T* __restrict__ o, int64_t ldo,
+                      const int* __restrict__ slot, int64_t slot_ld, const int* __restrict__ tokens, int64_t tok_ld,
+                      int pad_idx, const T* __restrict__ knew, const T* __restrict__ vnew, int64_t ldn, int pos_new) {
+  pdl_prologue();
+  constexpr int LPH = 64 / EPL;                       // lanes per head
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int row = gw / wpr, part = gw % wpr;          // part: which 32*EPL-wide slice of the row this warp owns
+  if (row >= rows) return;
+  const int col = (part * 32 + lane) * EPL;           // first element of this lane within a K / V / q / o row
+  float qv[EPL];
+  {
+    RawVec<T, EPL> r;
+    raw_load<T, EPL>(r, q + (int64_t)row * ldq + col);
+    raw_unpack(r, qv);
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) qv[e] *= 0.125f;    // 1 / sqrt(64) on q, as modules.py:18
+  }
+  RawVec<T, EPL> knew_r, vnew_r;
+  raw_load<T, EPL>(knew_r, knew + (int64_t)row * ldn + col);
+  raw_load<T, EPL>(vnew_r, vnew + (int64_t)row * ldn + col);
+  {
+    const int64_t crow = (int64_t)row * kv_rows_per_seq + pos_new;
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(knew_r.w) / 16); ++i) {
+      reinterpret_cast<uint4*>(kc + crow * ldk + col)[i] = knew_r.w[i];
+      reinterpret_cast<uint4*>(vc + crow * ldv + col)[i] = vnew_r.w[i];
+    }
+  }
+  // lane l: physical cache row of position l, or -1 (position masked / beyond Lk)
+  int myrow = -1;
+  if (lane < Lk && tokens[(int64_t)row * tok_ld + lane] != pad_idx)
+    myrow = (slot ? slot[(int64_t)row * slot_ld + lane] : row) * kv_rows_per_seq + lane;
+  // ---- one pass over the cached positions, ROW_UB at a time: K and V of a batch are fetched together (2 * ROW_UB
+  // independent loads in flight per lane), scores go through an online softmax (running max m / sum l, rescaled
+  // accumulator), so there is a single memory round trip per batch instead of one for Q.K^T and one for P.V
+  float acc[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;
+#pragma unroll
+  for (int jb = 0; jb < 32; jb += ROW_UB) {
+    if (jb < Lk) {                                    // warp-uniform
+      RawVec<T, EPL> kraw[ROW_UB], vraw[ROW_UB];
+      int rr[ROW_UB];
+#pragma unroll
+      for (int u = 0; u < ROW_UB; ++u) {
+        rr[u] = __shfl_sync(0xffffffffu, myrow, jb + u);
+        raw_zero<T, EPL>(kraw[u]);
+        raw_zero<T, EPL>(vraw[u]);
+        if (rr[u] >= 0 && jb + u != pos_new) {
+          raw_load<T, EPL>(kraw[u], kc + (int64_t)rr[u] * ldk + col);
+          raw_load<T, EPL>(vraw[u], vc + (int64_t)rr[u] * ldv + col);
+        }
+      }
+      float sb[ROW_UB];
+      float bmax = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < ROW_UB; ++u) {
+        sb[u] = -INFINITY;
+        if (jb + u < Lk) {                            // warp-uniform
+          float kv[EPL];
+          if (jb + u == pos_new) raw_unpack(knew_r, kv); else raw_unpack(kraw[u], kv);
+          float part_s = 0.f;
+#pragma unroll
+          for (int e = 0; e < EPL; ++e) part_s = fmaf(qv[e], kv[e], part_s);
+#pragma unroll
+          for (int off = 1; off < LPH; off <<= 1) part_s += __shfl_xor_sync(0xffffffffu, part_s, off);
+          if (rr[u] >= 0) sb[u] = part_s;
+          bmax = fmaxf(bmax, sb[u]);
+        }
+      }
+      const float m_new = fmaxf(m_run, bmax);
+      if (m_new != -INFINITY) {                       // identical in the lanes of a head; other heads may differ
+        const float rescale = (m_run == -INFINITY) ? 0.f : __expf(m_run - m_new);
+        l_run *= rescale;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) acc[e] *= rescale;
+#pragma unroll
+        for (int u = 0; u < ROW_UB; ++u) {
+          if (jb + u < Lk) {
+            const float pj = (sb[u] == -INFINITY) ? 0.f : __expf(sb[u] - m_new);
+            l_run += pj;
+            float vv[EPL];
+            if (jb + u == pos_new) raw_unpack(vnew_r, vv); else raw_unpack(vraw[u], vv);
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) acc[e] = fmaf(pj, vv[e], acc[e]);
+          }
+        }
+        m_run = m_new;
+      }
+    }
+  }
+  {
+    const float inv = 1.f / l_run;                    // all keys masked -> inf/NaN exactly like the reference's softmax
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) acc[e] *= inv;
+  }
+  raw_pack_store<EPL>(o + (int64_t)row * ldo + col, acc);
+}
+
 template <typename T, int G>
 int launch_decode64(int64_t groups, int64_t H, int64_t Lk, const void* q, int64_t ldq, const void* kc, int64_t ldk,
                     const void* vc, int64_t ldv, int64_t kv_rows_per_seq, void* o, int64_t ldo, const int* slot,
@@ -745,6 +908,24 @@ extern "C" int icap_mha_decode_self(int dtype, int64_t rows, int64_t H, int64_t 
                   ((uintptr_t)o % 16 == 0) && ((uintptr_t)k_new % 16 == 0) && ((uintptr_t)v_new % 16 == 0) &&
                   (ldq * esz) % 16 == 0 && (ldk * esz) % 16 == 0 && (ldv * esz) % 16 == 0 && (ldo * esz) % 16 == 0 &&
                   (ld_new * esz) % 16 == 0;
+  if (dk == 64 && dv == 64 && al && pos + 1 <= 32 && (H * 64) % 256 == 0 && !getenv("ICAP_DECODE_SLOW") &&
+      !getenv("ICAP_DECODE_NO_ROW")) {
+    // row-per-warp kernel: EPL elements per lane, wpr warps per row
+    static const int ub_env = getenv("ICAP_DECODE_UB") ? atoi(getenv("ICAP_DECODE_UB")) : 4;
+    const int width = (int)(H * 64);
+    constexpr int epl = 8;
+    const int wpr = width / (32 * epl);
+    const unsigned grid = (unsigned)ceil_div64(rows * wpr, 8);
+#define ROWK(T, U)                                                                                                   \
+  icap_launch(mha_decode_row_kernel<T, 8, U>, grid, 256, 0, st, (int)rows, wpr, (int)(pos + 1), (const T*)q, ldq,    \
+              (T*)kc, ldk, (T*)vc, ldv, (int)kv_rows_per_seq, (T*)o, ldo, slot, slot_ld, tokens, tok_ld, pad_idx,    \
+              (const T*)k_new, (const T*)v_new, ld_new, (int)pos)
+    if (dtype == ICAP_F32) { if (ub_env == 8) ROWK(float, 8); else ROWK(float, 4); }
+    else { if (ub_env == 8) ROWK(bf16, 8); else ROWK(bf16, 4); }
+#undef ROWK
+    ICAP_LAUNCH_CHECK("icap_mha_decode_self(row)");
+    return 0;
+  }
   if (dk == 64 && dv == 64 && al && !getenv("ICAP_DECODE_SLOW")) {
     if (dtype == ICAP_F32)
       return launch_decode64<float, 1>(rows, H, pos + 1, q, ldq, kc, ldk, vc, ldv, kv_rows_per_seq, o, ldo, slot, slot_ld,

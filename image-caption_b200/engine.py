@@ -934,18 +934,19 @@ class CaptionEngine:
                 cache = caches[i]
                 att = self.new(rows, dv_tot)
                 # K/V of position t are appended to the cache inside the attention kernel
+                # (ICAP_DECODE_FUSED_APPEND=0: separate strided copy + plain decode attention, for A/B timing)
+                sl = slot[cur].data_ptr() if slot is not None else None
                 if os.environ.get("ICAP_DECODE_FUSED_APPEND", "1") == "0":
                     call("icap_copy2d", qkv.data_ptr() + dk_tot * esz, self.act, nqkv, cache.data_ptr() + t * nkv * esz,
                          self.act, T * nkv, rows, nkv, 0, s())
                     call("icap_mha_decode", self.act, rows, H, t + 1, dk, dv, qkv.data_ptr(), nqkv, cache.data_ptr(), nkv,
-                         cache.data_ptr() + dk_tot * esz, nkv, T, att.data_ptr(), dv_tot,
-                         slot[cur].data_ptr() if slot is not None else None, Tmax, tk.data_ptr(), Tmax, cfg.pad_idx,
-                         None, 1, None, s())
+                         cache.data_ptr() + dk_tot * esz, nkv, T, att.data_ptr(), dv_tot, sl, Tmax, tk.data_ptr(), Tmax,
+                         cfg.pad_idx, None, 1, None, s())
                 else:
-                  call("icap_mha_decode_self", self.act, rows, H, t, dk, dv, qkv.data_ptr(), nqkv,
-                       qkv.data_ptr() + dk_tot * esz, qkv.data_ptr() + 2 * dk_tot * esz, nqkv, cache.data_ptr(), nkv,
-                       cache.data_ptr() + dk_tot * esz, nkv, T, att.data_ptr(), dv_tot,
-                       slot[cur].data_ptr() if slot is not None else None, Tmax, tk.data_ptr(), Tmax, cfg.pad_idx, s())
+                    call("icap_mha_decode_self", self.act, rows, H, t, dk, dv, qkv.data_ptr(), nqkv,
+                         qkv.data_ptr() + dk_tot * esz, qkv.data_ptr() + 2 * dk_tot * esz, nqkv, cache.data_ptr(), nkv,
+                         cache.data_ptr() + dk_tot * esz, nkv, T, att.data_ptr(), dv_tot, sl, Tmax, tk.data_ptr(), Tmax,
+                         cfg.pad_idx, s())
                 o = self.new(rows, d)
                 self.gemm(att, True, self.w(pre + ".self_attention.joint_linear.weight"), dv_tot, True, rows, d, dv_tot, o)
                 x1, *_ = self.add_ln(o, x, rows, pre + ".self_attention.layer_norm", None, 0.0)
