@@ -30,6 +30,8 @@ MODEL_KW = dict(num_vocab=10000, max_length=22, encode_dim_positions=84, encode_
                 output_name="bench", dropout=0.2)
 BATCH, REGIONS, CAP_LEN = 256, 36, 22
 DECODE_BATCH = 512
+WORKLOAD = ("configs[1]: teacher-forced train step fwd+bwd+Adam, model A (d512/8h/ffn2048/6+6), batch 256 per GPU, "
+            "R=36x2048, T=21, V=10k")
 
 
 def peaks():
@@ -115,8 +117,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "train_samples_per_sec", "value": v, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1] teacher-forced train step (model A d512/8h/6+6, R=36, T=21, V=10k)",
-                       "sample": f"batch {bs} per step (bounded sample of the batch-256 workload)"},
+            "config": {"workload": WORKLOAD,
+                       "sample": f"each step = one train step on batch {bs} (bounded sample of the batch-256 workload), "
+                                 "torch CPU fp32, dropout off (eval-mode arithmetic)"},
             "cpu_baseline": {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
                              "sample": f"{args.steps} train steps (fwd+bwd+Adam, eval-mode arithmetic) at batch {bs}"},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -344,8 +347,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: teacher-forced train step fwd+bwd+Adam, dropout 0.2/0.1 on, model A "
-                                   "(d512/8h/ffn2048/6+6), batch 256 per GPU, R=36x2048, T=21, V=10k",
+            "config": {"workload": WORKLOAD, "dropout": "on (0.2 / attention 0.1)",
                        "global_batch": world * BATCH, "parallelism": f"dp{world}",
                        "l2": "4 rotating input batches (314 MB) + 1.3 GB of parameter/optimizer state per step >> 126 MB L2",
                        "cuda_graph": True},
