@@ -40,6 +40,13 @@ __global__ void copy2d_kernel(const TS* __restrict__ src, int64_t src_ld, TD* __
       const int64_t r = u / c4, c = (u % c4) * 4;
       float v[4];
       load4(src + r * src_ld + c, v);
+      if (accumulate == 2) {            // atomic: several streams may accumulate into dst concurrently (fp32 dst only)
+        if constexpr (sizeof(TD) == 4) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) atomicAdd(reinterpret_cast<float*>(dst + r * dst_ld + c) + j, v[j]);
+        }
+        continue;
+      }
       if (accumulate) {
         float o[4];
         load4(dst + r * dst_ld + c, o);
@@ -52,6 +59,10 @@ __global__ void copy2d_kernel(const TS* __restrict__ src, int64_t src_ld, TD* __
     for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < rows * cols; u += (int64_t)gridDim.x * blockDim.x) {
       const int64_t r = u / cols, c = u % cols;
       float v = to_f32(src[r * src_ld + c]);
+      if (accumulate == 2) {
+        if constexpr (sizeof(TD) == 4) atomicAdd(reinterpret_cast<float*>(dst + r * dst_ld + c), v);
+        continue;
+      }
       if (accumulate) v += to_f32(dst[r * dst_ld + c]);
       dst[r * dst_ld + c] = from_f32<TD>(v);
     }
@@ -284,6 +295,8 @@ inline unsigned grid_for(int64_t work, int threads) {
 extern "C" int icap_copy2d(const void* src, int src_dtype, int64_t src_ld, void* dst, int dst_dtype, int64_t dst_ld,
                            int64_t rows, int64_t cols, int accumulate, void* stream) {
   ICAP_ARG(src && dst && rows > 0 && cols > 0, "icap_copy2d: null/empty argument");
+  ICAP_ARG(accumulate >= 0 && accumulate <= 2 && (accumulate != 2 || dst_dtype == ICAP_F32),
+           "icap_copy2d: accumulate must be 0, 1 or 2 (atomic, fp32 destination only)");
   const int ss = src_dtype == ICAP_F32 ? 4 : 2, ds = dst_dtype == ICAP_F32 ? 4 : 2;
   const int vec = (cols % 4 == 0) && ((uintptr_t)src % (4 * ss) == 0) && ((uintptr_t)dst % (4 * ds) == 0) &&
                   (src_ld % 4 == 0) && (dst_ld % 4 == 0);

@@ -174,6 +174,12 @@ class CaptionEngine:
         # traffic slows the L2-bound GEMMs it overlaps more than it saves -- so it is off by default.
         self.adam_in_backward = os.environ.get("ICAP_ADAM_IN_BWD", "0") == "1"
         self._adam_plan = None           # (lr, b1, b2, eps, gscale_dev, gscale, prev_lo) while such a backward runs
+        # micro-batching (train_step_mb): the batch is cut into slices whose forward + backward run on separate
+        # streams and accumulate into the shared gradient buffer
+        self._mb_active = False
+        self._mb_streams: List[torch.cuda.Stream] = []
+        self._mb_sides: List[torch.cuda.Stream] = []
+        self._mb_inv = None
         self.p16 = torch.empty(self.n_flat, dtype=torch.bfloat16, device=self.dev) if precision == "bf16" else None
         self.shadow_fresh = False
         self.adam_m: Optional[torch.Tensor] = None
@@ -514,16 +520,17 @@ class CaptionEngine:
     def _unpack_embed_grads(self, dwcat: torch.Tensor) -> None:
         cfg = self.cfg
         d, Df, Dp, Kc = cfg.encode_input_size, cfg.encode_dim_features, cfg.encode_dim_positions, self._cat_width()
-        call("icap_copy2d", dwcat.data_ptr(), F32, Kc, self.g("encoder.feature_embedding.weight"), F32, Df, d, Df, 1,
+        acc = 2 if self._mb_active else 1           # micro-batches on several streams share g32: atomic accumulate
+        call("icap_copy2d", dwcat.data_ptr(), F32, Kc, self.g("encoder.feature_embedding.weight"), F32, Df, d, Df, acc,
              self._s())
         if cfg.split_position:
             call("icap_copy2d", dwcat.data_ptr() + Df * 4, F32, Kc, self.g("encoder.position_embedding.weight"), F32, 4,
-                 d, 4, 1, self._s())
+                 d, 4, acc, self._s())
             call("icap_copy2d", dwcat.data_ptr() + (Df + 4) * 4, F32, Kc, self.g("encoder.object_embedding.weight"), F32,
-                 Dp - 4, d, Dp - 4, 1, self._s())
+                 Dp - 4, d, Dp - 4, acc, self._s())
         else:
             call("icap_copy2d", dwcat.data_ptr() + Df * 4, F32, Kc, self.g("encoder.position_embedding.weight"), F32, Dp,
-                 d, Dp, 1, self._s())
+                 d, Dp, acc, self._s())
 
     def encode(self, feats: torch.Tensor, pos: torch.Tensor):
         """Encoder.forward (model.py:257-332).  feats [B,R,Df] fp32, pos [B,R,Dp] fp32 (device)."""
@@ -731,8 +738,8 @@ class CaptionEngine:
         call("icap_xent", self.act, M, V, logits.data_ptr(), ldl, tgt.data_ptr(), cfg.pad_idx, grad_scale.data_ptr(),
              row_loss.data_ptr(), int(record), self._s())
         if self.dp_unnormalized and record:
-            call("icap_copy2d", count2.data_ptr(), F32, 1, self.g32.data_ptr() + 4 * self.n_flat, F32, 1, 1, 1, 1,
-                 self._s())
+            call("icap_copy2d", count2.data_ptr(), F32, 1, self.g32.data_ptr() + 4 * self.n_flat, F32, 1, 1, 1,
+                 2 if self._mb_active else 1, self._s())
         call("icap_xent_finalize", M, row_loss.data_ptr(), inv_count.data_ptr(), int(cfg.focal), out2.data_ptr(),
              self._s())
         if record:
@@ -851,6 +858,57 @@ class CaptionEngine:
         call("icap_step_tick", self.step_dev.data_ptr(), self._s())
         self.shadow_fresh = True
         return out2
+
+    def train_step_mb(self, feats, pos, captions, n_mb: int = 2, lr: float = 5e-4, train_mode: bool = True,
+                      betas=(0.9, 0.999), eps: float = 1e-8) -> torch.Tensor:
+        """Same arithmetic as train_step (one optimizer step on the whole batch, loss = mean over ALL non-pad
+        targets), but the batch is cut into n_mb slices whose forward + backward are enqueued on separate streams:
+        while one slice runs a tensor-core GEMM on part of the SMs, another runs its LayerNorm / attention kernels.
+        Uses the data-parallel normalisation: every slice back-propagates the SUM of its token losses and adds its
+        token count to the tail slot of g32; Adam divides by the total.  Returns [mean loss, 1]."""
+        B = feats.shape[0]
+        assert not self.cfg.focal, "micro-batching does not support FocalLoss (its gradient scale needs the global mean)"
+        assert B % n_mb == 0
+        dev = self.dev
+        main = torch.cuda.current_stream(dev)
+        while len(self._mb_streams) < n_mb:
+            self._mb_streams.append(torch.cuda.Stream(device=dev))
+            self._mb_sides.append(torch.cuda.Stream(device=dev))
+        if self._mb_inv is None:
+            self._mb_inv = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.refresh_shadow()
+        self.g32.zero_()
+        saved = (self.dp_unnormalized, self._side, self.base_seed)
+        self.dp_unnormalized, self._mb_active = True, True
+        self.training = train_mode
+        bs = B // n_mb
+        outs, keep_all = [], []
+        try:
+            for i in range(n_mb):
+                st = self._mb_streams[i]
+                st.wait_stream(main)
+                self._side = self._mb_sides[i]
+                self.base_seed = (saved[2] + 0x51ED27 * (i + 1)) & 0xFFFFFFFF       # different dropout masks per slice
+                with torch.cuda.stream(st):
+                    sl = slice(i * bs, (i + 1) * bs)
+                    logits, tgt, count2, dec = self.forward_logits(feats[sl], pos[sl], captions[sl], record=True)
+                    out2 = self.loss_from_logits(logits, tgt, count2, dec, record=True)
+                    keep_all.append(self.keep)              # backward() drops self.keep: hold the activations
+                    self.backward(zero_grads=False)
+                    outs.append((out2, count2))
+            for i in range(n_mb):
+                main.wait_stream(self._mb_streams[i])
+        finally:
+            self.dp_unnormalized, self._side, self.base_seed = saved
+            self._mb_active = False
+        call("icap_reciprocal", self.g32.data_ptr() + 4 * self.n_flat, self._mb_inv.data_ptr(), 1.0, self._s())
+        self.adam_step(lr, betas=betas, eps=eps, gscale_dev=self._mb_inv)
+        # mean loss over all non-pad targets = sum_i loss_i * n_i / sum_i n_i
+        num = sum(o[0][0] * o[1][0] for o in outs)
+        den = sum(o[1][0] for o in outs)
+        res = torch.stack([num / den, torch.ones((), device=dev)])
+        del keep_all
+        return res
 
     def forward_backward(self, feats, pos, captions, train_mode: bool = True) -> torch.Tensor:
         """zero_grad + forward + backward; gradients land in g32 (data parallel: all-reduce them next)."""

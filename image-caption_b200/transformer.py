@@ -559,6 +559,15 @@ class GraphedTrainStep:
         self.warmup = warmup
         self.launches_per_step = 0
         self.single_graph_dp = False
+        # ICAP_MICRO_BATCHES=n: forward + backward of n batch slices on n streams inside the graph (engine.train_step_mb)
+        self.micro_batches = 1 if (dp is not None or model.cfg.focal) else max(1, int(os.environ.get("ICAP_MICRO_BATCHES", "1")))
+        if batch % self.micro_batches:
+            self.micro_batches = 1
+
+    def _one_step(self) -> torch.Tensor:
+        if self.micro_batches > 1:
+            return self.eng.train_step_mb(self.feats, self.pos, self.cap, n_mb=self.micro_batches, lr=self.lr)
+        return self.eng.train_step(self.feats, self.pos, self.cap, lr=self.lr)
 
     def load(self, feats: torch.Tensor, pos: torch.Tensor, cap: torch.Tensor) -> None:
         self.feats.copy_(feats, non_blocking=True)
@@ -576,7 +585,7 @@ class GraphedTrainStep:
         with torch.cuda.stream(side):
             for _ in range(self.warmup):
                 if self.dp is None:
-                    eng.train_step(self.feats, self.pos, self.cap, lr=self.lr)
+                    self._one_step()
                 else:
                     self.dp.step_eager(eng, self.feats, self.pos, self.cap, self.lr)
         torch.cuda.current_stream(eng.dev).wait_stream(side)
@@ -591,7 +600,7 @@ class GraphedTrainStep:
         n0 = _native.launch_count
         if self.dp is None:
             with torch.cuda.graph(self.graph):
-                self.out2 = eng.train_step(self.feats, self.pos, self.cap, lr=self.lr)
+                self.out2 = self._one_step()
         elif self.dp.overlap:
             # ONE graph: forward, backward with the bucketed NCCL all-reduces on the communication stream, Adam
             try:

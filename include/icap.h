@@ -135,7 +135,8 @@ int icap_mha_decode_self(int dtype, int64_t rows, int64_t H, int64_t pos, int64_
                          int64_t ldv, int64_t kv_rows_per_seq, void* o, int64_t ldo, const int* slot, int64_t slot_ld,
                          const int* tokens, int64_t tok_ld, int pad_idx, void* stream);
 
-/* dst[r][c] (+)= convert(src[r][c]) : operand packing / dtype casts / gradient unpacking. */
+/* dst[r][c] (+)= convert(src[r][c]) : operand packing / dtype casts / gradient unpacking.
+ * accumulate: 0 = store, 1 = dst += src, 2 = atomic dst += src (fp32 dst; concurrent accumulation from several streams). */
 int icap_copy2d(const void* src, int src_dtype, int64_t src_ld, void* dst, int dst_dtype, int64_t dst_ld, int64_t rows,
                 int64_t cols, int accumulate, void* stream);
 /* dst[r,:] = (base ? base[r,:] : 0) + src[(r / div) * mul + off, :]  -- row broadcast: the "whole image" token

@@ -377,6 +377,30 @@ def test_adam_sliced_into_backward_equals_adam_after_backward():
     assert float(diff.max()) <= 3.1e-3          # at most a couple of lr-sized steps apart (sign flips of ~0 gradients)
 
 
+def test_micro_batched_step_equals_whole_batch_step():
+    """train_step_mb (batch slices on separate streams, shared gradient buffer, Adam divides by the total token
+    count) == train_step on the whole batch: same loss, same parameters after the step (dropout off)."""
+    kw = model_a_cfg(encode_num_blocks=2, decode_num_blocks=2)
+    f, p, c = O.synthetic_batch(64, 36, 2048, 84, 22, 10000, seed=5)
+    f, p, c = f.to(DEV), p.to(DEV), c.to(DEV)
+    res = {}
+    for n_mb in (1, 2, 4):
+        torch.manual_seed(0)
+        m = pkg.Transformer(device=DEV, **kw).to(DEV).train()
+        eng = m._engine()
+        if n_mb == 1:
+            losses = [float(eng.train_step(f, p, c, lr=5e-4, train_mode=False)[0]) for _ in range(2)]
+        else:
+            losses = [float(eng.train_step_mb(f, p, c, n_mb=n_mb, lr=5e-4, train_mode=False)[0]) for _ in range(2)]
+        torch.cuda.synchronize()
+        res[n_mb] = (losses, eng.p32.clone())
+    for n_mb in (2, 4):
+        np.testing.assert_allclose(res[n_mb][0], res[1][0], rtol=2e-3)
+        diff = (res[n_mb][1] - res[1][1]).abs()
+        assert float((diff > 2e-4).float().mean()) < 0.01
+        assert float(diff.max()) <= 2.1e-3
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     N = pkg._native
     monkeypatch.setattr(N, "_lib", None)
