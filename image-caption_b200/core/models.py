@@ -48,12 +48,19 @@ class MODEL_init:
         return decode_captions(captions=caption_vector, index_to_word=self.idx_to_word)
 
     def save(self, path):
-        torch.save(self.model.state_dict(), path)
+        torch.save(self.model.state_dict(), path)           # the reference's checkpoint format, unchanged
 
     def load(self, path):
         state_dict = torch.load(path, map_location=DEVICE)
         self.model.load_state_dict(state_dict)
         self.model.eval()
+
+    # resume support (the reference cannot resume: it never saves the optimizer, models.py:62-63)
+    def save_optimizer(self, path):
+        torch.save(self.model.optimizer_state_dict(), path)
+
+    def load_optimizer(self, path):
+        self.model.load_optimizer_state_dict(torch.load(path, map_location="cpu"))
 
     def preprocess(self, image_path, save_img=False, max_obj=False):
         raise NotImplementedError("image feature extraction (YOLOv5 + ResNet-101, core/preprocess.py:91-138) is the "

@@ -311,6 +311,27 @@ class Transformer(nn.Module):
         mask = torch.count_nonzero(k, dim=2).eq(0)
         return mask.unsqueeze(1).expand(k.size(0), q.size(1), k.size(1))
 
+    # ------------------------------------------------------------------ optimizer state (resume; not in the reference)
+    def optimizer_state_dict(self) -> dict:
+        """Adam state of the fused step (exp_avg / exp_avg_sq over the flat buffer + step count).  The reference saves
+        only model.state_dict() and cannot resume (models.py:62-63); `save()` keeps that format and this
+        is stored next to it."""
+        eng = self._engine()
+        if eng.adam_m is None:
+            return {"step": int(eng.step_dev), "exp_avg": None, "exp_avg_sq": None}
+        return {"step": int(eng.step_dev), "exp_avg": eng.adam_m.detach().cpu().clone(),
+                "exp_avg_sq": eng.adam_v.detach().cpu().clone()}
+
+    def load_optimizer_state_dict(self, state: dict) -> None:
+        eng = self._engine()
+        eng.step_dev.fill_(int(state["step"]))
+        if state.get("exp_avg") is None:
+            eng.adam_m = eng.adam_v = None
+            return
+        assert state["exp_avg"].numel() == eng.n_flat, "optimizer state belongs to a different model configuration"
+        eng.adam_m = state["exp_avg"].to(eng.dev, torch.float32).clone()
+        eng.adam_v = state["exp_avg_sq"].to(eng.dev, torch.float32).clone()
+
     # ------------------------------------------------------------------ fused training step
     def train_step_fused(self, object_features, position_features, target_caption, lr: float = 5e-4,
                          train_mode: Optional[bool] = None) -> torch.Tensor:

@@ -401,6 +401,30 @@ def test_micro_batched_step_equals_whole_batch_step():
         assert float(diff.max()) <= 2.1e-3
 
 
+def test_checkpoint_and_optimizer_resume(tmp_path):
+    """state_dict round trip in the reference's format + optimizer-state resume: (2 steps, save, 1 step) ==
+    (load into a fresh model, 1 step)."""
+    kw = model_a_cfg(encode_num_blocks=1, decode_num_blocks=1, num_vocab=500, encode_dim_features=256)
+    f, p, c = O.synthetic_batch(16, 12, 256, 84, 22, 500, seed=6)
+    torch.manual_seed(0)
+    a = pkg.Transformer(device=DEV, **kw).to(DEV).train()
+    a.set_precision("fp32")
+    for _ in range(2):
+        a.train_step_fused(f, p, c, lr=5e-4, train_mode=False)
+    torch.save(a.state_dict(), tmp_path / "model_2.pt")
+    torch.save(a.optimizer_state_dict(), tmp_path / "opt_2.pt")
+    a.train_step_fused(f, p, c, lr=5e-4, train_mode=False)
+    b = pkg.Transformer(device=DEV, **kw).to(DEV).train()
+    b.set_precision("fp32")
+    sd = torch.load(tmp_path / "model_2.pt")
+    assert list(sd.keys()) == list(O.init_state_dict(O.OracleConfig(**kw), seed=0).keys())      # reference key order
+    b.load_state_dict(sd)
+    b.load_optimizer_state_dict(torch.load(tmp_path / "opt_2.pt"))
+    b.train_step_fused(f, p, c, lr=5e-4, train_mode=False)
+    for (n1, q1), (n2, q2) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert n1 == n2 and torch.allclose(q1, q2, rtol=1e-5, atol=1e-6), n1
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     N = pkg._native
     monkeypatch.setattr(N, "_lib", None)
