@@ -494,8 +494,10 @@ class CaptionEngine:
 
     # ------------------------------------------------------------------ encoder
     def _cat_width(self) -> int:
+        # width of the packed [features | positions | 0] operand: a multiple of 64 elements, so that its row pitch is a
+        # multiple of 128 B (a ragged pitch makes every TMA box row straddle two L2 lines: 26.6 vs 18 us for the GEMM)
         cfg = self.cfg
-        return (cfg.encode_dim_features + cfg.encode_dim_positions + 7) // 8 * 8
+        return (cfg.encode_dim_features + cfg.encode_dim_positions + 63) // 64 * 64
 
     def _pack_embed_weights(self) -> torch.Tensor:
         """[Wf | Wp (| Wobj) | 0] as one [d, Kc] matrix: feature_embedding + position_embedding
