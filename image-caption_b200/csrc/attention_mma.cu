@@ -42,13 +42,35 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// global [rows][64] bf16 (row stride ld) -> swizzled smem tile, rows >= nrows zero-filled up to rows_pad
+// global [rows][64] bf16 (row stride ld) -> swizzled smem tile, rows >= nrows zero-filled up to rows_pad.
+// cp.async (LDGSTS, no register staging); every thread keeps its 16-byte column and steps a row pointer, so the loop
+// body is one copy + one pointer add + the swizzled smem address.  Call load_tiles_wait() before the barrier.
 __device__ __forceinline__ void load_tile(uint32_t sbase, const bf16* g, int64_t ld, int nrows, int rows_pad, int nthreads) {
-  for (int u = threadIdx.x; u < rows_pad * 8; u += nthreads) {
-    const int r = u >> 3, c = u & 7;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (r < nrows) v = *reinterpret_cast<const uint4*>(g + (int64_t)r * ld + c * 8);
-    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tile_addr(sbase, r, c)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  const int c = threadIdx.x & 7, rstep = nthreads >> 3;
+  const bf16* gp = g + (int64_t)(threadIdx.x >> 3) * ld + c * 8;
+  const int64_t gstep = (int64_t)rstep * ld;
+  for (int r = threadIdx.x >> 3; r < rows_pad; r += rstep, gp += gstep) {
+    const uint32_t dst = tile_addr(sbase, r, c);
+    if (r < nrows) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gp) : "memory");
+    else asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(dst), "r"(0u) : "memory");
+  }
+}
+__device__ __forceinline__ void load_tiles_wait() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// bit j of word w = key 32*w + j exists and is valid (computed once per warp: NW byte loads per lane instead of one per element)
+template <int NW>
+__device__ __forceinline__ void key_mask(uint32_t (&km)[NW], const uint8_t* __restrict__ kvalid_b, int Lk, int lane) {
+#pragma unroll
+  for (int w = 0; w < NW; ++w) {
+    const int j = w * 32 + lane;
+    km[w] = __ballot_sync(0xffffffffu, j < Lk && (kvalid_b == nullptr || kvalid_b[j] != 0));
   }
 }
 
@@ -76,16 +98,21 @@ __device__ __forceinline__ void qk_tile(float (&s)[NT8][4], uint32_t sQ, uint32_
 template <int NT8>
 __device__ __forceinline__ void softmax_tile(float (&s)[NT8][4], int m0, int lane, int Lq, int Lk, float scale,
                                              const uint8_t* __restrict__ kvalid_b, int causal) {
+  constexpr int NW = (NT8 * 8 + 31) / 32;
+  uint32_t km[NW];
+  key_mask<NW>(km, kvalid_b, Lk, lane);
   const int r0 = m0 + (lane >> 2), r1 = r0 + 8;
+  const float c = scale * 1.4426950408889634f;      // logits are kept pre-multiplied by log2(e): p = 2^(v - max)
   float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
   for (int nt = 0; nt < NT8; ++nt) {
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
+      const int jl = (nt & 3) * 8 + 2 * (lane & 3) + e;             // bit within word nt / 4
       const int j = nt * 8 + 2 * (lane & 3) + e;
-      const bool dead = (j >= Lk) || (kvalid_b && !kvalid_b[j]);
-      const float v0 = (dead || (causal && j > r0)) ? -INFINITY : s[nt][e] * scale;
-      const float v1 = (dead || (causal && j > r1)) ? -INFINITY : s[nt][2 + e] * scale;
+      const bool dead = !((km[nt >> 2] >> jl) & 1u);
+      const float v0 = (dead || (causal && j > r0)) ? -INFINITY : s[nt][e] * c;
+      const float v1 = (dead || (causal && j > r1)) ? -INFINITY : s[nt][2 + e] * c;
       s[nt][e] = v0; s[nt][2 + e] = v1;
       mx0 = fmaxf(mx0, v0); mx1 = fmaxf(mx1, v1);
     }
@@ -97,8 +124,8 @@ __device__ __forceinline__ void softmax_tile(float (&s)[NT8][4], int m0, int lan
   for (int nt = 0; nt < NT8; ++nt) {
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const float p0 = (s[nt][e] == -INFINITY) ? 0.f : __expf(s[nt][e] - mx0);
-      const float p1 = (s[nt][2 + e] == -INFINITY) ? 0.f : __expf(s[nt][2 + e] - mx1);
+      const float p0 = ex2_approx(s[nt][e] - mx0);                  // 2^(-inf) = 0 for masked keys (a fully masked
+      const float p1 = ex2_approx(s[nt][2 + e] - mx1);              // row gives NaN, exactly like the reference)
       s[nt][e] = p0; s[nt][2 + e] = p1;
       sum0 += p0; sum1 += p1;
     }
@@ -193,6 +220,7 @@ mha_fwd_mma_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* __restri
   load_tile(sQ, q + (int64_t)b * Lq * ldq + h * D, ldq, Lq, LqP, nthreads);
   load_tile(sK, k + (int64_t)b * Lk * ldk + h * D, ldk, Lk, LkP, nthreads);
   load_tile(sV, v + (int64_t)b * Lk * ldv + h * D, ldv, Lk, LkP, nthreads);
+  load_tiles_wait();
   __syncthreads();
   const int m0 = warp * 16;
   float s[NT8][4];
@@ -232,6 +260,7 @@ mha_bwd_mma_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* __restri
   load_tile(sK, k + (int64_t)b * Lk * ldk + h * D, ldk, Lk, LkP, nthreads);
   load_tile(sV, v + (int64_t)b * Lk * ldv + h * D, ldv, Lk, LkP, nthreads);
   load_tile(sDO, dout + (int64_t)b * Lq * lddo + h * D, lddo, Lq, LqP, nthreads);
+  load_tiles_wait();
   __syncthreads();
   const float scale = 0.125f;
   {
