@@ -576,10 +576,14 @@ int make_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int6
   cuuint64_t gstride[1] = {(cuuint64_t)ld * esz};
   cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
+  static const int promo_env = getenv("ICAP_TMA_L2_PROMOTION") ? atoi(getenv("ICAP_TMA_L2_PROMOTION")) : 256;
+  const CUtensorMapL2promotion promo = promo_env == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                       : promo_env == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                       : promo_env == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                          : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   CUresult r = fn(tm, dtype == ICAP_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                   const_cast<void*>(ptr), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   ICAP_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): ptr=%p rows=%lld cols=%lld ld=%lld", (int)r, ptr,
            (long long)rows, (long long)cols, (long long)ld);
   return 0;
