@@ -244,6 +244,19 @@ __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
   h = __floats2bfloat162_rn(v[6], v[7]); t.w = *reinterpret_cast<uint32_t*>(&h);
   *reinterpret_cast<uint4*>(p) = t;
 }
+// v[0..7] = keep ? v * keep_scale : 0 for the 8 elements of vector e8, without materialising the keep mask.
+// Same decisions as dropout_keep8 / dropout_keep4 (rand32 of pair index 4*e8 + i; e8 < 2^30 so the index is 32-bit:
+// hash32(idx * C + seed) with idx * C advanced by one multiply + adds).
+__device__ __forceinline__ void dropout_apply8(float (&v)[8], uint32_t sf, uint32_t e8, uint32_t thresh, float keep_scale) {
+  const uint32_t t16 = thresh >> 16;
+  uint32_t k = (e8 * 4u) * 0x9E3779B1u + sf;
+#pragma unroll
+  for (int i = 0; i < 4; ++i, k += 0x9E3779B1u) {
+    const uint32_t h = hash32(k);
+    v[2 * i] = (h & 0xFFFFu) >= t16 ? v[2 * i] * keep_scale : 0.f;
+    v[2 * i + 1] = (h >> 16) >= t16 ? v[2 * i + 1] * keep_scale : 0.f;
+  }
+}
 __device__ __forceinline__ uint32_t dropout_keep8(uint32_t sf, uint64_t e8, uint32_t thresh) {
   return dropout_keep2(sf, 4 * e8, thresh) | (dropout_keep2(sf, 4 * e8 + 1, thresh) << 2) |
          (dropout_keep2(sf, 4 * e8 + 2, thresh) << 4) | (dropout_keep2(sf, 4 * e8 + 3, thresh) << 6);
@@ -278,16 +291,15 @@ add_ln_fwd8_kernel(int M, int d, TA* __restrict__ a, const TR* __restrict__ res,
 #pragma unroll
   for (int r = 0; r < RPW; ++r) {
     const int row = row0 + r;
-    const TR* rrow = res ? res + (int64_t)(row % res_rows) * d : nullptr;
+    const int rrow_i = row < res_rows ? row : row % res_rows;       // residual: usually one row per output row
+    const TR* rrow = res ? res + (int64_t)rrow_i * d : nullptr;
     float sum = 0.f;
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
       const int vi = it * 32 + lane;
       if (row < M && vi < nvec) {
         if (p_drop > 0.f) {
-          const uint32_t keep = dropout_keep8(sf, (uint64_t)row * nvec + vi, thresh);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[r][it][j] = (keep >> j) & 1 ? v[r][it][j] * keep_scale : 0.f;
+          dropout_apply8(v[r][it], sf, (uint32_t)row * (uint32_t)nvec + (uint32_t)vi, thresh, keep_scale);
         }
         if (rrow) {
           float rr[8];
@@ -413,9 +425,7 @@ add_ln_bwd_rows8_kernel(int M, int d, const T* __restrict__ dy1, const T* __rest
         if (ds) store8(ds + (int64_t)row * d + vi * 8, o);
         if (da) {
           if (p_drop > 0.f) {
-            const uint32_t keep = dropout_keep8(sf, (uint64_t)row * nvec + vi, thresh);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = (keep >> j) & 1 ? o[j] * keep_scale : 0.f;
+            dropout_apply8(o, sf, (uint32_t)row * (uint32_t)nvec + (uint32_t)vi, thresh, keep_scale);
           }
           store8(da + (int64_t)row * d + vi * 8, o);
         }
@@ -502,8 +512,8 @@ extern "C" int icap_add_ln_fwd(int a_dtype, int act_dtype, int64_t M, int64_t d,
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((unsigned)ceil_div64(M, 8));
   const uint32_t th = dropout_threshold(p_drop);
-  if (d % 8 == 0 && aligned16(a) && aligned16(res) && aligned16(y) && aligned16(gamma) && aligned16(beta) &&
-      !getenv("ICAP_LN_NARROW")) {
+  if (d % 8 == 0 && M * (d / 8) < (1ll << 30) && aligned16(a) && aligned16(res) && aligned16(y) && aligned16(gamma) &&
+      aligned16(beta) && !getenv("ICAP_LN_NARROW")) {
     static const int rpw = getenv("ICAP_LN_RPW") ? atoi(getenv("ICAP_LN_RPW")) : 1;     // rows per warp (1 or 2)
     dim3 grid8((unsigned)ceil_div64(M, 8 * (rpw == 1 ? 1 : 2)));
 #define GO8R(NIT, R, TA, TR, TY)                                                                                  \
@@ -569,8 +579,8 @@ static int add_ln_bwd_impl(int which, int act_dtype, int64_t M, int64_t d, const
   dim3 cgrid((unsigned)col_blocks, (unsigned)ceil_div64(M, rows_per_block)), cblock(32, 8);
   const void* dab = da ? da : ds;       // dbias2 sums the GEMM-branch gradient
   ICAP_ARG(dbias2 == nullptr || dab != nullptr, "icap_add_ln_bwd: dbias2 needs ds or da");
-  if (d % 8 == 0 && aligned16(dy1) && aligned16(dy2) && aligned16(s) && aligned16(ds) && aligned16(da) &&
-      aligned16(gamma) && !getenv("ICAP_LN_NARROW")) {
+  if (d % 8 == 0 && M * (d / 8) < (1ll << 30) && aligned16(dy1) && aligned16(dy2) && aligned16(s) && aligned16(ds) &&
+      aligned16(da) && aligned16(gamma) && !getenv("ICAP_LN_NARROW")) {
     static const int rpw = getenv("ICAP_LN_RPW") ? atoi(getenv("ICAP_LN_RPW")) : 1;     // rows per warp (1 or 2)
     const unsigned row_blocks8 = (unsigned)ceil_div64(M, 8 * (rpw == 1 ? 1 : 2));
     const int64_t col_blocks8 = ceil_div64(d, 256);
