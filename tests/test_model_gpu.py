@@ -255,6 +255,38 @@ def test_decode_with_generated_pad_tokens():
     assert not ids_match_except_near_ties(out, ref, m.last_gaps, tol=1e-6)
 
 
+@pytest.mark.parametrize("B,R", [(1, 37), (3, 37), (2, 5)])
+def test_odd_shapes_vs_oracle(B, R):
+    """Real data has R = NUM_OBJECT + 1 = 37 regions (features.py:101) and the demo path runs batch 1: loss,
+    logits, gradients (fp32) and decode ids against the oracle at those shapes; bf16 within tolerance."""
+    kw = model_a_cfg(encode_num_blocks=2, decode_num_blocks=2, max_length=10, num_vocab=777)
+    cfg = O.OracleConfig(**kw)
+    sd = O.init_state_dict(cfg, seed=5)
+    f, p, c = O.synthetic_batch(B, R, 2048, 84, 10, 777, seed=31 + B + R)
+    ref_logits = O.logits_forward(sd, cfg, f, p, c)
+    ref_loss, ref_grads = O.loss_and_grads(sd, cfg, f, p, c)
+    m = build(kw, sd, "fp32")
+    assert rel(m.logits(f, p, c), ref_logits) < 1e-4
+    loss = m(f, p, c)["loss"]
+    assert abs(float(loss) - float(ref_loss)) / float(ref_loss) < 1e-5
+    loss.backward()
+    for name, q in m.named_parameters():
+        r = ref_grads[name]
+        # tiny batches: one ReLU pre-activation within rounding distance of 0 moves a whole gradient row (see
+        # test_model_a_vs_oracle), so the Frobenius bound is looser than at batch 6
+        assert float((q.grad.cpu() - r).norm() / (r.norm() + 1e-12)) < 5e-3, name
+    ref_ids, _, _ = O.generate_caption_vector(sd, cfg, f, p, return_gaps=True)
+    ids, att = m.generate_caption_vector(f, p)
+    assert att[0].shape == (B, R)
+    assert not ids_match_except_near_ties(ids, ref_ids, m.last_gaps)
+    ref = O.beam_search(sd, cfg, f, p, beam_size=3)
+    out = m.beam_search(f, p, beam_size=3)
+    assert not ids_match_except_near_ties(out, ref, m.last_gaps, tol=1e-6)
+    mb = build(kw, sd, "bf16")
+    assert rel(mb.logits(f, p, c), ref_logits) < 2e-2
+    assert mb.beam_search(f, p, beam_size=3).shape == ref.shape
+
+
 def test_config5_scaled_shapes_vs_oracle():
     """BASELINE configs[4] shapes (scaled variant): d_model 1024, 16 heads, FFN 4096, 100 regions, vocab 30k (2+2
     blocks here so the CPU oracle finishes in seconds): logits fp32 / bf16, beam-5 ids in fp32."""
