@@ -174,6 +174,9 @@ class CaptionEngine:
         # traffic slows the L2-bound GEMMs it overlaps more than it saves -- so it is off by default.
         self.adam_in_backward = os.environ.get("ICAP_ADAM_IN_BWD", "0") == "1"
         self._adam_plan = None           # (lr, b1, b2, eps, gscale_dev, gscale, prev_lo) while such a backward runs
+        # cross-attention K|V projections of all decoder layers (forward) and their dgrad into the encoder-output
+        # gradient (backward) depend only on the encoder output: launched on the side stream
+        self.xkv_side = os.environ.get("ICAP_XKV_SIDE", "1") != "0"
         # micro-batching (train_step_mb): the batch is cut into slices whose forward + backward run on separate
         # streams and accumulate into the shared gradient buffer
         self._mb_active = False
@@ -253,7 +256,7 @@ class CaptionEngine:
              out: torch.Tensor, ldc: Optional[int] = None, bias: Optional[int] = None, epi: int = 0,
              aux: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: int = 1,
              lda: Optional[int] = None, a_ptr: Optional[int] = None, c_ptr: Optional[int] = None,
-             c_dtype: Optional[int] = None) -> None:
+             c_dtype: Optional[int] = None, side: bool = False) -> None:
         ab = BF16 if self.precision == "bf16" else F32
         if c_dtype is None:
             c_dtype = F32 if out.dtype == torch.float32 else BF16
@@ -263,6 +266,9 @@ class CaptionEngine:
                 bias, epi, _ptr(aux), (aux.shape[-1] if aux is not None else 0), int(accumulate), split_k)
         if self._gemm_log is not None:
             self._gemm_log.append(args)
+        if side and self._bwd_side is not None:
+            self.side_call("icap_gemm", *args)       # off the critical path: backward side stream
+            return
         ev = self._prof_begin()
         call("icap_gemm", *args, self._s())
         self._prof_end(ev, 2.0 * M * Nn * K)
@@ -385,8 +391,9 @@ class CaptionEngine:
     # ------------------------------------------------------------------ blocks
     def mha_block(self, prefix: str, xq: torch.Tensor, xkv: torch.Tensor, B: int, Lq: int, Lk: int, H: int,
                   dk_tot: int, dv_tot: int, kvalid: Optional[torch.Tensor], causal: bool,
-                  attn_mean: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """MultiHeadAttention.forward (modules.py:67-92) with q = xq, k = v = xkv."""
+                  attn_mean: Optional[torch.Tensor] = None, kv_pre=None) -> torch.Tensor:
+        """MultiHeadAttention.forward (modules.py:67-92) with q = xq, k = v = xkv.
+        kv_pre = (tensor, event): the packed K|V projection of xkv was already launched on another stream."""
         cfg = self.cfg
         d = xq.shape[1]
         Mq, Mk = B * Lq, B * Lk
@@ -405,8 +412,12 @@ class CaptionEngine:
         else:
             qkv = self.new(Mq, dk_tot)
             self.gemm(xq, True, self.w(wq), d, True, Mq, dk_tot, d, qkv)
-            kvb = self.new(Mk, dk_tot + dv_tot)
-            self.gemm(xkv, True, self.w(wk), d, True, Mk, dk_tot + dv_tot, d, kvb)   # packed [Wk;Wv]
+            if kv_pre is not None:
+                kvb = kv_pre[0]
+                torch.cuda.current_stream(self.dev).wait_event(kv_pre[1])
+            else:
+                kvb = self.new(Mk, dk_tot + dv_tot)
+                self.gemm(xkv, True, self.w(wk), d, True, Mk, dk_tot + dv_tot, d, kvb)   # packed [Wk;Wv]
             q_ptr, k_ptr, v_ptr = qkv.data_ptr(), kvb.data_ptr(), kvb.data_ptr() + dk_tot * kvb.element_size()
             ldq, ldk, ldv = dk_tot, dk_tot + dv_tot, dk_tot + dv_tot
         att = self.new(Mq, dv_tot)
@@ -449,12 +460,15 @@ class CaptionEngine:
                     self.add_grad(xq, dx)
                     self.wgrad(dkv, xkv, self.g(wk), dk_tot + dv_tot, d, Mk)
                     # all decoder layers accumulate into ONE gradient buffer of the encoder output
+                    # (side stream when enabled: only the encoder backward needs it -- encode() appends the join)
                     gl = self.gr.setdefault(id(xkv), [])
+                    on_side = self.xkv_side and not cfg.move_first_image_feature
                     if gl:
-                        self.gemm(dkv, True, self.w(wk), d, False, Mk, d, dk_tot + dv_tot, gl[0], accumulate=True)
+                        self.gemm(dkv, True, self.w(wk), d, False, Mk, d, dk_tot + dv_tot, gl[0], accumulate=True,
+                                  side=on_side)
                     else:
                         dxkv = self.new(Mk, d)
-                        self.gemm(dkv, True, self.w(wk), d, False, Mk, d, dk_tot + dv_tot, dxkv)
+                        self.gemm(dkv, True, self.w(wk), d, False, Mk, d, dk_tot + dv_tot, dxkv, side=on_side)
                         gl.append(dxkv)
             bwd.lo = self.offsets[wq]          # lowest flat offset this closure writes gradients to (DP buckets)
             self.tape.append(bwd)
@@ -576,6 +590,11 @@ class CaptionEngine:
                 x = self.mha_block(pre + ".multihead_attention", x, x, B, R, R, H, cfg.encode_q_k_dim, cfg.encode_v_dim,
                                    None, False)
                 x = self.ffn_block(pre + ".feed_forward", x, cfg.encode_hidden_size, None)
+        if rec:
+            def join_side():        # the cross-attention dgrads into d(encoder output) ran on the side stream
+                if self._bwd_side is not None:
+                    torch.cuda.current_stream(self.dev).wait_stream(self._bwd_side)
+            self.tape.append(join_side)
         return x, kvalid
 
     def _encode_split_objects(self, xcat, wcat, dwcat, kvalid, B, R):
@@ -652,13 +671,31 @@ class CaptionEngine:
                      self.g("decoder.word_embedding.weight"), self._s())
             bwd.lo = self.offsets["decoder.word_embedding.weight"]
             self.tape.append(bwd)
+        kv_pre = [None] * cfg.decode_num_blocks
+        if (self.xkv_side and self.tape is not None and self.wgrad_side_stream and self.precision == "bf16"
+                and self._prof is None and self._gemm_log is None):
+            # K|V projections of the encoder output for every decoder layer, on the side stream while the decoder's
+            # self-attention blocks run (the buffers live until the end of the step: self.keep)
+            main = torch.cuda.current_stream(self.dev)
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.dev)
+            self._side.wait_stream(main)
+            nkv = cfg.decode_q_k_dim + cfg.decode_v_dim
+            with torch.cuda.stream(self._side):
+                for i in range(cfg.decode_num_blocks):
+                    kvb = self.new(B * R, nkv)
+                    self.gemm(enc, True, self.w(f"decoder.decoder.{i}.encode_attention.k_linear.weight"), d, True, B * R,
+                              nkv, d, kvb)
+                    ev = torch.cuda.Event()
+                    ev.record(self._side)
+                    kv_pre[i] = (kvb, ev)
         for i in range(cfg.decode_num_blocks):
             pre = f"decoder.decoder.{i}"
             last = i == cfg.decode_num_blocks - 1
             x = self.mha_block(pre + ".self_attention", x, x, B, T, T, H, cfg.decode_q_k_dim, cfg.decode_v_dim,
                                tok_valid, True)
             x = self.mha_block(pre + ".encode_attention", x, enc, B, T, R, H, cfg.decode_q_k_dim, cfg.decode_v_dim,
-                               kvalid_enc, False, attn_mean=ctx_mean if last else None)
+                               kvalid_enc, False, attn_mean=ctx_mean if last else None, kv_pre=kv_pre[i])
             x = self.ffn_block(pre + ".feed_forward", x, cfg.decode_hidden_size, rowscale)
         if cfg.move_first_image_feature:
             x = self._move_first_tail(x, enc, B, T, R)
