@@ -584,7 +584,8 @@ static int add_ln_bwd_impl(int which, int act_dtype, int64_t M, int64_t d, const
     static const int rpw = getenv("ICAP_LN_RPW") ? atoi(getenv("ICAP_LN_RPW")) : 1;     // rows per warp (1 or 2)
     const unsigned row_blocks8 = (unsigned)ceil_div64(M, 8 * (rpw == 1 ? 1 : 2));
     const int64_t col_blocks8 = ceil_div64(d, 256);
-    int64_t splits8 = ceil_div64(148 * 3, col_blocks8);
+    static const int cols_waves = getenv("ICAP_LN_COLS_WAVES") ? atoi(getenv("ICAP_LN_COLS_WAVES")) : 3;
+    int64_t splits8 = ceil_div64(148 * cols_waves, col_blocks8);
     if (splits8 > ceil_div64(M, 16)) splits8 = ceil_div64(M, 16);
     const int rpb8 = (int)ceil_div64(M, splits8);
     dim3 cgrid8((unsigned)col_blocks8, (unsigned)ceil_div64(M, rpb8));
