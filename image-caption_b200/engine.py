@@ -958,6 +958,26 @@ class CaptionEngine:
         self.backward(zero_grads=False)
         return out2
 
+    def _proj_res_ln(self, att: torch.Tensor, resid: torch.Tensor, prefix: str, rows: int, d: int, dv_tot: int):
+        """joint_linear -> (+ residual) -> LayerNorm of an attention block in a decode step (modules.py:86-90, eval):
+        one fused launch for small row counts in bf16 (the GEMM and the LayerNorm are both latency bound there),
+        otherwise GEMM + add_ln."""
+        # (measured on B200, rows = 2560: the fused mma.sync kernel takes ~18 us against 8.5 + 5.6 us for the tcgen05 GEMM
+        #  + LayerNorm pair -- 80 CTAs of legacy tensor-core throughput lose to 148 SMs of tcgen05 -- so it is opt-in)
+        fused = (self.precision == "bf16" and d in (256, 512) and dv_tot % 64 == 0 and rows <= 8192
+                 and os.environ.get("ICAP_FUSED_PROJ_LN", "0") == "1")
+        if fused:
+            y = self.new(rows, d)
+            call("icap_linear_res_ln", rows, d, dv_tot, att.data_ptr(), dv_tot,
+                 self.w(prefix + ".joint_linear.weight"), dv_tot, None, resid.data_ptr(), d,
+                 self.p(prefix + ".layer_norm.weight"), self.p(prefix + ".layer_norm.bias"), None, y.data_ptr(), d,
+                 LN_EPS, self._s())
+            return y
+        o = self.new(rows, d)
+        self.gemm(att, True, self.w(prefix + ".joint_linear.weight"), dv_tot, True, rows, d, dv_tot, o)
+        y, *_ = self.add_ln(o, resid, rows, prefix + ".layer_norm", None, 0.0)
+        return y
+
     # ------------------------------------------------------------------ KV-cached decoding
     def decode(self, feats: torch.Tensor, pos: torch.Tensor, beam_size: int = 1, log_domain: bool = False,
                want_attention: bool = False, want_gaps: bool = False):
@@ -1044,9 +1064,7 @@ class CaptionEngine:
                          qkv.data_ptr() + dk_tot * esz, qkv.data_ptr() + 2 * dk_tot * esz, nqkv, cache.data_ptr(), nkv,
                          cache.data_ptr() + dk_tot * esz, nkv, T, att.data_ptr(), dv_tot, sl, Tmax, tk.data_ptr(), Tmax,
                          cfg.pad_idx, s())
-                o = self.new(rows, d)
-                self.gemm(att, True, self.w(pre + ".self_attention.joint_linear.weight"), dv_tot, True, rows, d, dv_tot, o)
-                x1, *_ = self.add_ln(o, x, rows, pre + ".self_attention.layer_norm", None, 0.0)
+                x1 = self._proj_res_ln(att, x, pre + ".self_attention", rows, d, dv_tot)
                 # --- cross-attention over the image regions (modules.py:196-200)
                 q2 = self.new(rows, dk_tot)
                 self.gemm(x1, True, self.w(pre + ".encode_attention.q_linear.weight"), d, True, rows, dk_tot, d, q2)
@@ -1054,9 +1072,7 @@ class CaptionEngine:
                 call("icap_mha_decode", self.act, rows, H, R, dk, dv, q2.data_ptr(), dk_tot, cross[i].data_ptr(), nkv,
                      cross[i].data_ptr() + dk_tot * esz, nkv, R, att2.data_ptr(), dv_tot, None, 0, None, 0, cfg.pad_idx,
                      kvalid.data_ptr(), k, attn[t].data_ptr() if (attn is not None and last) else None, s())
-                o2 = self.new(rows, d)
-                self.gemm(att2, True, self.w(pre + ".encode_attention.joint_linear.weight"), dv_tot, True, rows, d, dv_tot, o2)
-                x2, *_ = self.add_ln(o2, x1, rows, pre + ".encode_attention.layer_norm", None, 0.0)
+                x2 = self._proj_res_ln(att2, x1, pre + ".encode_attention", rows, d, dv_tot)
                 # --- FFN + non-pad row mask (modules.py:202-204)
                 x = self.ffn_block(pre + ".feed_forward", x2, hid, rowscale)
             if cfg.move_first_image_feature:

@@ -92,6 +92,15 @@ int icap_add_ln_bwd_params(int act_dtype, int64_t M, int64_t d, const void* dy1,
                            const float* mean, const float* rstd, const float* rowscale, const void* ds, const void* da,
                            float* dgamma, float* dbeta, float* dbias2, void* stream);
 
+/* y[M,N] = (LayerNorm(A[M,K] . W[N,K]^T + bias + res[M,N]) * gamma + beta) * rowscale[row]  -- bf16 in / out, fp32
+ * accumulation and statistics, no dropout (eval).  One launch instead of icap_gemm + icap_add_ln_fwd for the output
+ * projections of a decode step (joint_linear + residual + LayerNorm, modules.py:86-90), where the row count
+ * (batch * beam) is small and both kernels are latency bound.  N in {256, 512}, K % 64 == 0; returns -2 for shapes
+ * it does not cover (use the two-kernel path then). */
+int icap_linear_res_ln(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* W, int64_t ldw,
+                       const float* bias, const void* res, int64_t ldr, const float* gamma, const float* beta,
+                       const float* rowscale, void* y, int64_t ldy, float eps, void* stream);
+
 /* Fused log-softmax + NLL per row; with write_grad=1 the logits are overwritten IN PLACE by
  * (softmax - onehot) * inv_count[0] (zero rows for ignored targets).  row_loss: fp32 [M].
  * Replaces CrossEntropyLoss(ignore_index=pad_idx, 'mean'), model.py:76,93-96. */

@@ -168,6 +168,30 @@ def test_mha_decode_self_fused_append():
         assert rel_err(o, o_ref) < (1e-5 if act == F32 else 1e-2)
 
 
+@pytest.mark.parametrize("M,Nn,K", [(2560, 512, 512), (77, 512, 512), (512, 256, 256), (33, 512, 2048)])
+def test_linear_res_ln_fused(M, Nn, K):
+    """Fused output projection + residual + LayerNorm of a decode step == fp64 reference (bf16 inputs)."""
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    A = torch.randn(M, K, device=dev(), generator=g).bfloat16()
+    W = (torch.randn(Nn, K, device=dev(), generator=g) / math.sqrt(K)).bfloat16()
+    res = torch.randn(M, Nn, device=dev(), generator=g).bfloat16()
+    bias = torch.randn(Nn, device=dev(), generator=g)
+    gamma = torch.randn(Nn, device=dev(), generator=g)
+    beta = torch.randn(Nn, device=dev(), generator=g)
+    rs = (torch.rand(M, device=dev(), generator=g) > 0.2).float()
+    y = torch.full((M, Nn), float("nan"), device=dev(), dtype=torch.bfloat16)
+    for use_bias, use_rs in ((True, True), (False, False)):
+        N.call("icap_linear_res_ln", M, Nn, K, A.data_ptr(), K, W.data_ptr(), K, bias.data_ptr() if use_bias else None,
+               res.data_ptr(), Nn, gamma.data_ptr(), beta.data_ptr(), rs.data_ptr() if use_rs else None, y.data_ptr(), Nn,
+               1e-6, S())
+        x = A.double() @ W.double().t() + res.double() + (bias.double() if use_bias else 0.0)
+        ref = torch.nn.functional.layer_norm(x, (Nn,), gamma.double(), beta.double(), 1e-6)
+        if use_rs:
+            ref = ref * rs.double()[:, None]
+        torch.cuda.synchronize()
+        assert rel_err(y, ref) < 8e-3
+
+
 # ------------------------------------------------------------------------------------------ add + LayerNorm
 @pytest.mark.parametrize("act", [F32, BF16])
 @pytest.mark.parametrize("M,d", [(77, 32), (500, 512), (64, 1024), (33, 256)])

@@ -1,10 +1,5 @@
-for v in 1 2 3 6; do
-echo "== ICAP_LN_COLS_WAVES=$v"
-ICAP_LN_COLS_WAVES=$v timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-decode 2>&1 | python -c "
-import sys,json
-for l in sys.stdin:
-    if l.startswith('{'):
-        d=json.loads(l); print('ms_per_step', d['ms_per_step'], 'value', d['value'])
-    else: print(l.rstrip()[-300:])
-"
+timeout 300 python -m pytest tests -m gpu -x -q -k "linear_res_ln or decode or golden or odd_shapes" 2>&1 | tail -2
+for v in 0 1; do
+echo "== ICAP_FUSED_PROJ_LN=$v"
+ICAP_FUSED_PROJ_LN=$v timeout 300 python tools/decode_time.py 2>&1 | head -2
 done
