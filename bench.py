@@ -346,6 +346,42 @@ def run_ours(args):
         extra["beam5_frac_of_tensor_peak"] = extra["beam5_captions_per_s"] * GFLOP_BEAM5_PER_IMAGE * 1e9 / (pk["tflops"] * 1e12)
         model.train()
 
+    # ---------------- data feed: batches named by image number into a device-resident region cache
+    if world == 1 and not args.no_decode:
+        n_img = 2048
+        F, P, _ = O.synthetic_batch(n_img, REGIONS, 2048, 84, CAP_LEN, 10000, seed=99)
+        t0 = time.perf_counter()
+        cache = pkg.RegionCache(model, F.numpy(), P.numpy())
+        torch.cuda.synchronize(dev)
+        extra["region_cache_build_images_per_s"] = n_img / (time.perf_counter() - t0)
+        extra["region_cache_bytes_per_image"] = cache.nbytes // n_img
+        gen = torch.Generator().manual_seed(5)
+        idx_pool = [torch.randint(0, n_img, (BATCH,), generator=gen).pin_memory() for _ in range(4)]
+        # what the reference's DataLoader does on the host for the same batch (dataset.py:12-18 + default collate)
+        t0 = time.perf_counter()
+        torch.stack([F[int(i)] for i in idx_pool[0]])
+        extra["reference_host_collate_ms_per_batch"] = 1e3 * (time.perf_counter() - t0)
+        gc = pkg.GraphedTrainStep(model, BATCH, REGIONS, CAP_LEN, lr=5e-4, cache=cache)
+        gc.load(idx_pool[0], None, pool[0][2])
+        gc.capture()
+
+        def cached_loop(n, offset):
+            for i in range(n):
+                gc.load(idx_pool[i % 4], None, pool[i % 4][2])         # 2 KB of image numbers + 22 KB of captions
+                out = gc.step()
+                losses_host[offset + i:offset + i + 1].copy_(out.reshape(1), non_blocking=True)
+        cached_loop(4, args.steps)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        cached_loop(args.steps, 0)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        cache.check()
+        extra["train_region_cache_e2e_samples_per_s"] = BATCH * args.steps / (e0.elapsed_time(e1) / 1e3)
+        extra["train_region_cache_h2d_bytes_per_step"] = idx_pool[0].numel() * 8 + pool[0][2].numel() * 4
+        extra["train_region_cache_launches_per_step"] = gc.launches_per_step
+        del gc, cache
+
     cpu = cpu_baseline_sample() if not args.no_cpu_baseline else None
     line = {"metric": "train_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,

@@ -7,6 +7,8 @@ drop-in tree `core.TRANSFORMER.model` / `core.models` exactly like the reference
 """
 from .engine import ModelConfig, CaptionEngine, param_layout, flat_offsets   # noqa: F401
 from .transformer import Transformer, PolicyNetwork, GraphedTrainStep, GraphedDecode, DataParallel, GradBuckets                       # noqa: F401
+from .engine import RegionBatch                                              # noqa: F401
+from .feed import RegionCache, PrefetchLoader                                # noqa: F401
 from . import _native                                                        # noqa: F401
 
-__all__ = ["Transformer", "PolicyNetwork", "GraphedTrainStep", "GraphedDecode", "DataParallel", "GradBuckets", "ModelConfig", "CaptionEngine", "param_layout", "flat_offsets"]
+__all__ = ["Transformer", "PolicyNetwork", "GraphedTrainStep", "GraphedDecode", "DataParallel", "GradBuckets", "RegionCache", "RegionBatch", "PrefetchLoader", "ModelConfig", "CaptionEngine", "param_layout", "flat_offsets"]

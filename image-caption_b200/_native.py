@@ -38,6 +38,7 @@ SIGNATURES = {
     "icap_rows_gather_add": [I, P, L, P, L, P, L, L, L, L, L, L, P],
     "icap_rows_segsum_add": [I, P, L, P, L, L, L, L, L, L, P],
     "icap_region_valid": [P, L, L, P, P, P],
+    "icap_gather_regions": [I, P, P, L, P, I, L, L, L, P, P, P, P, P],
     "icap_caption_prep": [P, I, L, L, I, P, P, P, P, P, P, P],
     "icap_embed_fwd": [I, I, P, L, L, L, P, P, P, I, P],
     "icap_embed_bwd": [I, P, L, L, I, P, P, P],

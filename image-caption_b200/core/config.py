@@ -34,6 +34,7 @@ NUM_EPOCH = int(os.environ.get("ICAP_NUM_EPOCH", 1000))
 BATCH_SIZE = int(os.environ.get("ICAP_BATCH_SIZE", 32))
 DROPOUT = 0.3
 LEARNING_RATE = 0.0005
+REGION_CACHE = os.environ.get("ICAP_REGION_CACHE", "1") != "0"    # keep each split's region features packed in HBM
 LOG_PATH = f'./logs_{OUTPUT_NAME}/'
 WRITE_LOG = ['loss']
 

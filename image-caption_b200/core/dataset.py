@@ -1,8 +1,68 @@
 """Dataset shims.  The reference's TrainDataset / TestDataset (core/dataset.py:8-52) read COCO artefacts
 (hickle feature arrays + pickled caption vectors) that cannot exist offline; `SyntheticCaptionDataset`
 yields tensors of the same shapes / dtypes / conventions (features.py:101-118, preprocess.py:121-134,303-345)."""
+import numpy as np
 import torch
 from torch.utils.data import Dataset
+
+from core.utils import load_coco_data
+
+
+class TrainDataset(Dataset):
+    """core/dataset.py:8-30: one item per CAPTION -> (features[image], positions[image], caption, image_idx)."""
+
+    def __init__(self, data_path, split):
+        self.data = load_coco_data(data_path=data_path, split=split)
+
+    def __getitem__(self, index):
+        image_idx = self.data['image_idxs'][index]
+        return np.asarray(self.data['features'][image_idx]), np.asarray(self.data['positions'][image_idx]), \
+            self.data['captions'][index], image_idx
+
+    def __len__(self):
+        return len(self.data['captions'])
+
+    @property
+    def len_image(self):
+        return len(self.data['positions'])
+
+    @property
+    def data_dict(self):
+        return self.data
+
+
+class TestDataset(TrainDataset):
+    """core/dataset.py:33-52: (features[image], positions[image], image_idx)."""
+
+    def __init__(self, data_path, split='test'):
+        super().__init__(data_path, split)
+
+    def __getitem__(self, index):
+        image_idx = self.data['image_idxs'][index]
+        return np.asarray(self.data['features'][image_idx]), np.asarray(self.data['positions'][image_idx]), image_idx
+
+
+class IndexedCaptions(Dataset):
+    """The same items WITHOUT the region arrays: (image_idx, caption) / (image_idx,).  Used with a device-resident
+    `RegionCache` of `dataset.data['features'|'positions']`: the host never gathers or ships the
+    300 KB of fp32 features per caption that dataset.py:12-18 returns."""
+
+    def __init__(self, dataset, with_captions=True, unique_images=False):
+        d = dataset.data
+        self.image_idxs = np.asarray(d['image_idxs'], dtype=np.int64)
+        self.captions = np.asarray(d['captions'], dtype=np.int32) if with_captions else None
+        if unique_images:                      # evaluation: decode every image once, not once per caption
+            self.image_idxs = np.unique(self.image_idxs)
+            assert not with_captions
+        self.len_image = len(d['positions'])
+
+    def __len__(self):
+        return len(self.image_idxs)
+
+    def __getitem__(self, i):
+        if self.captions is None:
+            return (int(self.image_idxs[i]),)
+        return int(self.image_idxs[i]), self.captions[i]
 
 
 class SyntheticCaptionDataset(Dataset):
@@ -37,6 +97,14 @@ class SyntheticCaptionDataset(Dataset):
                 cap[i, 1:1 + int(lens[i])] = words[i, :int(lens[i])]
                 cap[i, 1 + int(lens[i])] = 2
             self.captions = cap
+
+    @property
+    def data(self):
+        """The reference's data dict (utils.py:32-64) over the synthetic arrays."""
+        d = {'features': self.features, 'positions': self.positions, 'image_idxs': self.image_idx.numpy()}
+        if self.with_captions:
+            d['captions'] = self.captions.numpy()
+        return d
 
     def __len__(self):
         return len(self.image_idx)

@@ -108,3 +108,28 @@ class TRANSFORMER(MODEL_init):
             return self.model(object_features=object_features.to(DEVICE),
                               position_features=position_features.to(DEVICE),
                               target_caption=target_caption.to(DEVICE))
+
+    # ---- device-resident region cache: batches are named by image number, nothing else crosses PCIe
+    def cache_regions(self, features, positions, chunk_images=1024):
+        """features [n_img, R, 2048] / positions [n_img, R, Dp] of a whole split (ndarray, memmap or CPU tensor) ->
+        RegionCache in HBM, packed for the encoder in the model's compute dtype."""
+        from image_caption_b200 import RegionCache
+        return RegionCache(self.model, features, positions, chunk_images=chunk_images)
+
+    def train_step_cached(self, cache, batch_image_idxs, batch_captions):
+        self.last_loss = self.model.train_step_fused(cache.batch(batch_image_idxs), None, batch_captions,
+                                                     lr=LEARNING_RATE)
+
+    def compute_loss_cached(self, cache, image_idxs, target_caption):
+        with torch.no_grad():
+            return self.model(object_features=cache.batch(image_idxs), position_features=None,
+                              target_caption=target_caption.to(DEVICE))
+
+    def generate_caption_cached(self, cache, image_idxs, beam_size=None):
+        batch = cache.batch(image_idxs)
+        if beam_size in [None, 1]:
+            caption_vector, attention_list = self.model.generate_caption_vector(batch, None)
+            return self.decode_captions(caption_vector.cpu().numpy()), attention_list
+        assert isinstance(beam_size, int) and beam_size > 1
+        caption_vector = self.model.beam_search(batch, None, beam_size=beam_size)
+        return self.decode_captions(caption_vector.cpu().numpy()), None

@@ -85,6 +85,40 @@ __global__ void region_valid_kernel(const float* __restrict__ pos, int64_t M, in
   }
 }
 
+// region cache -> batch: packed row (b, r) of xcat <- cache row (idx[b], r), with the precomputed validity of that
+// region.  One warp per row, 16-byte lanes, 4 loads in flight per lane.  An index outside [0, n_images) raises *err
+// and reads image 0 (the output stays defined; the host checks the flag once per epoch).
+template <typename TI>
+__global__ void gather_regions_kernel(const uint4* __restrict__ cache, const uint8_t* __restrict__ vcache,
+                                      const TI* __restrict__ idx, int64_t rows, int R, int row_vec, int64_t n_images,
+                                      uint4* __restrict__ xcat, uint8_t* __restrict__ kvalid,
+                                      float* __restrict__ rowscale, int* __restrict__ err) {
+  pdl_prologue();
+  const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t b = row / R;
+  const int r = (int)(row - b * R);
+  int64_t img = (int64_t)idx[b];
+  if (img < 0 || img >= n_images) {
+    if (lane == 0 && err) *err = 1;
+    img = 0;
+  }
+  const uint4* __restrict__ src = cache + (img * R + r) * row_vec;
+  uint4* __restrict__ dst = xcat + row * row_vec;
+  int j = lane;
+  for (; j + 96 < row_vec; j += 128) {
+    const uint4 a = __ldg(src + j), c = __ldg(src + j + 32), d = __ldg(src + j + 64), e = __ldg(src + j + 96);
+    dst[j] = a; dst[j + 32] = c; dst[j + 64] = d; dst[j + 96] = e;
+  }
+  for (; j < row_vec; j += 32) dst[j] = __ldg(src + j);
+  if (lane == 0) {
+    const uint8_t v = vcache[img * R + r];
+    kvalid[row] = v;
+    rowscale[row] = v ? 1.f : 0.f;
+  }
+}
+
 // captions [B, L] -> input tokens cap[:, :-1], targets cap[:, 1:], validity, non-pad target count
 template <typename TI>
 __global__ void caption_prep_kernel(const TI* __restrict__ cap, int B, int L, int pad, int* __restrict__ inp,
@@ -350,6 +384,28 @@ extern "C" int icap_region_valid(const float* pos, int64_t M, int64_t Dp, uint8_
   ICAP_ARG(pos && M > 0 && Dp > 0, "icap_region_valid: null/empty argument");
   icap_launch(region_valid_kernel, (unsigned)ceil_div64(M, 8), 256, 0, (cudaStream_t)stream, pos, M, (int)Dp, kvalid, rowscale);
   ICAP_LAUNCH_CHECK("icap_region_valid");
+  return 0;
+}
+
+extern "C" int icap_gather_regions(int dtype, const void* cache, const uint8_t* valid_cache, int64_t n_images,
+                                   const void* idx, int idx_is_int64, int64_t B, int64_t R, int64_t Kc, void* xcat,
+                                   uint8_t* kvalid, float* rowscale, int* err, void* stream) {
+  ICAP_ARG(cache && valid_cache && idx && xcat && kvalid && rowscale && n_images > 0 && B > 0 && R > 0 && Kc > 0,
+           "icap_gather_regions: null/empty argument");
+  ICAP_ARG(dtype == ICAP_F32 || dtype == ICAP_BF16, "icap_gather_regions: dtype must be fp32 or bf16");
+  const int64_t row_bytes = Kc * (dtype == ICAP_BF16 ? 2 : 4);
+  ICAP_ARG(row_bytes % 16 == 0 && ((uintptr_t)cache & 15) == 0 && ((uintptr_t)xcat & 15) == 0,
+           "icap_gather_regions: packed rows must be 16-byte multiples and 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t rows = B * R;
+  const unsigned g = (unsigned)ceil_div64(rows, 8);
+  if (idx_is_int64)
+    icap_launch(gather_regions_kernel<long long>, g, 256, 0, st, (const uint4*)cache, valid_cache, (const long long*)idx,
+                rows, (int)R, (int)(row_bytes / 16), n_images, (uint4*)xcat, kvalid, rowscale, err);
+  else
+    icap_launch(gather_regions_kernel<int>, g, 256, 0, st, (const uint4*)cache, valid_cache, (const int*)idx, rows,
+                (int)R, (int)(row_bytes / 16), n_images, (uint4*)xcat, kvalid, rowscale, err);
+  ICAP_LAUNCH_CHECK("icap_gather_regions");
   return 0;
 }
 

@@ -144,6 +144,22 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+class RegionBatch:
+    """A batch named by image numbers into a device-resident `feed.RegionCache`.  Accepted wherever
+    the engine takes `feats` (with pos=None): the packed encoder input is gathered on the device inside encode()."""
+
+    def __init__(self, cache, idx: torch.Tensor):
+        assert idx.dim() == 1 and idx.dtype in (torch.int32, torch.int64)
+        self.cache, self.idx = cache, idx
+
+    @property
+    def shape(self):
+        return (self.idx.shape[0], self.cache.regions, self.cache.dim_features)
+
+    def __getitem__(self, sl):
+        return RegionBatch(self.cache, self.idx[sl])
+
+
 class CaptionEngine:
     def __init__(self, cfg: ModelConfig, flat_params: torch.Tensor, pos_table: torch.Tensor, precision: str = "bf16"):
         assert flat_params.is_cuda and flat_params.dtype == torch.float32
@@ -552,17 +568,26 @@ class CaptionEngine:
         """Encoder.forward (model.py:257-332).  feats [B,R,Df] fp32, pos [B,R,Dp] fp32 (device)."""
         cfg = self.cfg
         B, R, Df = feats.shape
-        Dp = pos.shape[2]
-        assert Df == cfg.encode_dim_features and Dp == cfg.encode_dim_positions
         M, d, Kc = B * R, cfg.encode_input_size, self._cat_width()
         H = cfg.encode_num_heads
         kvalid = self.new(M, dtype=torch.uint8)
         rowscale = self.new(M, dtype=torch.float32)
-        call("icap_region_valid", pos.data_ptr(), M, Dp, kvalid.data_ptr(), rowscale.data_ptr(), self._s())
-        xcat = self.new(M, Kc, zero=(Kc != Df + Dp))
-        call("icap_copy2d", feats.data_ptr(), F32, Df, xcat.data_ptr(), self.act, Kc, M, Df, 0, self._s())
-        call("icap_copy2d", pos.data_ptr(), F32, Dp, xcat.data_ptr() + Df * xcat.element_size(), self.act, Kc, M, Dp, 0,
-             self._s())
+        if isinstance(feats, RegionBatch):      # rows come packed from the device-resident cache: no fp32 staging
+            c = feats.cache
+            assert c.engine_key == (Kc, self.act, Df, cfg.encode_dim_positions) and c.xcat.device == self.dev, \
+                "region cache was built for a different model configuration / precision / device"
+            xcat = self.new(M, Kc)
+            call("icap_gather_regions", self.act, c.xcat.data_ptr(), c.valid.data_ptr(), c.num_images,
+                 feats.idx.data_ptr(), int(feats.idx.dtype == torch.int64), B, R, Kc, xcat.data_ptr(),
+                 kvalid.data_ptr(), rowscale.data_ptr(), c.err.data_ptr(), self._s())
+        else:
+            Dp = pos.shape[2]
+            assert Df == cfg.encode_dim_features and Dp == cfg.encode_dim_positions
+            call("icap_region_valid", pos.data_ptr(), M, Dp, kvalid.data_ptr(), rowscale.data_ptr(), self._s())
+            xcat = self.new(M, Kc, zero=(Kc != Df + Dp))
+            call("icap_copy2d", feats.data_ptr(), F32, Df, xcat.data_ptr(), self.act, Kc, M, Df, 0, self._s())
+            call("icap_copy2d", pos.data_ptr(), F32, Dp, xcat.data_ptr() + Df * xcat.element_size(), self.act, Kc, M,
+                 Dp, 0, self._s())
         wcat = self._pack_embed_weights()
         rec = self.tape is not None
         dwcat = self.new(d, Kc, dtype=torch.float32, zero=True) if rec else None
@@ -727,8 +752,13 @@ class CaptionEngine:
 
     # ------------------------------------------------------------------ full passes
     def prepare_inputs(self, feats, pos, captions=None):
-        feats = feats.to(self.dev, torch.float32, non_blocking=True).contiguous()
-        pos = pos.to(self.dev, torch.float32, non_blocking=True).contiguous()
+        if isinstance(feats, RegionBatch):
+            assert pos is None, "a RegionBatch carries its positions"
+            if feats.idx.device != self.dev:
+                feats = RegionBatch(feats.cache, feats.idx.to(self.dev, non_blocking=True))
+        else:
+            feats = feats.to(self.dev, torch.float32, non_blocking=True).contiguous()
+            pos = pos.to(self.dev, torch.float32, non_blocking=True).contiguous()
         if captions is not None:
             captions = captions.to(self.dev, non_blocking=True).contiguous()
             assert captions.dtype in (torch.int32, torch.int64)
@@ -930,7 +960,7 @@ class CaptionEngine:
                 self.base_seed = (saved[2] + 0x51ED27 * (i + 1)) & 0xFFFFFFFF       # different dropout masks per slice
                 with torch.cuda.stream(st):
                     sl = slice(i * bs, (i + 1) * bs)
-                    logits, tgt, count2, dec = self.forward_logits(feats[sl], pos[sl], captions[sl], record=True)
+                    logits, tgt, count2, dec = self.forward_logits(feats[sl], None if pos is None else pos[sl], captions[sl], record=True)
                     out2 = self.loss_from_logits(logits, tgt, count2, dec, record=True)
                     keep_all.append(self.keep)              # backward() drops self.keep: hold the activations
                     self.backward(zero_grads=False)

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .engine import BUFFER_NAMES, CaptionEngine, ModelConfig, flat_offsets, param_layout
+from .engine import BUFFER_NAMES, CaptionEngine, ModelConfig, RegionBatch, flat_offsets, param_layout
 from ._native import IcapError
 
 
@@ -272,15 +272,16 @@ class Transformer(nn.Module):
         if os.environ.get("ICAP_DECODE_GRAPH", "1") == "0":
             return eng.decode(f, p, beam_size=beam_size, log_domain=log_domain, want_attention=want_attention,
                               want_gaps=True)
-        key = (f.shape[0], f.shape[1], int(beam_size), bool(log_domain), bool(want_attention), id(eng))
+        cache = f.cache if isinstance(f, RegionBatch) else None
+        key = (f.shape[0], f.shape[1], int(beam_size), bool(log_domain), bool(want_attention), id(eng), id(cache))
         gd = self._decode_graphs.get(key)
         if gd is None:
             if len(self._decode_graphs) >= 4:          # each graph owns its KV-cache pool: keep only a few shapes
                 self._decode_graphs.pop(next(iter(self._decode_graphs)))
             gd = GraphedDecode(self, f.shape[0], f.shape[1], beam_size, log_domain=log_domain,
-                               want_attention=want_attention, want_gaps=True)
+                               want_attention=want_attention, want_gaps=True, cache=cache)
             self._decode_graphs[key] = gd
-        return gd.run(f, p)
+        return gd.run(f.idx) if cache is not None else gd.run(f, p)
 
     def generate_caption_vector(self, object_features, position_features):
         """model.py:101-132 -> (LongTensor [B, max_length+1], list of max_length-1 float32 arrays [B, R])."""
@@ -289,7 +290,7 @@ class Transformer(nn.Module):
             f, p, _ = eng.prepare_inputs(object_features, position_features)
             out = self._decode(f, p, 1, False, True)
             B = f.shape[0]
-            ids = torch.zeros(B, self.max_length + 1, dtype=torch.long, device=f.device)
+            ids = torch.zeros(B, self.max_length + 1, dtype=torch.long, device=eng.dev)
             ids[:, :self.max_length] = out["ids"].long()
             self.last_gaps = out["gaps"]
             att = out["attention"].cpu().numpy()                      # ONE device->host copy (reference: one per step)
@@ -495,15 +496,21 @@ class GraphedDecode:
     no EOS exit, model.py:114,169).  Replays cost one launch instead of ~2000 ctypes calls."""
 
     def __init__(self, model: Transformer, batch: int, regions: int, beam_size: int, log_domain: bool = False,
-                 want_attention: bool = False, want_gaps: bool = False):
+                 want_attention: bool = False, want_gaps: bool = False, cache=None):
         eng = model._engine()
         cfg = model.cfg
         self.eng = eng
         self.kw = dict(beam_size=int(beam_size), log_domain=log_domain, want_attention=want_attention,
                        want_gaps=want_gaps)
-        self.feats = torch.zeros(batch, regions, cfg.encode_dim_features, device=eng.dev)
-        self.pos = torch.zeros(batch, regions, cfg.encode_dim_positions, device=eng.dev)
-        self.pos[:, :, 2:4] = 1.0                      # placeholder keeps every region "valid" during warm-up
+        self.cache = cache
+        if cache is not None:                          # inputs = image numbers into a device-resident RegionCache
+            assert regions == cache.regions
+            self.idx = torch.zeros(batch, dtype=torch.int64, device=eng.dev)
+            self.feats, self.pos = RegionBatch(cache, self.idx), None
+        else:
+            self.feats = torch.zeros(batch, regions, cfg.encode_dim_features, device=eng.dev)
+            self.pos = torch.zeros(batch, regions, cfg.encode_dim_positions, device=eng.dev)
+            self.pos[:, :, 2:4] = 1.0                  # placeholder keeps every region "valid" during warm-up
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.out = None
         self._streams: list = []
@@ -538,7 +545,8 @@ class GraphedDecode:
                         st = self._streams[i]
                         st.wait_stream(main)
                         with torch.cuda.stream(st):
-                            outs.append(eng.decode(self.feats[i * bs:(i + 1) * bs], self.pos[i * bs:(i + 1) * bs], **self.kw))
+                            sl = slice(i * bs, (i + 1) * bs)
+                            outs.append(eng.decode(self.feats[sl], None if self.pos is None else self.pos[sl], **self.kw))
                     for i in range(nsplit):
                         main.wait_stream(self._streams[i])
                     self.out = {
@@ -547,12 +555,16 @@ class GraphedDecode:
                         "gaps": torch.cat([o["gaps"] for o in outs], dim=1) if outs[0]["gaps"] is not None else None,
                     }
 
-    def run(self, feats: torch.Tensor, pos: torch.Tensor):
-        """Returns the engine's output dict (static device tensors, overwritten by the next run)."""
+    def run(self, feats: torch.Tensor, pos: Optional[torch.Tensor] = None):
+        """Returns the engine's output dict (static device tensors, overwritten by the next run).  With a region
+        cache `feats` is the vector of image numbers."""
         if self.graph is None:
             self.capture()
-        self.feats.copy_(feats, non_blocking=True)
-        self.pos.copy_(pos, non_blocking=True)
+        if self.cache is not None:
+            self.idx.copy_(feats, non_blocking=True)
+        else:
+            self.feats.copy_(feats, non_blocking=True)
+            self.pos.copy_(pos, non_blocking=True)
         self.eng.refresh_shadow()                      # weights may have been stepped since the capture
         self.graph.replay()
         return self.out
@@ -564,16 +576,22 @@ class GraphedTrainStep:
     device-side step counter into their seeds."""
 
     def __init__(self, model: Transformer, batch: int, regions: int, caption_len: int, lr: float = 5e-4,
-                 warmup: int = 2, dp: Optional[DataParallel] = None):
+                 warmup: int = 2, dp: Optional[DataParallel] = None, cache=None):
         eng = model._engine()
         self.dp = dp
         self.graph2: Optional[torch.cuda.CUDAGraph] = None
         cfg = model.cfg
         dev = eng.dev
         self.model, self.eng, self.lr = model, eng, lr
-        self.feats = torch.zeros(batch, regions, cfg.encode_dim_features, device=dev)
-        self.pos = torch.zeros(batch, regions, cfg.encode_dim_positions, device=dev)
-        self.pos[:, :, 2:4] = 1.0                      # placeholder keeps every region "valid" during capture
+        self.cache = cache
+        if cache is not None:                          # inputs = image numbers into a device-resident RegionCache
+            assert regions == cache.regions
+            self.idx = torch.zeros(batch, dtype=torch.int64, device=dev)
+            self.feats, self.pos = RegionBatch(cache, self.idx), None
+        else:
+            self.feats = torch.zeros(batch, regions, cfg.encode_dim_features, device=dev)
+            self.pos = torch.zeros(batch, regions, cfg.encode_dim_positions, device=dev)
+            self.pos[:, :, 2:4] = 1.0                  # placeholder keeps every region "valid" during capture
         self.cap = torch.ones(batch, caption_len, dtype=torch.int32, device=dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.out2: Optional[torch.Tensor] = None
@@ -590,9 +608,14 @@ class GraphedTrainStep:
             return self.eng.train_step_mb(self.feats, self.pos, self.cap, n_mb=self.micro_batches, lr=self.lr)
         return self.eng.train_step(self.feats, self.pos, self.cap, lr=self.lr)
 
-    def load(self, feats: torch.Tensor, pos: torch.Tensor, cap: torch.Tensor) -> None:
-        self.feats.copy_(feats, non_blocking=True)
-        self.pos.copy_(pos, non_blocking=True)
+    def load(self, feats: torch.Tensor, pos: Optional[torch.Tensor], cap: torch.Tensor) -> None:
+        """Stage one batch (host or device tensors).  With a region cache: load(image_idx, None, captions)."""
+        if self.cache is not None:
+            assert pos is None
+            self.idx.copy_(feats, non_blocking=True)
+        else:
+            self.feats.copy_(feats, non_blocking=True)
+            self.pos.copy_(pos, non_blocking=True)
         self.cap.copy_(cap, non_blocking=True)
 
     def capture(self) -> None:

@@ -160,6 +160,16 @@ int icap_rows_segsum_add(int dtype, const void* src, int64_t src_ld, void* dst, 
 /* kvalid[row] = rowscale[row] = any(pos[row,:] != 0) : get_attention_key_pad_mask / get_non_pad_mask,
  * model.py:202-209,354-358. */
 int icap_region_valid(const float* pos, int64_t M, int64_t Dp, uint8_t* kvalid, float* rowscale, void* stream);
+/* Device-resident region cache -> one batch.  The reference gathers
+ * `features[image_idx]` / `positions[image_idx]` on the HOST for every caption (core/dataset.py:12-18, five captions
+ * per image) and ships [B, R, 2048] fp32 over PCIe every step.  Here the packed encoder input rows
+ * [features | positions | 0-pad] (width Kc, the A operand of the embedding GEMM, in the compute dtype) and the
+ * per-region validity byte live in HBM for the whole data set; a step sends only `idx` (B image numbers).
+ * xcat[(b, r), :] = cache[(idx[b], r), :]; kvalid / rowscale as icap_region_valid.  *err (nullable) is set to 1 when
+ * an index is outside [0, n_images) (that row then reads image 0). */
+int icap_gather_regions(int dtype, const void* cache, const uint8_t* valid_cache, int64_t n_images, const void* idx,
+                        int idx_is_int64, int64_t B, int64_t R, int64_t Kc, void* xcat, uint8_t* kvalid,
+                        float* rowscale, int* err, void* stream);
 /* inp = cap[:, :-1], tgt = cap[:, 1:], tok_valid/rowscale = inp != pad, count_f2 = {n, 1/n} with n the
  * number of non-pad targets (model.py:88-89,421-430; the 'mean' denominator of model.py:76). */
 int icap_caption_prep(const void* captions, int cap_is_int64, int64_t B, int64_t L, int pad_idx, int* inp, int* tgt,
