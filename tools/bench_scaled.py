@@ -61,27 +61,34 @@ def main():
            "train_batch_per_gpu": args.batch, "train_ms_per_step": ms,
            "train_samples_per_s": world * args.batch / ms * 1e3, "final_loss": float(loss),
            "train_tflops_per_gpu": args.batch / ms * 1e3 * GFLOP_TRAIN / 1e3}
-    if world > 1:
-        if rank == 0:
-            print(json.dumps(out), flush=True)
-        torch.cuda.synchronize()
-        os._exit(0)               # no NCCL teardown with captured graphs alive (see bench.py)
-    del gs
+    if world == 1:
+        del gs
     model.eval()
-    fd, pd, _ = O.synthetic_batch(args.decode_batch, 100, 2048, 84, 22, 30000, seed=2)
+    fd, pd, _ = O.synthetic_batch(args.decode_batch, 100, 2048, 84, 22, 30000, seed=2 + rank)
     fd, pd = fd.to(dev), pd.to(dev)
-    gd = pkg.GraphedDecode(model, args.decode_batch, 100, 5)
+    gd = pkg.GraphedDecode(model, args.decode_batch, 100, 5)       # partitioned by image: every rank its own batch
     for _ in range(2):
         gd.run(fd, pd)
     torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
     e0.record()
     for _ in range(3):
         gd.run(fd, pd)
     e1.record()
     torch.cuda.synchronize()
-    msd = e0.elapsed_time(e1) / 3
-    out.update({"beam5_batch": args.decode_batch, "beam5_ms": msd, "beam5_captions_per_s": args.decode_batch / msd * 1e3,
-                "beam5_tflops": args.decode_batch / msd * 1e3 * GFLOP_BEAM5 / 1e3})
+    t = torch.tensor([e0.elapsed_time(e1) / 3], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    msd = float(t)
+    out.update({"beam5_batch_per_gpu": args.decode_batch, "beam5_ms": msd,
+                "beam5_captions_per_s": world * args.decode_batch / msd * 1e3,
+                "beam5_tflops_per_gpu": args.decode_batch / msd * 1e3 * GFLOP_BEAM5 / 1e3})
+    if world > 1:
+        if rank == 0:
+            print(json.dumps(out), flush=True)
+        torch.cuda.synchronize()
+        os._exit(0)               # no NCCL teardown with captured graphs alive (see bench.py)
     print(json.dumps(out))
 
 
