@@ -27,6 +27,7 @@ SIGNATURES = {
     "icap_add_ln_bwd_rows": [I, L, L, P, P, P, P, P, P, P, P, P, F, U, P, P],
     "icap_add_ln_bwd_params": [I, L, L, P, P, P, P, P, P, P, P, P, P, P, P],
     "icap_linear_res_ln": [L, L, L, P, L, P, L, P, P, L, P, P, P, P, L, F, P],
+    "icap_gemm_ln": [L, L, L, P, L, P, L, P, P, L, P, P, P, P, L, P, L, P, P, F, F, U, P, P],
     "icap_xent": [I, L, L, P, L, P, I, P, P, I, P],
     "icap_xent_finalize": [L, P, P, I, P, P],
     "icap_argmax": [I, L, L, P, L, P, L, P, P],

@@ -1,0 +1,366 @@
+// Projection + dropout + residual + LayerNorm in ONE tcgen05 kernel (bf16, sm_100a):
+//
+//   s = dropout(A[M,K] . W[N,K]^T + bias) + R          y = ((s - mean) * rstd * gamma + beta) * rowscale
+//
+// for the model widths N = d in {128, 256, 512, 1024}.  LayerNorm needs whole rows, a 128 x N fp32 accumulator per CTA
+// would leave most SMs idle at these M, so the N columns of a 128-row block are split over a THREAD-BLOCK CLUSTER of
+// CL = N / BN CTAs (BN = 128 or 256): every CTA runs its own TMA -> tcgen05.mma main loop on a 128 x BN tile
+// (accumulator in TMEM), the epilogue threads (one row x BN/2 columns each, values kept in registers) reduce their row locally
+// (mean, sum of squared deviations), publish the pair into the shared memory of every CTA of the cluster (DSMEM),
+// and after one cluster barrier combine the 2*CL partials (Chan's parallel variance) and normalise.  The GEMM output
+// never touches HBM: against icap_gemm + icap_add_ln_fwd this saves one launch, one write and one read of [M, N].
+//
+// Replaces `joint_linear -> Dropout -> LayerNorm(out + residual)` (modules.py:86-90) and
+// `position_wise_2 -> Dropout -> LayerNorm(out + x)` [+ `*= non_pad_mask`] (modules.py:117-120,154-155,203-204).
+// The dropout decisions are those of icap_add_ln_fwd (same counter hash, same element index), so
+// icap_add_ln_bwd consumes the saved sum / mean / rstd unchanged.
+#include <cuda.h>
+#include <stdlib.h>
+#include "icap_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+constexpr int A_TILE_BYTES = BM * BK * 2;               // 16 KB per k-block
+constexpr int NTHREADS = 320, EPI_WARPS = 8;
+constexpr int MAX_CL = 8;
+constexpr int STATS_BYTES = MAX_CL * 2 * BM * 8;        // float2 {mean, M2} per (cluster rank, column half, row)
+constexpr int PAR_BYTES = 3 * 256 * 4;                  // gamma | beta | bias slices of this CTA (BN <= 256)
+// BN = columns per CTA: 128 (6-stage ring, more CTAs: small M) or 256 (4 stages, half the operand traffic per MAC)
+template <int BN> struct LCfg {
+  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STATS_BYTES + PAR_BYTES + 128 /*barriers*/ + 1024 /*align slack*/;
+};
+
+struct LnArgs {
+  int M, N, K;
+  const bf16* res;
+  int64_t ldr;
+  const float *bias, *gamma, *beta, *rowscale;
+  bf16* y;
+  int64_t ldy;
+  bf16* s;             // nullable: pre-norm sum for the backward
+  int64_t lds;
+  float *mean, *rstd;  // nullable
+  float eps, p_drop;
+  uint32_t thresh;
+  uint64_t seed;
+  const int* seed_dev;
+};
+
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void st_cluster_f2(uint32_t cluster_addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint4 t;
+  __nv_bfloat162 h;
+  h = __floats2bfloat162_rn(v[0], v[1]); t.x = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(v[2], v[3]); t.y = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(v[4], v[5]); t.z = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(v[6], v[7]); t.w = *reinterpret_cast<uint32_t*>(&h);
+  return t;
+}
+
+template <int CL, int BN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const LnArgs g) {
+  using CF = LCfg<BN>;
+  constexpr int STAGES = CF::STAGES, B_TILE_BYTES = CF::B_TILE_BYTES, STAGE_BYTES = CF::STAGE_BYTES;
+  constexpr int NCOL = BN / 2;                                   // columns per epilogue thread
+  constexpr bool PREFETCH_RES = NCOL == 64;                      // 128 columns per thread leave no registers for it
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem_base, sB = sA + STAGES * A_TILE_BYTES;
+  const uint32_t sStats = sB + STAGES * B_TILE_BYTES, sPar = sStats + STATS_BYTES;
+  const uint32_t bars = sPar + PAR_BYTES;
+  const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES, tfull_bar = bars + 16 * STAGES, slot_addr = tfull_bar + 8;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + (slot_addr - smem_u32(smem_raw)));
+  float* const par = reinterpret_cast<float*>(smem_raw + (sPar - smem_u32(smem_raw)));
+  const float2* const stats = reinterpret_cast<const float2*>(smem_raw + (sStats - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;        // cluster (CL,1,1), gridDim.x == CL: rank = column slice
+  const int n0 = (int)rank * BN, m0 = (int)blockIdx.y * BM;
+  const int nkb = (g.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(full_bar + 8 * i, 1);
+      mbar_init(empty_bar + 8 * i, 1);
+    }
+    mbar_init(tfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_addr), "n"(BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  // phase 1 of the cluster barrier: "this CTA is running" -- waited for right before the first DSMEM store
+  if constexpr (CL > 1) cluster_arrive();
+  pdl_prologue();    // everything above overlaps the previous kernel's tail when launched with PDL
+
+  float v[NCOL];     // epilogue threads: one row x NCOL columns of s
+  const int q = warp & 3, half = warp >= 6 ? 1 : 0;              // TMEM lane quarter / column half of an epilogue warp
+  const int r_in = q * 32 + lane, row = m0 + r_in;
+  const int c0 = half * NCOL;                                   // first column inside this CTA's BN
+  const bool live = warp >= 2 && row < g.M;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ TMA producer
+      int s = 0, ph = 0;
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(empty_bar + 8 * s, ph ^ 1);
+        mbar_expect_tx(full_bar + 8 * s, STAGE_BYTES);
+        tma_load_2d(sA + s * A_TILE_BYTES, &tmA, i * BK, m0, full_bar + 8 * s);    // box {64 k, 128 m}
+        tma_load_2d(sB + s * B_TILE_BYTES, &tmB, i * BK, n0, full_bar + 8 * s);    // box {64 k, BN n}
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ MMA issuer: D=f32, A=B=bf16 K-major, 128 x BN x 16
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int s = 0, ph = 0;
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(full_bar + 8 * s, ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t aS = sA + s * A_TILE_BYTES, bS = sB + s * B_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k)
+          umma_bf16(tmem_base, make_sdesc(aS + k * 32, 16, 1024), make_sdesc(bS + k * 32, 16, 1024), idesc,
+                    (i > 0 || k > 0) ? 1u : 0u);
+        umma_commit(empty_bar + 8 * s);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      umma_commit(tfull_bar);
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------- epilogue, part 1: s and its local statistics
+    for (int t = (int)threadIdx.x - 64; t < BN; t += 32 * EPI_WARPS) {    // stage gamma | beta | bias of this column slice
+      par[t] = __ldg(g.gamma + n0 + t);
+      par[BN + t] = __ldg(g.beta + n0 + t);
+      par[2 * BN + t] = g.bias ? __ldg(g.bias + n0 + t) : 0.f;
+    }
+    const uint4* const rp = reinterpret_cast<const uint4*>(g.res + (int64_t)row * g.ldr + n0 + c0);
+    uint4 rr[PREFETCH_RES ? 8 : 1];                               // residual: 64 bf16, in flight during the main loop
+    if constexpr (PREFETCH_RES) {
+      if (live && g.res) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rr[j] = __ldg(rp + j);
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");                // the staged parameters are visible to all epilogue warps
+    mbar_wait(tfull_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+#pragma unroll
+    for (int c = 0; c < NCOL / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tacc + (uint32_t)(32 * c), r);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[32 * c + j] = __uint_as_float(r[j]);
+    }
+    if (g.bias) {
+#pragma unroll
+      for (int j = 0; j < NCOL; j += 4) {
+        const float4 b = lds_f4(sPar + (uint32_t)(2 * BN + c0 + j) * 4);
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    }
+    if (g.p_drop > 0.f) {
+      uint64_t seed = g.seed;
+      if (g.seed_dev) seed += (uint64_t)(*g.seed_dev) * 0x9E3779B97F4A7C15ull;
+      const uint32_t sf = seed_fold(seed);
+      const float keep_scale = 1.f / (1.f - g.p_drop);
+      const uint32_t e8 = (uint32_t)row * (uint32_t)(g.N >> 3) + (uint32_t)((n0 + c0) >> 3);
+#pragma unroll
+      for (int j = 0; j < NCOL / 8; ++j)
+        dropout_apply8(*reinterpret_cast<float(*)[8]>(&v[8 * j]), sf, e8 + (uint32_t)j, g.thresh, keep_scale);
+    }
+    if (live && g.res) {
+#pragma unroll
+      for (int j = 0; j < NCOL / 8; ++j) {
+        uint4 rj;
+        if constexpr (PREFETCH_RES) rj = rr[j]; else rj = __ldg(rp + j);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rj);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[8 * j + 2 * i] += __low2float(h[i]); v[8 * j + 2 * i + 1] += __high2float(h[i]); }
+      }
+    }
+    if (live && g.s) {
+      uint4* sp = reinterpret_cast<uint4*>(g.s + (int64_t)row * g.lds + n0 + c0);
+#pragma unroll
+      for (int j = 0; j < NCOL / 8; ++j) sp[j] = pack8(v + 8 * j);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCOL; ++j) sum += v[j];
+    const float lmean = sum * (1.f / (float)NCOL);
+    float m2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCOL; ++j) { const float c = v[j] - lmean; m2 += c * c; }
+    // publish {mean, M2} of this NCOL-column piece into slot (rank, half) of EVERY CTA of the cluster
+    const uint32_t slot = sStats + (uint32_t)(((int)rank * 2 + half) * BM + r_in) * 8u;
+    if constexpr (CL > 1) {
+      cluster_wait();                                             // every CTA of the cluster has started
+#pragma unroll
+      for (int dst = 0; dst < CL; ++dst) st_cluster_f2(map_to_cta(slot, (uint32_t)dst), lmean, m2);
+    } else {
+      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(slot), "f"(lmean), "f"(m2) : "memory");
+    }
+  }
+  if constexpr (CL > 1) {
+    if (warp < 2) cluster_wait();                                 // phase 1 (the epilogue warps waited above)
+    cluster_arrive();                                             // phase 2: all partial statistics are published
+    cluster_wait();
+  } else {
+    __syncthreads();
+  }
+  if (warp >= 2) {
+    // ---------------------------------------------------------------- epilogue, part 2: combine, normalise, store
+    float mp[2 * CL], mean = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2 * CL; ++i) {
+      const float2 p = stats[i * BM + r_in];
+      mp[i] = p.x;
+      mean += p.x;
+      m2 += p.y;
+    }
+    mean *= 1.f / (float)(2 * CL);
+#pragma unroll
+    for (int i = 0; i < 2 * CL; ++i) { const float dlt = mp[i] - mean; m2 += (float)NCOL * dlt * dlt; }
+    const float rstd = rsqrtf(m2 / (float)(BN * CL) + g.eps);
+    if (live) {
+      if (g.mean && rank == 0 && half == 0) { g.mean[row] = mean; g.rstd[row] = rstd; }
+      const float rs = g.rowscale ? __ldg(g.rowscale + row) : 1.f;
+      uint4* yp = reinterpret_cast<uint4*>(g.y + (int64_t)row * g.ldy + n0 + c0);
+#pragma unroll
+      for (int j = 0; j < NCOL / 8; ++j) {
+        const float4 g0 = lds_f4(sPar + (uint32_t)(c0 + 8 * j) * 4), g1 = lds_f4(sPar + (uint32_t)(c0 + 8 * j + 4) * 4);
+        const float4 b0 = lds_f4(sPar + (uint32_t)(BN + c0 + 8 * j) * 4), b1 = lds_f4(sPar + (uint32_t)(BN + c0 + 8 * j + 4) * 4);
+        float o[8];
+        o[0] = ((v[8 * j + 0] - mean) * rstd * g0.x + b0.x) * rs;
+        o[1] = ((v[8 * j + 1] - mean) * rstd * g0.y + b0.y) * rs;
+        o[2] = ((v[8 * j + 2] - mean) * rstd * g0.z + b0.z) * rs;
+        o[3] = ((v[8 * j + 3] - mean) * rstd * g0.w + b0.w) * rs;
+        o[4] = ((v[8 * j + 4] - mean) * rstd * g1.x + b1.x) * rs;
+        o[5] = ((v[8 * j + 5] - mean) * rstd * g1.y + b1.y) * rs;
+        o[6] = ((v[8 * j + 6] - mean) * rstd * g1.z + b1.z) * rs;
+        o[7] = ((v[8 * j + 7] - mean) * rstd * g1.w + b1.w) * rs;
+        yp[j] = pack8(o);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+}
+
+template <int CL, int BN>
+int launch_ln(const CUtensorMap& ta, const CUtensorMap& tb, const LnArgs& g, cudaStream_t st) {
+  static bool attr_done = false;
+  auto kern = gemm_ln_kernel<CL, BN>;
+  constexpr int SMEM_BYTES = LCfg<BN>::SMEM_BYTES;
+  if (!attr_done) {
+    ICAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)CL, (unsigned)ceil_div64(g.M, BM));
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CL > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CL;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (icap_g_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  ICAP_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, g));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int icap_gemm_ln(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* W, int64_t ldw,
+                            const float* bias, const void* res, int64_t ldr, const float* gamma, const float* beta,
+                            const float* rowscale, void* y, int64_t ldy, void* sum_out, int64_t lds, float* mean_out,
+                            float* rstd_out, float eps, float p_drop, uint64_t seed, const int* seed_dev,
+                            void* stream) {
+  ICAP_ARG(M > 0 && K > 0 && A && W && gamma && beta && y, "icap_gemm_ln: null/empty argument");
+  ICAP_ARG((mean_out == nullptr) == (rstd_out == nullptr), "icap_gemm_ln: mean_out and rstd_out go together");
+  auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+  const bool ok = (N == 128 || N == 256 || N == 512 || N == 1024) && lda % 8 == 0 && ldw % 8 == 0 && ldy % 8 == 0 &&
+                  (res == nullptr || ldr % 8 == 0) && (sum_out == nullptr || lds % 8 == 0) && al16(A) && al16(W) &&
+                  al16(y) && al16(res) && al16(sum_out) && M * (N / 8) < (1ll << 30) && p_drop >= 0.f && p_drop < 1.f;
+  if (!ok) {
+    icap_set_error("icap_gemm_ln: unsupported shape/alignment (N=%lld must be 128/256/512/1024, 16-byte aligned rows)",
+                   (long long)N);
+    return -2;       // the caller falls back to icap_gemm + icap_add_ln_fwd (same arithmetic, two launches)
+  }
+  // Columns per CTA: 128 (cluster of N/128) while all clusters of the launch fit the GPU at once -- more CTAs, shorter
+  // main loops, the right shape for the small-M decode steps; otherwise 256 (cluster of N/256), one wave for the
+  // training row counts.  ICAP_GEMM_LN_BN=128|256 forces it.
+  const int64_t tiles_m = ceil_div64(M, BM);
+  int bn = (N == 128 || tiles_m * (N / 128) <= (int64_t)(icap_num_sms() * 3) / 4) ? 128 : 256;
+  if (const char* e = getenv("ICAP_GEMM_LN_BN")) { const int f = atoi(e); if ((f == 128 || f == 256) && N % f == 0) bn = f; }
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = icap_make_tmap_2d(&ta, A, M, K, lda, BM, ICAP_BF16))) return rc;
+  if ((rc = icap_make_tmap_2d(&tb, W, N, K, ldw, bn, ICAP_BF16))) return rc;
+  LnArgs g;
+  g.M = (int)M; g.N = (int)N; g.K = (int)K;
+  g.res = (const bf16*)res; g.ldr = ldr;
+  g.bias = bias; g.gamma = gamma; g.beta = beta; g.rowscale = rowscale;
+  g.y = (bf16*)y; g.ldy = ldy; g.s = (bf16*)sum_out; g.lds = lds;
+  g.mean = mean_out; g.rstd = rstd_out;
+  g.eps = eps; g.p_drop = p_drop; g.thresh = dropout_threshold(p_drop); g.seed = seed; g.seed_dev = seed_dev;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (bn == 128) {
+    switch (N / 128) {
+      case 1: rc = launch_ln<1, 128>(ta, tb, g, st); break;
+      case 2: rc = launch_ln<2, 128>(ta, tb, g, st); break;
+      case 4: rc = launch_ln<4, 128>(ta, tb, g, st); break;
+      default: rc = launch_ln<8, 128>(ta, tb, g, st); break;
+    }
+  } else {
+    switch (N / 256) {
+      case 1: rc = launch_ln<1, 256>(ta, tb, g, st); break;
+      case 2: rc = launch_ln<2, 256>(ta, tb, g, st); break;
+      default: rc = launch_ln<4, 256>(ta, tb, g, st); break;
+    }
+  }
+  if (rc) return rc;
+  ICAP_LAUNCH_CHECK("icap_gemm_ln");
+  return 0;
+}

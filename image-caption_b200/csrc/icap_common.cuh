@@ -137,6 +137,19 @@ __device__ __forceinline__ uint32_t dropout_keep4(uint64_t seed, uint64_t e4, ui
   const uint32_t sf = seed_fold(seed);
   return dropout_keep2(sf, 2 * e4, thresh) | (dropout_keep2(sf, 2 * e4 + 1, thresh) << 2);
 }
+// v[0..7] = keep ? v * keep_scale : 0 for the 8 elements of vector e8, without materialising the keep mask.
+// Same decisions as dropout_keep8 / dropout_keep4 (rand32 of pair index 4*e8 + i; e8 < 2^30 so the index is 32-bit:
+// hash32(idx * C + seed) with idx * C advanced by one multiply + adds).
+__device__ __forceinline__ void dropout_apply8(float (&v)[8], uint32_t sf, uint32_t e8, uint32_t thresh, float keep_scale) {
+  const uint32_t t16 = thresh >> 16;
+  uint32_t k = (e8 * 4u) * 0x9E3779B1u + sf;
+#pragma unroll
+  for (int i = 0; i < 4; ++i, k += 0x9E3779B1u) {
+    const uint32_t h = hash32(k);
+    v[2 * i] = (h & 0xFFFFu) >= t16 ? v[2 * i] * keep_scale : 0.f;
+    v[2 * i + 1] = (h >> 16) >= t16 ? v[2 * i + 1] * keep_scale : 0.f;
+  }
+}
 static inline uint32_t dropout_threshold(float p) {
   double t = (double)p * 4294967296.0;
   if (t < 0) t = 0;

@@ -244,19 +244,6 @@ __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
   h = __floats2bfloat162_rn(v[6], v[7]); t.w = *reinterpret_cast<uint32_t*>(&h);
   *reinterpret_cast<uint4*>(p) = t;
 }
-// v[0..7] = keep ? v * keep_scale : 0 for the 8 elements of vector e8, without materialising the keep mask.
-// Same decisions as dropout_keep8 / dropout_keep4 (rand32 of pair index 4*e8 + i; e8 < 2^30 so the index is 32-bit:
-// hash32(idx * C + seed) with idx * C advanced by one multiply + adds).
-__device__ __forceinline__ void dropout_apply8(float (&v)[8], uint32_t sf, uint32_t e8, uint32_t thresh, float keep_scale) {
-  const uint32_t t16 = thresh >> 16;
-  uint32_t k = (e8 * 4u) * 0x9E3779B1u + sf;
-#pragma unroll
-  for (int i = 0; i < 4; ++i, k += 0x9E3779B1u) {
-    const uint32_t h = hash32(k);
-    v[2 * i] = (h & 0xFFFFu) >= t16 ? v[2 * i] * keep_scale : 0.f;
-    v[2 * i + 1] = (h >> 16) >= t16 ? v[2 * i + 1] * keep_scale : 0.f;
-  }
-}
 __device__ __forceinline__ uint32_t dropout_keep8(uint32_t sf, uint64_t e8, uint32_t thresh) {
   return dropout_keep2(sf, 4 * e8, thresh) | (dropout_keep2(sf, 4 * e8 + 1, thresh) << 2) |
          (dropout_keep2(sf, 4 * e8 + 2, thresh) << 4) | (dropout_keep2(sf, 4 * e8 + 3, thresh) << 6);

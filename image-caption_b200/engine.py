@@ -193,6 +193,8 @@ class CaptionEngine:
         # cross-attention K|V projections of all decoder layers (forward) and their dgrad into the encoder-output
         # gradient (backward) depend only on the encoder output: launched on the side stream
         self.xkv_side = os.environ.get("ICAP_XKV_SIDE", "1") != "0"
+        # projection + dropout + residual + LayerNorm as one cluster kernel: 0 never, 1 inference passes, 2 training too
+        self.gemm_ln_mode = int(os.environ.get("ICAP_GEMM_LN", "0"))
         # micro-batching (train_step_mb): the batch is cut into slices whose forward + backward run on separate
         # streams and accumulate into the shared gradient buffer
         self._mb_active = False
@@ -367,6 +369,32 @@ class CaptionEngine:
              _ptr(rstd), int(rec), p, seed, self.step_dev.data_ptr(), LN_EPS, self._s())
         return y, mean, rstd, seed, p
 
+    def proj_add_ln(self, a: torch.Tensor, w_name: str, K: int, bias: Optional[int], res: torch.Tensor, norm: str,
+                    rowscale: Optional[torch.Tensor], p_drop: float):
+        """LayerNorm(dropout(a . W^T + bias) + res) [* rowscale]  (modules.py:86-90,117-120).  Returns
+        (y, s, mean, rstd, seed, p) with `s` the pre-norm sum the backward reads.  bf16 mode and d in
+        {128,256,512,1024}: ONE cluster kernel (icap_gemm_ln, statistics exchanged through DSMEM) when enabled
+        (ICAP_GEMM_LN: 0 = never, 1 = inference passes, 2 = training too); otherwise icap_gemm + icap_add_ln_fwd."""
+        M, d = a.shape[0], res.shape[1]
+        rec = self.tape is not None
+        fused = (self.precision == "bf16" and d in (128, 256, 512, 1024) and K % 8 == 0 and self._prof is None
+                 and self._gemm_log is None and (self.gemm_ln_mode == 2 or (self.gemm_ln_mode == 1 and not rec)))
+        if not fused:
+            o = self.new(M, d)
+            self.gemm(a, True, self.w(w_name), K, True, M, d, K, o, bias=bias)
+            y, mean, rstd, seed, p = self.add_ln(o, res, M, norm, rowscale, p_drop)
+            return y, o, mean, rstd, seed, p
+        y = self.new(M, d)
+        ssum = self.new(M, d) if rec else None
+        mean = self.new(M, dtype=torch.float32) if rec else None
+        rstd = self.new(M, dtype=torch.float32) if rec else None
+        seed = self._seed()
+        p = p_drop if self.training else 0.0
+        call("icap_gemm_ln", M, d, K, a.data_ptr(), a.shape[1], self.w(w_name), K, bias, res.data_ptr(), d,
+             self.p(norm + ".weight"), self.p(norm + ".bias"), _ptr(rowscale), y.data_ptr(), d, _ptr(ssum), d,
+             _ptr(mean), _ptr(rstd), LN_EPS, p, seed, self.step_dev.data_ptr(), self._s())
+        return y, ssum, mean, rstd, seed, p
+
     def ln_bwd(self, y: torch.Tensor, s: torch.Tensor, mean, rstd, norm: str, rowscale, p: float, seed: int,
                dbias2: Optional[int] = None):
         """Returns (ds, da): gradient for the residual input and for the GEMM-branch input."""
@@ -441,9 +469,8 @@ class CaptionEngine:
         p_att = ATTN_DROPOUT if self.training else 0.0
         call("icap_mha_fwd", self.act, B, H, Lq, Lk, dk, dv, q_ptr, ldq, k_ptr, ldk, v_ptr, ldv, att.data_ptr(), dv_tot,
              _ptr(kvalid), int(causal), p_att, seed_a, self.step_dev.data_ptr(), _ptr(attn_mean), self._s())
-        o = self.new(Mq, d)
-        self.gemm(att, True, self.w(prefix + ".joint_linear.weight"), dv_tot, True, Mq, d, dv_tot, o)
-        y, mean, rstd, seed_l, p_l = self.add_ln(o, xq, Mq, prefix + ".layer_norm", None, cfg.dropout)
+        y, o, mean, rstd, seed_l, p_l = self.proj_add_ln(att, prefix + ".joint_linear.weight", dv_tot, None, xq,
+                                                         prefix + ".layer_norm", None, cfg.dropout)
 
         if self.tape is not None:
             def bwd():
@@ -502,9 +529,7 @@ class CaptionEngine:
         gin = x if x_in is None else x_in
         h = self.new(M, hidden)
         self.gemm(gin, True, self.w(w1), d, True, M, hidden, d, h, bias=self.p(b1), epi=N.EPI_RELU)
-        f = self.new(M, d)
-        self.gemm(h, True, self.w(w2), hidden, True, M, d, hidden, f, bias=self.p(b2))
-        y, mean, rstd, seed_l, p_l = self.add_ln(f, x, M, norm, rowscale, cfg.dropout)
+        y, f, mean, rstd, seed_l, p_l = self.proj_add_ln(h, w2, hidden, self.p(b2), x, norm, rowscale, cfg.dropout)
 
         if self.tape is not None:
             def bwd():
@@ -1003,9 +1028,8 @@ class CaptionEngine:
                  self.p(prefix + ".layer_norm.weight"), self.p(prefix + ".layer_norm.bias"), None, y.data_ptr(), d,
                  LN_EPS, self._s())
             return y
-        o = self.new(rows, d)
-        self.gemm(att, True, self.w(prefix + ".joint_linear.weight"), dv_tot, True, rows, d, dv_tot, o)
-        y, *_ = self.add_ln(o, resid, rows, prefix + ".layer_norm", None, 0.0)
+        y, *_ = self.proj_add_ln(att, prefix + ".joint_linear.weight", dv_tot, None, resid, prefix + ".layer_norm", None,
+                                 0.0)
         return y
 
     # ------------------------------------------------------------------ KV-cached decoding

@@ -92,6 +92,18 @@ int icap_add_ln_bwd_params(int act_dtype, int64_t M, int64_t d, const void* dy1,
                            const float* mean, const float* rstd, const float* rowscale, const void* ds, const void* da,
                            float* dgamma, float* dbeta, float* dbias2, void* stream);
 
+/* y = (LayerNorm(dropout(A[M,K] . W[N,K]^T + bias) + res) * gamma + beta) * rowscale in ONE tcgen05 kernel (bf16, N = d in
+ * {128, 256, 512, 1024}): the N columns of a 128-row block are split over a thread-block cluster of N/128 CTAs, each
+ * with its own TMA -> tcgen05.mma main loop; the row statistics are exchanged through distributed shared memory.
+ * sum_out (nullable) receives the pre-norm sum, mean_out / rstd_out (nullable, fp32 [M]) the statistics: exactly
+ * what icap_add_ln_fwd(write_sum=1) leaves for icap_add_ln_bwd, with the same dropout decisions (seed, element).
+ * Returns -2 (nothing launched) for other shapes / unaligned rows: call icap_gemm + icap_add_ln_fwd instead.
+ * Replaces joint_linear / position_wise_2 -> Dropout -> LayerNorm(out + residual) [-> *= non_pad_mask],
+ * modules.py:86-90,117-120,154-155,203-204. */
+int icap_gemm_ln(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* W, int64_t ldw,
+                 const float* bias, const void* res, int64_t ldr, const float* gamma, const float* beta,
+                 const float* rowscale, void* y, int64_t ldy, void* sum_out, int64_t lds, float* mean_out,
+                 float* rstd_out, float eps, float p_drop, uint64_t seed, const int* seed_dev, void* stream);
 /* y[M,N] = (LayerNorm(A[M,K] . W[N,K]^T + bias + res[M,N]) * gamma + beta) * rowscale[row]  -- bf16 in / out, fp32
  * accumulation and statistics, no dropout (eval).  One launch instead of icap_gemm + icap_add_ln_fwd for the output
  * projections of a decode step (joint_linear + residual + LayerNorm, modules.py:86-90), where the row count

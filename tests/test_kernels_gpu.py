@@ -192,6 +192,61 @@ def test_linear_res_ln_fused(M, Nn, K):
         assert rel_err(y, ref) < 8e-3
 
 
+@pytest.mark.parametrize("bn", ["auto", "128", "256"])
+@pytest.mark.parametrize("M,Nn,K", [(2560, 512, 512), (77, 512, 512), (300, 256, 256), (129, 1024, 1024),
+                                    (640, 512, 2048), (9216, 512, 512), (50, 128, 72)])
+def test_gemm_ln_cluster_fused(M, Nn, K, bn, monkeypatch):
+    """icap_gemm_ln (cluster of N/128 or N/256 CTAs, statistics exchanged through DSMEM) == fp64 reference, and its
+    saved sum / mean / rstd and DROPOUT decisions == icap_gemm + icap_add_ln_fwd (so icap_add_ln_bwd can consume them)."""
+    if bn != "auto":
+        if Nn % int(bn):
+            pytest.skip("width not a multiple of the forced tile")
+        monkeypatch.setenv("ICAP_GEMM_LN_BN", bn)
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    A = torch.randn(M, K, device=dev(), generator=g).bfloat16()
+    W = (torch.randn(Nn, K, device=dev(), generator=g) / math.sqrt(K)).bfloat16()
+    res = torch.randn(M, Nn, device=dev(), generator=g).bfloat16()
+    bias = torch.randn(Nn, device=dev(), generator=g)
+    gamma = torch.randn(Nn, device=dev(), generator=g)
+    beta = torch.randn(Nn, device=dev(), generator=g)
+    rs = (torch.rand(M, device=dev(), generator=g) > 0.2).float()
+    step = torch.tensor([3], dtype=torch.int32, device=dev())
+    for use_bias, use_rs in ((True, True), (False, False)):
+        y = torch.full((M, Nn), float("nan"), device=dev(), dtype=torch.bfloat16)
+        N.call("icap_gemm_ln", M, Nn, K, A.data_ptr(), K, W.data_ptr(), K, bias.data_ptr() if use_bias else None,
+               res.data_ptr(), Nn, gamma.data_ptr(), beta.data_ptr(), rs.data_ptr() if use_rs else None, y.data_ptr(), Nn,
+               None, 0, None, None, 1e-6, 0.0, 0, None, S())
+        x = A.double() @ W.double().t() + res.double() + (bias.double() if use_bias else 0.0)
+        ref = torch.nn.functional.layer_norm(x, (Nn,), gamma.double(), beta.double(), 1e-6)
+        if use_rs:
+            ref = ref * rs.double()[:, None]
+        torch.cuda.synchronize()
+        assert rel_err(y, ref) < 8e-3
+    # training form: dropout 0.3, sum / mean / rstd saved -- against the two-kernel path with the same seed
+    seed, p = 12345, 0.3
+    y = torch.empty(M, Nn, device=dev(), dtype=torch.bfloat16)
+    ssum = torch.empty(M, Nn, device=dev(), dtype=torch.bfloat16)
+    mean, rstd = torch.empty(M, device=dev()), torch.empty(M, device=dev())
+    N.call("icap_gemm_ln", M, Nn, K, A.data_ptr(), K, W.data_ptr(), K, bias.data_ptr(), res.data_ptr(), Nn,
+           gamma.data_ptr(), beta.data_ptr(), rs.data_ptr(), y.data_ptr(), Nn, ssum.data_ptr(), Nn, mean.data_ptr(),
+           rstd.data_ptr(), 1e-6, p, seed, step.data_ptr(), S())
+    o = torch.empty(M, Nn, device=dev(), dtype=torch.bfloat16)
+    N.call("icap_gemm", BF16, 1, 1, M, Nn, K, A.data_ptr(), K, W.data_ptr(), K, o.data_ptr(), Nn, BF16, bias.data_ptr(),
+           0, None, 0, 0, 1, S())
+    y2 = torch.empty_like(y)
+    mean2, rstd2 = torch.empty_like(mean), torch.empty_like(rstd)
+    N.call("icap_add_ln_fwd", BF16, BF16, M, Nn, o.data_ptr(), res.data_ptr(), M, gamma.data_ptr(), beta.data_ptr(),
+           rs.data_ptr(), y2.data_ptr(), mean2.data_ptr(), rstd2.data_ptr(), 1, p, seed, step.data_ptr(), 1e-6, S())
+    torch.cuda.synchronize()
+    # identical dropout decisions: a dropped element leaves s == res exactly in both paths
+    dropped, dropped2 = ssum == res, o == res          # `o` now holds the two-kernel path's pre-norm sum
+    assert float((dropped != dropped2).float().mean()) < 2e-3        # (an element whose GEMM value rounds to 0 may differ)
+    assert 0.25 < float(dropped.float().mean()) < 0.35
+    assert rel_err(ssum, o.double()) < 8e-3            # the two-kernel path rounds the GEMM output to bf16 first
+    assert rel_err(mean, mean2.double()) < 5e-3 and rel_err(rstd, rstd2.double()) < 5e-3
+    assert rel_err(y, y2.double()) < 1.5e-2
+
+
 # ------------------------------------------------------------------------------------------ add + LayerNorm
 @pytest.mark.parametrize("act", [F32, BF16])
 @pytest.mark.parametrize("M,d", [(77, 32), (500, 512), (64, 1024), (33, 256)])
