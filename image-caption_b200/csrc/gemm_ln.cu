@@ -73,17 +73,22 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
 
 template <int CL, int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
-gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const LnArgs g) {
+gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmY,
+               const __grid_constant__ CUtensorMap tmS, const LnArgs g) {
   using CF = LCfg<BN>;
   constexpr int STAGES = CF::STAGES, B_TILE_BYTES = CF::B_TILE_BYTES, STAGE_BYTES = CF::STAGE_BYTES;
   constexpr int NCOL = BN / 2;                                   // columns per epilogue thread
-  constexpr bool PREFETCH_RES = NCOL == 64;                      // 128 columns per thread leave no registers for it
+  constexpr int NB = NCOL / 64;                                  // 32-row x 64-column (4 KB, 128B-swizzled) boxes per warp
+  constexpr int BOX = 4096, BPS = B_TILE_BYTES / BOX;            // boxes per B slot of the ring
+  static_assert(2 * BPS == 8 * NB && STAGES >= 4 && STAGES * A_TILE_BYTES >= 8 * NB * BOX, "staging plan");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base, sB = sA + STAGES * A_TILE_BYTES;
   const uint32_t sStats = sB + STAGES * B_TILE_BYTES, sPar = sStats + STATS_BYTES;
   const uint32_t bars = sPar + PAR_BYTES;
-  const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES, tfull_bar = bars + 16 * STAGES, slot_addr = tfull_bar + 8;
+  const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES, tfull_bar = bars + 16 * STAGES;
+  const uint32_t rfull_bar = tfull_bar + 8, slot_addr = rfull_bar + 8;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + (slot_addr - smem_u32(smem_raw)));
   float* const par = reinterpret_cast<float*>(smem_raw + (sPar - smem_u32(smem_raw)));
   const float2* const stats = reinterpret_cast<const float2*>(smem_raw + (sStats - smem_u32(smem_raw)));
@@ -101,6 +106,10 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(empty_bar + 8 * i, 1);
     }
     mbar_init(tfull_bar, 1);
+    mbar_init(rfull_bar, 1);
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
+    if (g.res) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
+    if (g.s) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmS) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -121,6 +130,15 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int c0 = half * NCOL;                                   // first column inside this CTA's BN
   const bool live = warp >= 2 && row < g.M;
 
+  // Staging plan (all boxes 32 rows x 64 bf16 columns, 128B-swizzled, 4 KB).  Box id b = (half * NB + j) * 4 + q belongs
+  // to the epilogue warp (q, half), column box j.  The residual tile is fetched by the TMA producer as two extra "stages"
+  // of the operand ring -- ring slots nkb, nkb+1 (B part), freed by the MMAs of k-blocks nkb-STAGES.. -- so it lands
+  // while the last k-blocks are still being multiplied.  After the accumulator is complete the whole ring is free:
+  // y is staged in the A part, the saved sum in the B parts of ring slots nkb+2, nkb+3.
+  auto res_box = [&](int b) { return sB + (uint32_t)(((nkb + b / BPS) % STAGES) * B_TILE_BYTES + (b % BPS) * BOX); };
+  auto sum_box = [&](int b) { return sB + (uint32_t)(((nkb + 2 + b / BPS) % STAGES) * B_TILE_BYTES + (b % BPS) * BOX); };
+  auto y_box = [&](int b) { return sA + (uint32_t)(b * BOX); };
+
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------------------ TMA producer
@@ -131,6 +149,17 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_load_2d(sA + s * A_TILE_BYTES, &tmA, i * BK, m0, full_bar + 8 * s);    // box {64 k, 128 m}
         tma_load_2d(sB + s * B_TILE_BYTES, &tmB, i * BK, n0, full_bar + 8 * s);    // box {64 k, BN n}
         if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+      if (g.res) {
+        mbar_expect_tx(rfull_bar, BM * BN * 2);
+        for (int e = 0; e < 2; ++e) {
+          mbar_wait(empty_bar + 8 * s, ph ^ 1);                                    // ring slot nkb + e is free
+          for (int bb = 0; bb < BPS; ++bb) {
+            const int b = e * BPS + bb, qq = b & 3, hj = b >> 2;                   // hj = half * NB + j
+            tma_load_2d(res_box(b), &tmR, n0 + hj * 64, m0 + qq * 32, rfull_bar);  // box {64 cols, 32 rows}
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
       }
     }
     __syncwarp();
@@ -160,14 +189,9 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       par[BN + t] = __ldg(g.beta + n0 + t);
       par[2 * BN + t] = g.bias ? __ldg(g.bias + n0 + t) : 0.f;
     }
-    const uint4* const rp = reinterpret_cast<const uint4*>(g.res + (int64_t)row * g.ldr + n0 + c0);
-    uint4 rr[PREFETCH_RES ? 8 : 1];                               // residual: 64 bf16, in flight during the main loop
-    if constexpr (PREFETCH_RES) {
-      if (live && g.res) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) rr[j] = __ldg(rp + j);
-      }
-    }
+    const uint32_t sw = (uint32_t)(lane & 7);                     // 128B swizzle: 16-byte chunk c of row r sits at c ^ (r & 7)
+    const uint32_t my_row = (uint32_t)lane * 128u;
+    const int row0 = m0 + q * 32;
     asm volatile("bar.sync 1, 256;" ::: "memory");                // the staged parameters are visible to all epilogue warps
     mbar_wait(tfull_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -196,20 +220,40 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int j = 0; j < NCOL / 8; ++j)
         dropout_apply8(*reinterpret_cast<float(*)[8]>(&v[8 * j]), sf, e8 + (uint32_t)j, g.thresh, keep_scale);
     }
-    if (live && g.res) {
+    if (g.res) {
+      mbar_wait(rfull_bar, 0);                                    // the residual tile has landed (rows >= M: zero filled)
 #pragma unroll
-      for (int j = 0; j < NCOL / 8; ++j) {
-        uint4 rj;
-        if constexpr (PREFETCH_RES) rj = rr[j]; else rj = __ldg(rp + j);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rj);
+      for (int jb = 0; jb < NB; ++jb) {
+        const uint32_t box = res_box((half * NB + jb) * 4 + q) + my_row;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { v[8 * j + 2 * i] += __low2float(h[i]); v[8 * j + 2 * i + 1] += __high2float(h[i]); }
+        for (int t = 0; t < 8; ++t) {
+          uint4 rj;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rj.x), "=r"(rj.y), "=r"(rj.z), "=r"(rj.w)
+                       : "r"(box + (((uint32_t)t ^ sw) << 4)));
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rj);
+          const int c = jb * 64 + t * 8;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { v[c + 2 * i] += __low2float(h[i]); v[c + 2 * i + 1] += __high2float(h[i]); }
+        }
       }
     }
-    if (live && g.s) {
-      uint4* sp = reinterpret_cast<uint4*>(g.s + (int64_t)row * g.lds + n0 + c0);
+    if (g.s) {                                                    // saved pre-norm sum: registers -> swizzled box -> TMA store
 #pragma unroll
-      for (int j = 0; j < NCOL / 8; ++j) sp[j] = pack8(v + 8 * j);
+      for (int jb = 0; jb < NB; ++jb) {
+        const uint32_t box = sum_box((half * NB + jb) * 4 + q);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const uint4 o = pack8(v + jb * 64 + t * 8);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(box + my_row + (((uint32_t)t ^ sw) << 4)), "r"(o.x),
+                       "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0 && row0 < g.M) {
+          tma_store_2d(&tmS, box, n0 + c0 + jb * 64, row0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
     }
     float sum = 0.f;
 #pragma unroll
@@ -249,10 +293,11 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
     for (int i = 0; i < 2 * CL; ++i) { const float dlt = mp[i] - mean; m2 += (float)NCOL * dlt * dlt; }
     const float rstd = rsqrtf(m2 / (float)(BN * CL) + g.eps);
-    if (live) {
-      if (g.mean && rank == 0 && half == 0) { g.mean[row] = mean; g.rstd[row] = rstd; }
-      const float rs = g.rowscale ? __ldg(g.rowscale + row) : 1.f;
-      uint4* yp = reinterpret_cast<uint4*>(g.y + (int64_t)row * g.ldy + n0 + c0);
+    if (live && g.mean && rank == 0 && half == 0) { g.mean[row] = mean; g.rstd[row] = rstd; }
+    {
+      const float rs = (live && g.rowscale) ? __ldg(g.rowscale + row) : 1.f;
+      const uint32_t sw = (uint32_t)(lane & 7), my_row = (uint32_t)lane * 128u;
+      const int row0 = m0 + q * 32;
 #pragma unroll
       for (int j = 0; j < NCOL / 8; ++j) {
         const float4 g0 = lds_f4(sPar + (uint32_t)(c0 + 8 * j) * 4), g1 = lds_f4(sPar + (uint32_t)(c0 + 8 * j + 4) * 4);
@@ -266,8 +311,20 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         o[5] = ((v[8 * j + 5] - mean) * rstd * g1.y + b1.y) * rs;
         o[6] = ((v[8 * j + 6] - mean) * rstd * g1.z + b1.z) * rs;
         o[7] = ((v[8 * j + 7] - mean) * rstd * g1.w + b1.w) * rs;
-        yp[j] = pack8(o);
+        const uint4 o4 = pack8(o);
+        const uint32_t box = y_box((half * NB + j / 8) * 4 + q);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(box + my_row + (((uint32_t)(j & 7) ^ sw) << 4)),
+                     "r"(o4.x), "r"(o4.y), "r"(o4.z), "r"(o4.w) : "memory");
+        if ((j & 7) == 7) {                                       // one 64-column box complete: hand it to the TMA engine
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0 && row0 < g.M) {
+            tma_store_2d(&tmY, box, n0 + c0 + (j / 8) * 64, row0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
       }
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -277,7 +334,8 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 template <int CL, int BN>
-int launch_ln(const CUtensorMap& ta, const CUtensorMap& tb, const LnArgs& g, cudaStream_t st) {
+int launch_ln(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const CUtensorMap& ty,
+              const CUtensorMap& ts, const LnArgs& g, cudaStream_t st) {
   static bool attr_done = false;
   auto kern = gemm_ln_kernel<CL, BN>;
   constexpr int SMEM_BYTES = LCfg<BN>::SMEM_BYTES;
@@ -306,7 +364,7 @@ int launch_ln(const CUtensorMap& ta, const CUtensorMap& tb, const LnArgs& g, cud
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  ICAP_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, g));
+  ICAP_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tr, ty, ts, g));
   return 0;
 }
 
@@ -338,6 +396,11 @@ extern "C" int icap_gemm_ln(int64_t M, int64_t N, int64_t K, const void* A, int6
   int rc;
   if ((rc = icap_make_tmap_2d(&ta, A, M, K, lda, BM, ICAP_BF16))) return rc;
   if ((rc = icap_make_tmap_2d(&tb, W, N, K, ldw, bn, ICAP_BF16))) return rc;
+  CUtensorMap ty, tr, ts;                                        // 32-row x 64-column boxes of the [M, N] tensors
+  if ((rc = icap_make_tmap_2d(&ty, y, M, N, ldy, 32, ICAP_BF16))) return rc;
+  tr = ty; ts = ty;
+  if (res && (rc = icap_make_tmap_2d(&tr, res, M, N, ldr, 32, ICAP_BF16))) return rc;
+  if (sum_out && (rc = icap_make_tmap_2d(&ts, sum_out, M, N, lds, 32, ICAP_BF16))) return rc;
   LnArgs g;
   g.M = (int)M; g.N = (int)N; g.K = (int)K;
   g.res = (const bf16*)res; g.ldr = ldr;
@@ -348,16 +411,16 @@ extern "C" int icap_gemm_ln(int64_t M, int64_t N, int64_t K, const void* A, int6
   cudaStream_t st = (cudaStream_t)stream;
   if (bn == 128) {
     switch (N / 128) {
-      case 1: rc = launch_ln<1, 128>(ta, tb, g, st); break;
-      case 2: rc = launch_ln<2, 128>(ta, tb, g, st); break;
-      case 4: rc = launch_ln<4, 128>(ta, tb, g, st); break;
-      default: rc = launch_ln<8, 128>(ta, tb, g, st); break;
+      case 1: rc = launch_ln<1, 128>(ta, tb, tr, ty, ts, g, st); break;
+      case 2: rc = launch_ln<2, 128>(ta, tb, tr, ty, ts, g, st); break;
+      case 4: rc = launch_ln<4, 128>(ta, tb, tr, ty, ts, g, st); break;
+      default: rc = launch_ln<8, 128>(ta, tb, tr, ty, ts, g, st); break;
     }
   } else {
     switch (N / 256) {
-      case 1: rc = launch_ln<1, 256>(ta, tb, g, st); break;
-      case 2: rc = launch_ln<2, 256>(ta, tb, g, st); break;
-      default: rc = launch_ln<4, 256>(ta, tb, g, st); break;
+      case 1: rc = launch_ln<1, 256>(ta, tb, tr, ty, ts, g, st); break;
+      case 2: rc = launch_ln<2, 256>(ta, tb, tr, ty, ts, g, st); break;
+      default: rc = launch_ln<4, 256>(ta, tb, tr, ty, ts, g, st); break;
     }
   }
   if (rc) return rc;

@@ -192,7 +192,7 @@ beam_select_kernel(int kin, int V, const T* __restrict__ logits, int64_t ldl, co
   const int b = blockIdx.x;
   const bool vec = ((uintptr_t)logits % 16 == 0) && (ldl * sizeof(T)) % 16 == 0;
   const int L = kout + 1;
-  __shared__ float s_t1[KMAX], s_t2[KMAX];           // two largest logits of every row
+  __shared__ float s_w1[KMAX][NT / 32], s_w2[KMAX][NT / 32];   // two largest logits of every (row, warp)
   __shared__ float red2[2][NT / 32];
   __shared__ float c_s[CAND_CAP];
   __shared__ int c_i[CAND_CAP];
@@ -218,7 +218,10 @@ beam_select_kernel(int kin, int V, const T* __restrict__ logits, int64_t ldl, co
       t1 = n1;
     }
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) { red2[0][threadIdx.x >> 5] = t1; red2[1][threadIdx.x >> 5] = t2; }
+    if ((threadIdx.x & 31) == 0) {
+      red2[0][threadIdx.x >> 5] = t1; red2[1][threadIdx.x >> 5] = t2;
+      s_w1[r][threadIdx.x >> 5] = t1; s_w2[r][threadIdx.x >> 5] = t2;      // this warp's two largest logits of row r
+    }
     __syncthreads();
     float mx = red2[0][0], m2 = red2[1][0];
     for (int i = 1; i < NT / 32; ++i) {
@@ -235,28 +238,55 @@ beam_select_kernel(int kin, int V, const T* __restrict__ logits, int64_t ldl, co
       for (int i = 0; i < 8; ++i) if (i < n) sum += expf(v[i] - mx);
     }
     sum = block_sum(sum, red);
-    if (threadIdx.x == 0) {
-      s_mx[r] = mx; s_den[r] = log_domain ? logf(sum) : sum;
-      s_t1[r] = mx; s_t2[r] = m2;
-    }
+    if (threadIdx.x == 0) { s_mx[r] = mx; s_den[r] = log_domain ? logf(sum) : sum; }
   }
   if (threadIdx.x == 0) c_n = 0;
   __syncthreads();
-  // ---- fast path: tau = the L-th largest of the 2*kin scores {score(row r, its top-2 logits)} is a lower bound of
-  // the L-th best candidate overall, so only candidates with score >= tau (a handful) have to be collected and ranked.
-  bool fast = 2 * kin >= L;
-  if (fast) {
-    if (threadIdx.x == 0) {
-      float cs[2 * KMAX];
-      for (int r = 0; r < kin; ++r) {
-        const float pv = prev ? prev[b * kin + r] : 0.f;
-        cs[2 * r] = (log_domain ? (s_t1[r] - s_mx[r] - s_den[r]) : (expf(s_t1[r] - s_mx[r]) / s_den[r])) + pv;
-        cs[2 * r + 1] = (log_domain ? (s_t2[r] - s_mx[r] - s_den[r]) : (expf(s_t2[r] - s_mx[r]) / s_den[r])) + pv;
+  // ---- fast path: any L actual candidates bound the L-th best candidate from below.  tau = the L-th largest score
+  // among the two largest logits of every (row, warp) -- 16 per row.  (With only the two largest per ROW the bound is
+  // loose whenever the best L candidates come from one beam: additive probability scores make that the common case
+  // for a flat distribution, thousands of candidates passed and the slow path below ran: +1.8 ms per beam-5 decode.)
+  // Only candidates with score >= tau (about L of them) have to be collected and ranked.
+  {
+    if (threadIdx.x < 32) {
+      constexpr int PER = 2 * (NT / 32);               // bound candidates per row
+      const int lane = threadIdx.x, total = kin * PER;
+      float cs[(KMAX * PER + 31) / 32];
+#pragma unroll
+      for (int u = 0; u < (KMAX * PER + 31) / 32; ++u) {
+        const int e = lane + 32 * u;
+        float sc = -INFINITY;
+        if (e < total) {
+          const int r = e / PER, w = (e % PER) >> 1;
+          const float lg = (e & 1) ? s_w2[r][w] : s_w1[r][w];
+          if (lg > -INFINITY) {
+            const float pv = prev ? prev[b * kin + r] : 0.f;
+            sc = (log_domain ? (lg - s_mx[r] - s_den[r]) : (expf(lg - s_mx[r]) / s_den[r])) + pv;
+          }
+        }
+        cs[u] = sc;
       }
-      for (int a = 0; a < L; ++a)                      // partial selection sort: cs[L-1] = L-th largest
-        for (int c = a + 1; c < 2 * kin; ++c)
-          if (cs[c] > cs[a]) { const float t = cs[a]; cs[a] = cs[c]; cs[c] = t; }
-      s_tau = cs[L - 1];
+      float kth = -INFINITY;
+      for (int round = 0; round < L; ++round) {        // L rounds of "largest remaining"
+        float bs = -INFINITY;
+        int bu = 0;
+#pragma unroll
+        for (int u = 0; u < (KMAX * PER + 31) / 32; ++u) if (cs[u] > bs) { bs = cs[u]; bu = u; }
+        float ws = bs;
+        int wl = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float os = __shfl_xor_sync(0xffffffffu, ws, o);
+          const int ol = __shfl_xor_sync(0xffffffffu, wl, o);
+          if (os > ws || (os == ws && ol < wl)) { ws = os; wl = ol; }
+        }
+        kth = ws;
+        if (lane == wl) {
+#pragma unroll
+          for (int u = 0; u < (KMAX * PER + 31) / 32; ++u) if (u == bu) cs[u] = -INFINITY;
+        }
+      }
+      if (lane == 0) s_tau = kth;                      // -inf (fewer than L real candidates): everything passes
     }
     __syncthreads();
     const float tau = s_tau;

@@ -194,7 +194,8 @@ class CaptionEngine:
         # gradient (backward) depend only on the encoder output: launched on the side stream
         self.xkv_side = os.environ.get("ICAP_XKV_SIDE", "1") != "0"
         # projection + dropout + residual + LayerNorm as one cluster kernel: 0 never, 1 inference passes, 2 training too
-        self.gemm_ln_mode = int(os.environ.get("ICAP_GEMM_LN", "0"))
+        # (measured on B200: beam-5 decode 17.0 -> 15.8 ms, training step 4.53 -> 4.44 ms)
+        self.gemm_ln_mode = int(os.environ.get("ICAP_GEMM_LN", "2"))
         # micro-batching (train_step_mb): the batch is cut into slices whose forward + backward run on separate
         # streams and accumulate into the shared gradient buffer
         self._mb_active = False
@@ -378,7 +379,7 @@ class CaptionEngine:
         M, d = a.shape[0], res.shape[1]
         rec = self.tape is not None
         fused = (self.precision == "bf16" and d in (128, 256, 512, 1024) and K % 8 == 0 and self._prof is None
-                 and self._gemm_log is None and (self.gemm_ln_mode == 2 or (self.gemm_ln_mode == 1 and not rec)))
+                 and (self.gemm_ln_mode == 2 or (self.gemm_ln_mode == 1 and not rec)))
         if not fused:
             o = self.new(M, d)
             self.gemm(a, True, self.w(w_name), K, True, M, d, K, o, bias=bias)
