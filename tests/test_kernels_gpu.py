@@ -561,6 +561,59 @@ def test_beam_select(log_domain, kin, kout, V):
     assert torch.allclose(gap, ref_s[:, kout - 1] - ref_s[:, kout], rtol=1e-3, atol=1e-7)
 
 
+@pytest.mark.parametrize("log_domain", [0, 1])
+@pytest.mark.parametrize("case", ["flat", "one_beam_dominates", "ties", "tiny_vocab", "bf16_flat"])
+def test_beam_select_degenerate_distributions(log_domain, case):
+    """The candidate threshold must stay exact when the distribution is nearly uniform, when one beam's previous score
+    dwarfs the others (all winners from one row -- the additive probability scores of model.py:176-181 make this the
+    common case early in training), with exact ties (more tied candidates than the fast path's list: slow path), and
+    when whole warps see no vocabulary entries."""
+    B, kin, kout, V = 9, 5, 5, 10000
+    g = torch.Generator(device="cuda").manual_seed(11)
+    dtype, code = torch.float32, F32
+    if case in ("flat", "bf16_flat"):
+        logits = torch.randn(B * kin, V, device=dev(), generator=g) * 1e-2
+        prev = torch.rand(B, kin, device=dev(), generator=g) * 1e-3
+        if case == "bf16_flat":
+            dtype, code = torch.bfloat16, BF16
+    elif case == "one_beam_dominates":
+        logits = torch.randn(B * kin, V, device=dev(), generator=g) * 0.3
+        prev = torch.rand(B, kin, device=dev(), generator=g) * 1e-4
+        prev[:, 2] += 0.5 if not log_domain else 5.0
+    elif case == "ties":
+        logits = torch.zeros(B * kin, V, device=dev())
+        logits[:, 4000:6000] = 1.0                                  # 2000 tied maxima per row
+        prev = torch.zeros(B, kin, device=dev())
+    else:
+        V = 300                                                    # threads 38.. of the block see nothing
+        logits = torch.randn(B * kin, V, device=dev(), generator=g)
+        prev = torch.rand(B, kin, device=dev(), generator=g) * 0.1
+    logits = logits.to(dtype).contiguous()
+    x = logits.float()
+    sm = torch.log_softmax(x, 1) if log_domain else torch.softmax(x, 1)
+    cand = (sm.view(B, kin, V) + prev[:, :, None]).view(B, kin * V)
+    os_ = torch.empty(B, kout, device=dev())
+    op = torch.empty(B, kout, dtype=torch.int32, device=dev())
+    ot = torch.empty(B, kout, dtype=torch.int32, device=dev())
+    gap = torch.empty(B, device=dev())
+    N.call("icap_beam_select", code, B, kin, V, logits.data_ptr(), V, prev.data_ptr(), kout, os_.data_ptr(), op.data_ptr(),
+           ot.data_ptr(), gap.data_ptr(), log_domain, S())
+    torch.cuda.synchronize()
+    idx = op.long() * V + ot.long()
+    ref_s = torch.topk(cand, kout + 1, dim=1).values
+    if case == "ties":                                             # lowest flat index wins ties (CPU topk order, SURVEY 8a)
+        want = torch.arange(4000, 4000 + kout, device=dev()).expand(B, kout)
+        assert torch.equal(idx, want)
+        assert float(gap.abs().max()) == 0.0
+    else:
+        # the selected candidates' scores are the k best, in order (indices may differ only between exactly equal scores)
+        got = cand.gather(1, idx)
+        assert torch.allclose(got, ref_s[:, :kout], rtol=1e-6, atol=1e-9)
+        assert torch.allclose(os_, ref_s[:, :kout], rtol=1e-5, atol=1e-7)
+        assert len({tuple(r) for r in idx.tolist()}) >= 1 and all(len(set(r)) == kout for r in idx.tolist())
+        assert torch.allclose(gap, ref_s[:, kout - 1] - ref_s[:, kout], rtol=1e-2, atol=1e-7)
+
+
 def test_beam_reorder():
     B, k, Tmax, t = 4, 3, 8, 2
     g = torch.Generator(device="cuda").manual_seed(2)
