@@ -193,54 +193,54 @@ beam_select_kernel(int kin, int V, const T* __restrict__ logits, int64_t ldl, co
   const bool vec = ((uintptr_t)logits % 16 == 0) && (ldl * sizeof(T)) % 16 == 0;
   const int L = kout + 1;
   __shared__ float s_w1[KMAX][NT / 32], s_w2[KMAX][NT / 32];   // two largest logits of every (row, warp)
-  __shared__ float red2[2][NT / 32];
+  __shared__ float s_we[KMAX][NT / 32];
   __shared__ float c_s[CAND_CAP];
   __shared__ int c_i[CAND_CAP];
   __shared__ int c_n;
   __shared__ float s_tau;
   for (int r = 0; r < kin; ++r) {
     const T* x = logits + ((int64_t)b * kin + r) * ldl;
-    float t1 = -INFINITY, t2 = -INFINITY;             // t1 >= t2: the thread's two largest logits (= max pass)
+    // ONE pass: the thread's two largest logits (t1 >= t2) and its online softmax sum  es = sum exp(x - t1)
+    float t1 = -INFINITY, t2 = -INFINITY, es = 0.f;
     for (int j = threadIdx.x * 8; j < V; j += NT * 8) {
       float v[8];
-      load_chunk8(x, j, V, vec, v);
+      load_chunk8(x, j, V, vec, v);                   // out-of-range elements arrive as -inf
+      const float old = t1;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float xv = v[i];
         if (xv > t1) { t2 = t1; t1 = xv; } else if (xv > t2) t2 = xv;
       }
+      if (t1 > old) es *= expf(old - t1);             // new running maximum: rescale what has been summed
+      if (t1 > -INFINITY) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) es += expf(v[i] - t1);
+      }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {                // merge the sorted pairs across the warp
+    for (int o = 16; o > 0; o >>= 1) {                // merge the sorted pairs and the (max, sum) pairs across the warp
       const float o1 = __shfl_xor_sync(0xffffffffu, t1, o), o2 = __shfl_xor_sync(0xffffffffu, t2, o);
+      const float oe = __shfl_xor_sync(0xffffffffu, es, o);
       const float n1 = fmaxf(t1, o1);
+      es = es * (t1 == n1 ? 1.f : expf(t1 - n1)) + oe * (o1 == n1 ? 1.f : expf(o1 - n1));
       t2 = fmaxf(fminf(t1, o1), fmaxf(t2, o2));
       t1 = n1;
     }
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) {
-      red2[0][threadIdx.x >> 5] = t1; red2[1][threadIdx.x >> 5] = t2;
+    if ((threadIdx.x & 31) == 0) {                    // per-(row, warp) slots: no block barrier between the rows
       s_w1[r][threadIdx.x >> 5] = t1; s_w2[r][threadIdx.x >> 5] = t2;      // this warp's two largest logits of row r
+      s_we[r][threadIdx.x >> 5] = es;                                      // and its sum of exp(x - t1)
     }
-    __syncthreads();
-    float mx = red2[0][0], m2 = red2[1][0];
-    for (int i = 1; i < NT / 32; ++i) {
-      const float o1 = red2[0][i], o2 = red2[1][i];
-      const float n1 = fmaxf(mx, o1);
-      m2 = fmaxf(fminf(mx, o1), fmaxf(m2, o2));
-      mx = n1;
-    }
-    float sum = 0.f;
-    for (int j = threadIdx.x * 8; j < V; j += NT * 8) {
-      float v[8];
-      const int n = load_chunk8(x, j, V, vec, v);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) if (i < n) sum += expf(v[i] - mx);
-    }
-    sum = block_sum(sum, red);
-    if (threadIdx.x == 0) { s_mx[r] = mx; s_den[r] = log_domain ? logf(sum) : sum; }
   }
   if (threadIdx.x == 0) c_n = 0;
+  __syncthreads();
+  if (threadIdx.x < kin) {                            // thread r: softmax maximum and denominator of row r
+    const int r = threadIdx.x;
+    float mx = s_w1[r][0];
+    for (int i = 1; i < NT / 32; ++i) mx = fmaxf(mx, s_w1[r][i]);
+    float sum = 0.f;
+    for (int i = 0; i < NT / 32; ++i) sum += s_we[r][i] * (s_w1[r][i] == mx ? 1.f : expf(s_w1[r][i] - mx));
+    s_mx[r] = mx; s_den[r] = log_domain ? logf(sum) : sum;
+  }
   __syncthreads();
   // ---- fast path: any L actual candidates bound the L-th best candidate from below.  tau = the L-th largest score
   // among the two largest logits of every (row, warp) -- 16 per row.  (With only the two largest per ROW the bound is
