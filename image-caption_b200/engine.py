@@ -184,6 +184,7 @@ class CaptionEngine:
         self.wgrad_side_stream = os.environ.get("ICAP_WGRAD_STREAM", "1") != "0"
         call("icap_set_pdl", 1 if os.environ.get("ICAP_PDL", "1") == "1" else 0)
         self._side: Optional[torch.cuda.Stream] = None
+        self._warm: Optional[torch.cuda.Stream] = None       # warm-up stream of the graph captures (see warm_stream)
         self._bwd_side: Optional[torch.cuda.Stream] = None
         # optional (ICAP_ADAM_IN_BWD=1): Adam in slices on the side stream as the gradients of a suffix of the flat
         # buffer complete during the backward.  Measured on B200: 4.91 vs 4.77 ms/step -- the 1.7 GB of optimizer
@@ -223,6 +224,13 @@ class CaptionEngine:
             assert getattr(cfg, k) % 8 == 0, f"{k} must be a multiple of 8"
         assert cfg.encode_input_size == cfg.decode_input_size, \
             "cross-attention reads encoder rows with decoder projections: widths must match (as in the reference)"
+
+    def warm_stream(self) -> torch.cuda.Stream:
+        """ONE stream for the eager warm-up pass that precedes every graph capture.  The caching allocator keeps freed
+        blocks per stream: a fresh stream per capture would strand ~2 GB of cached blocks each time."""
+        if self._warm is None:
+            self._warm = torch.cuda.Stream(device=self.dev)
+        return self._warm
 
     # ------------------------------------------------------------------ parameter views
     def w(self, name: str, rows: Optional[int] = None, cols: Optional[int] = None):

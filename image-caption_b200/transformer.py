@@ -518,7 +518,7 @@ class GraphedDecode:
     def capture(self) -> None:
         eng = self.eng
         with torch.no_grad():
-            side = torch.cuda.Stream(device=eng.dev)
+            side = eng.warm_stream()
             side.wait_stream(torch.cuda.current_stream(eng.dev))
             with torch.cuda.stream(side):
                 eng.decode(self.feats, self.pos, **self.kw)            # warm-up: function attributes, allocator
@@ -624,7 +624,7 @@ class GraphedTrainStep:
         eng = self.eng
         # warm-up on a side stream (allocator + function attributes), then roll the optimizer state back
         p0, step0 = eng.p32.clone(), eng.step_dev.clone()
-        side = torch.cuda.Stream(device=eng.dev)
+        side = eng.warm_stream()
         side.wait_stream(torch.cuda.current_stream(eng.dev))
         with torch.cuda.stream(side):
             for _ in range(self.warmup):
