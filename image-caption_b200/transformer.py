@@ -178,6 +178,7 @@ class Transformer(nn.Module):
         self._init_parameters()
         self._eng: Optional[CaptionEngine] = None
         self._decode_graphs: dict = {}
+        self._train_graphs: dict = {}
 
     # ------------------------------------------------------------------ init (SURVEY.md §8a "Initialisation")
     @torch.no_grad()
@@ -220,6 +221,7 @@ class Transformer(nn.Module):
         self._flat = flat
         self._eng = None
         self._decode_graphs = {}
+        self._train_graphs = {}
         if any_p.is_cuda:
             self.device = any_p.device
 
@@ -236,6 +238,7 @@ class Transformer(nn.Module):
         if precision != self.precision:
             self.precision, self._eng = precision, None
             self._decode_graphs = {}
+            self._train_graphs = {}
         return self
 
     def _engine(self) -> CaptionEngine:
@@ -328,10 +331,15 @@ class Transformer(nn.Module):
         eng.step_dev.fill_(int(state["step"]))
         if state.get("exp_avg") is None:
             eng.adam_m = eng.adam_v = None
+            self._train_graphs = {}                    # captured steps point at the old moment buffers
             return
         assert state["exp_avg"].numel() == eng.n_flat, "optimizer state belongs to a different model configuration"
-        eng.adam_m = state["exp_avg"].to(eng.dev, torch.float32).clone()
-        eng.adam_v = state["exp_avg_sq"].to(eng.dev, torch.float32).clone()
+        if eng.adam_m is None:
+            eng.adam_m = state["exp_avg"].to(eng.dev, torch.float32).clone()
+            eng.adam_v = state["exp_avg_sq"].to(eng.dev, torch.float32).clone()
+        else:                                          # in place: captured step graphs keep pointing at these buffers
+            eng.adam_m.copy_(state["exp_avg"])
+            eng.adam_v.copy_(state["exp_avg_sq"])
 
     # ------------------------------------------------------------------ fused training step
     def train_step_fused(self, object_features, position_features, target_caption, lr: float = 5e-4,
@@ -340,8 +348,21 @@ class Transformer(nn.Module):
         (core/models.py:115-126).  Returns the device loss (0-d view, no host sync)."""
         eng = self._engine()
         f, p, c = eng.prepare_inputs(object_features, position_features, target_caption)
-        out2 = eng.train_step(f, p, c, lr=lr, train_mode=self.training if train_mode is None else train_mode)
-        return out2[0]
+        mode = self.training if train_mode is None else bool(train_mode)
+        if os.environ.get("ICAP_TRAIN_GRAPH", "1") == "0":
+            return eng.train_step(f, p, c, lr=lr, train_mode=mode)[0]
+        # one CUDA graph per (batch, regions, caption length, lr, mode) shape: a replay costs one launch instead of
+        # ~330 ctypes calls.  The returned loss is a view of the graph's static output (overwritten by the next step).
+        cache = f.cache if isinstance(f, RegionBatch) else None
+        key = (f.shape[0], f.shape[1], c.shape[1], float(lr), mode, id(eng), id(cache))
+        gs = self._train_graphs.get(key)
+        if gs is None:
+            if len(self._train_graphs) >= 4:           # every graph owns its activation pool: keep only a few shapes
+                self._train_graphs.pop(next(iter(self._train_graphs)))
+            gs = GraphedTrainStep(self, f.shape[0], f.shape[1], c.shape[1], lr=lr, cache=cache, train_mode=mode)
+            self._train_graphs[key] = gs
+        gs.load(f.idx if cache is not None else f, p, c)
+        return gs.step()
 
 
 class PolicyNetwork(Transformer):
@@ -576,9 +597,10 @@ class GraphedTrainStep:
     device-side step counter into their seeds."""
 
     def __init__(self, model: Transformer, batch: int, regions: int, caption_len: int, lr: float = 5e-4,
-                 warmup: int = 2, dp: Optional[DataParallel] = None, cache=None):
+                 warmup: int = 2, dp: Optional[DataParallel] = None, cache=None, train_mode: bool = True):
         eng = model._engine()
         self.dp = dp
+        self.train_mode = bool(train_mode)             # False: dropout off (the reference's eval-mode arithmetic)
         self.graph2: Optional[torch.cuda.CUDAGraph] = None
         cfg = model.cfg
         dev = eng.dev
@@ -606,7 +628,7 @@ class GraphedTrainStep:
     def _one_step(self) -> torch.Tensor:
         if self.micro_batches > 1:
             return self.eng.train_step_mb(self.feats, self.pos, self.cap, n_mb=self.micro_batches, lr=self.lr)
-        return self.eng.train_step(self.feats, self.pos, self.cap, lr=self.lr)
+        return self.eng.train_step(self.feats, self.pos, self.cap, lr=self.lr, train_mode=self.train_mode)
 
     def load(self, feats: torch.Tensor, pos: Optional[torch.Tensor], cap: torch.Tensor) -> None:
         """Stage one batch (host or device tensors).  With a region cache: load(image_idx, None, captions)."""
@@ -624,6 +646,8 @@ class GraphedTrainStep:
         eng = self.eng
         # warm-up on a side stream (allocator + function attributes), then roll the optimizer state back
         p0, step0 = eng.p32.clone(), eng.step_dev.clone()
+        m0 = eng.adam_m.clone() if eng.adam_m is not None else None       # a capture in the middle of a training run
+        v0 = eng.adam_v.clone() if eng.adam_v is not None else None       # must not disturb the optimizer state
         side = eng.warm_stream()
         side.wait_stream(torch.cuda.current_stream(eng.dev))
         with torch.cuda.stream(side):
@@ -635,8 +659,13 @@ class GraphedTrainStep:
         torch.cuda.current_stream(eng.dev).wait_stream(side)
         eng.p32.copy_(p0)
         eng.step_dev.copy_(step0)
-        eng.adam_m.zero_()
-        eng.adam_v.zero_()
+        if m0 is None:
+            eng.adam_m.zero_()
+            eng.adam_v.zero_()
+        else:
+            eng.adam_m.copy_(m0)
+            eng.adam_v.copy_(v0)
+        del p0, m0, v0
         eng.shadow_fresh = False
         eng.refresh_shadow()
         torch.cuda.synchronize(eng.dev)
@@ -670,8 +699,10 @@ class GraphedTrainStep:
     def step(self) -> torch.Tensor:
         if self.graph is None:
             self.capture()
+        self.eng.refresh_shadow()                      # fp32 weights changed outside (load_state_dict, another optimizer)
         self.graph.replay()
         if self.graph2 is not None:
             self.dp.reduce(self.eng)
             self.graph2.replay()
+        self.eng.shadow_fresh = True                   # the fused Adam wrote the bf16 shadow
         return self.out2[0]

@@ -433,6 +433,39 @@ def test_micro_batched_step_equals_whole_batch_step():
         assert float(diff.max()) <= 2.1e-3
 
 
+def test_train_step_fused_auto_graph_equals_eager(monkeypatch):
+    """The drop-in wrapper's train_step (core/models.py:115-126 -> train_step_fused) replays one CUDA graph per batch
+    shape.  Same losses and weights as the eager launch sequence -- including when a NEW shape is captured in the
+    middle of a run (the capture's warm-up steps must not leak into the weights or the Adam moments)."""
+    kw = model_a_cfg(encode_num_blocks=1, decode_num_blocks=1, num_vocab=500, encode_dim_features=256)
+    sd = O.init_state_dict(O.OracleConfig(**kw), seed=0)
+    batches = [O.synthetic_batch(16, 12, 256, 84, 22, 500, seed=20),
+               O.synthetic_batch(16, 12, 256, 84, 22, 500, seed=21),
+               O.synthetic_batch(9, 12, 256, 84, 22, 500, seed=22),          # new batch size: second capture, mid-run
+               O.synthetic_batch(16, 12, 256, 84, 22, 500, seed=23),          # back to the first graph
+               O.synthetic_batch(9, 7, 256, 84, 22, 500, seed=24)]            # third capture (regions differ)
+    out = {}
+    for graph in ("0", "1"):
+        monkeypatch.setenv("ICAP_TRAIN_GRAPH", graph)
+        m = build(kw, sd, "fp32").train()
+        losses = [float(m.train_step_fused(f, p, c, lr=5e-4, train_mode=False)) for f, p, c in batches]
+        out[graph] = (losses, {n: q.detach().clone() for n, q in m.state_dict().items()}, m.optimizer_state_dict())
+        assert len(m._train_graphs) == (3 if graph == "1" else 0)
+    for a, b in zip(out["0"][0], out["1"][0]):
+        assert abs(a - b) <= 1e-5 * abs(a), (out["0"][0], out["1"][0])
+    # Whole tensors in norm: Adam's first steps move every weight by ~lr * sign(g), so an element whose gradient is at
+    # the rounding-noise level of the fp32 atomics (embedding scatter-add, column sums) may flip between two runs.
+    # A leaked warm-up step would move EVERY element by ~lr: ~2e-2 of the norm.
+    for n, q in out["0"][1].items():
+        if q.is_floating_point() and q.dim() >= 2:
+            assert float((q - out["1"][1][n]).norm()) <= 1e-3 * float(q.norm()), n
+    assert out["0"][2]["step"] == out["1"][2]["step"] == len(batches)
+    ma, mb = out["0"][2]["exp_avg"], out["1"][2]["exp_avg"]
+    assert float((ma - mb).norm()) <= 1e-4 * float(ma.norm())
+    va, vb = out["0"][2]["exp_avg_sq"], out["1"][2]["exp_avg_sq"]
+    assert float((va - vb).norm()) <= 1e-4 * float(va.norm())
+
+
 def test_checkpoint_and_optimizer_resume(tmp_path):
     """state_dict round trip in the reference's format + optimizer-state resume: (2 steps, save, 1 step) ==
     (load into a fresh model, 1 step)."""
