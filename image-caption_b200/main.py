@@ -55,7 +55,7 @@ def train(num_images=64, max_iters=None, region_cache=REGION_CACHE):
         t_cache = model.cache_regions(train_ds.data['features'], train_ds.data['positions'])
         v_cache = model.cache_regions(valid_ds.data['features'], valid_ds.data['positions'])
         print(f'[train] region cache: {(t_cache.nbytes + v_cache.nbytes) / 2**20:.1f} MiB in HBM')
-        train_loader = DataLoader(IndexedCaptions(train_ds), batch_size=BATCH_SIZE, shuffle=True, drop_last=True,
+        train_loader = DataLoader(IndexedCaptions(train_ds), batch_size=BATCH_SIZE, shuffle=True,
                                   collate_fn=_collate_idx)
         valid_loader = DataLoader(IndexedCaptions(valid_ds), batch_size=BATCH_SIZE, shuffle=False,
                                   collate_fn=_collate_idx)
@@ -64,7 +64,7 @@ def train(num_images=64, max_iters=None, region_cache=REGION_CACHE):
         caption_of = lambda b: (model.generate_caption_cached(v_cache, b[0])[0], b[0])                    # noqa: E731
     else:
         t_cache = v_cache = None
-        train_loader = DataLoader(train_ds, batch_size=BATCH_SIZE, shuffle=True, drop_last=True)
+        train_loader = DataLoader(train_ds, batch_size=BATCH_SIZE, shuffle=True)
         valid_loader = DataLoader(valid_ds, batch_size=BATCH_SIZE, shuffle=False)
         step = lambda b: model.train_step(b[0], b[1], b[2])                                               # noqa: E731
         loss_of = lambda cache, b: model.compute_loss(b[0], b[1], b[2])                                   # noqa: E731
