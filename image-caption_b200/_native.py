@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libicap.so")
 
 F32, BF16 = 0, 1
 EPI_NONE, EPI_RELU, EPI_RELU_MASK = 0, 1, 2
+EPI_B_STATIC = 16      # flag: B / bias are weights the preceding kernel of the stream does not write
 
 P, I, L, F, U = c_void_p, c_int, c_int64, c_float, c_uint64
 
@@ -20,21 +21,24 @@ SIGNATURES = {
     "icap_sm_check": [I],
     "icap_set_pdl": [I],
     "icap_gemm": [I, I, I, L, L, L, P, L, P, L, P, L, I, P, I, P, L, I, I, P],
+    "icap_reload_env": [],
+    "icap_debug_trace": [P, I],
     "icap_mha_fwd": [I, L, L, L, L, L, L, P, L, P, L, P, L, P, L, P, I, F, U, P, P, P],
     "icap_mha_bwd": [I, L, L, L, L, L, L, P, L, P, L, P, L, P, L, P, L, P, L, P, L, P, I, F, U, P, P],
     "icap_add_ln_fwd": [I, I, L, L, P, P, L, P, P, P, P, P, P, I, F, U, P, F, P],
     "icap_add_ln_bwd": [I, L, L, P, P, P, P, P, P, P, P, P, P, P, P, F, U, P, P],
     "icap_add_ln_bwd_rows": [I, L, L, P, P, P, P, P, P, P, P, P, F, U, P, P],
     "icap_add_ln_bwd_params": [I, L, L, P, P, P, P, P, P, P, P, P, P, P, P],
-    "icap_linear_res_ln": [L, L, L, P, L, P, L, P, P, L, P, P, P, P, L, F, P],
     "icap_gemm_ln": [L, L, L, P, L, P, L, P, P, L, P, P, P, P, L, P, L, P, P, F, F, U, P, P],
     "icap_xent": [I, L, L, P, L, P, I, P, P, I, P],
     "icap_xent_finalize": [L, P, P, I, P, P],
     "icap_argmax": [I, L, L, P, L, P, L, P, P],
     "icap_beam_select": [I, L, L, L, P, L, P, L, P, P, P, P, I, P],
     "icap_beam_reorder": [L, L, L, L, P, P, P, P, P, P, P],
+    "icap_log_softmax_argmax": [L, L, P, L, P, L, P, P],
+    "icap_log_softmax_bwd": [L, L, P, L, P, L, P, L, P],
     "icap_mha_decode": [I, L, L, L, L, L, P, L, P, L, P, L, L, P, L, P, L, P, L, I, P, L, P, P],
-    "icap_mha_decode_self": [I, L, L, L, L, L, P, L, P, P, L, P, L, P, L, L, P, L, P, L, P, L, I, P],
+    "icap_mha_decode_self": [I, L, L, L, L, L, P, L, P, P, L, P, L, P, L, L, P, L, P, L, P, L, I, L, P],
     "icap_copy2d": [P, I, L, P, I, L, L, L, I, P],
     "icap_rows_gather_add": [I, P, L, P, L, P, L, L, L, L, L, L, P],
     "icap_rows_segsum_add": [I, P, L, P, L, L, L, L, L, L, P],

@@ -12,7 +12,10 @@ PAD_IDX = 0
 MAX_OBJ = 5
 
 IMAGE_MODEL = 'YOLOv5'
-CAPTION_MODEL = 'Transformer'          # the RL fine-tuning mode (SelfCriticNetwork) is out of scope, SURVEY.md §2 #5
+# 'Transformer' (teacher-forced CE) or 'RL_Transformer' (SelfCriticNetwork: PolicyNetwork + self-critical loss, the
+# reference's shipped default, config.py:14).  The default here is the north_star's Transformer path.
+CAPTION_MODEL = os.environ.get("ICAP_CAPTION_MODEL", 'Transformer')
+assert CAPTION_MODEL in ('Transformer', 'RL_Transformer')
 
 MODEL_NAME = 'maxlen49_36obj_1wordCount'
 OUTPUT_NAME = os.environ.get("ICAP_OUTPUT_NAME", 'maxlen49_36obj_1wordCount_256_25b_32h_split_img_obj')
@@ -22,8 +25,9 @@ OUTPUT_PATH = f'./output/{OUTPUT_NAME}'
 WORD_TO_IDX_PATH = f'{DATA_PATH}/train/word_index.pkl'
 SYNTHETIC_VOCAB = int(os.environ.get("ICAP_SYNTHETIC_VOCAB", 10000))   # used when word_index.pkl is absent
 
-# the reference pins cuda:2 (config.py:35); one process drives one GPU here
-DEVICE = torch.device(os.environ.get("ICAP_DEVICE", "cuda:0") if torch.cuda.is_available() else "cpu")
+# the reference pins cuda:2 (config.py:35); one process drives one GPU here.  There is no CPU execution path: without a
+# GPU the device is still "cuda:0" and the first kernel launch fails loudly.
+DEVICE = torch.device(os.environ.get("ICAP_DEVICE", "cuda:0"))
 
 # encoder (config.py:51-56)
 ENCODE_DIM_FEATURES = 2048
@@ -37,6 +41,13 @@ LEARNING_RATE = 0.0005
 REGION_CACHE = os.environ.get("ICAP_REGION_CACHE", "1") != "0"    # keep each split's region features packed in HBM
 LOG_PATH = f'./logs_{OUTPUT_NAME}/'
 WRITE_LOG = ['loss']
+if CAPTION_MODEL.find('RL') != -1:                 # config.py:65-68,81-85
+    WRITE_LOG = ['loss', 'language_model_loss', 'structure_loss', 'reward']
+    STRUCTURE_LOSS_WEIGHT = 0.5
+    CIDER_REWARD_WEIGHT = 1
+    BLEU_REWARD_WEIGHT = 1
+    ENTROPY_REWARD_WEIGHT = 1
+    SELF_CIDER_REWARD_WEIGHT = 1
 
 if OUTPUT_NAME == 'maxlen49_36obj_1wordCount_256_25b_32h_split_img_obj':      # config.py:105-129
     MOVE_FIRST_IMAGE_FAETURE = False

@@ -8,6 +8,8 @@ import torch
 import torch.nn as nn
 
 from core.TRANSFORMER.model import Transformer
+from core.TRANSFORMER.model_RL import PolicyNetwork
+from core.TRANSFORMER.loss import ReinforcementLearningLoss
 from core.config import *          # noqa: F401,F403  (the reference does the same, models.py:12)
 from core.utils import decode_captions
 
@@ -133,3 +135,65 @@ class TRANSFORMER(MODEL_init):
         assert isinstance(beam_size, int) and beam_size > 1
         caption_vector = self.model.beam_search(batch, None, beam_size=beam_size)
         return self.decode_captions(caption_vector.cpu().numpy()), None
+
+
+class SelfCriticNetwork(MODEL_init):
+    """core/models.py:138-211: PolicyNetwork (logits out) + ReinforcementLearningLoss, torch.optim.Adam on the flat
+    parameter views.  `reward_fn(target_ids, sample_ids) -> [B]` replaces the pycocoevalcap scorers (un-vendored CPU
+    string metrics); forward, the log-softmax/arg-max "sampler" and the whole backward run on libicap."""
+
+    def __init__(self, reward_fn=None):
+        super(SelfCriticNetwork, self).__init__()
+        self.model = PolicyNetwork(num_vocab=self.num_vocab,
+                                   max_length=MAX_LENGTH + 2,
+                                   encode_dim_positions=ENCODE_DIM_POSITIONS,
+                                   encode_dim_features=ENCODE_DIM_FEATURES,
+                                   encode_input_size=ENCODE_INPUT_SIZE,
+                                   encode_q_k_dim=ENCODE_Q_K_DIM,
+                                   encode_v_dim=ENCODE_V_DIM,
+                                   encode_hidden_size=ENCODE_HIDDEN_SIZE,
+                                   encode_num_blocks=ENCODE_NUM_BLOCKS,
+                                   encode_num_heads=ENCODE_NUM_HEADS,
+                                   dim_word_embedding=DIM_WORD_EMBEDDING,
+                                   decode_input_size=DECODE_INPUT_SIZE,
+                                   decode_q_k_dim=DECODE_Q_K_DIM,
+                                   decode_v_dim=DECODE_V_DIM,
+                                   decode_hidden_size=DECODE_HIDDEN_SIZE,
+                                   decode_num_blocks=DECODE_NUM_BLOCKS,
+                                   decode_num_heads=DECODE_NUM_HEADS,
+                                   dropout=DROPOUT,
+                                   device=DEVICE,
+                                   move_first_image_feature=MOVE_FIRST_IMAGE_FAETURE,
+                                   split_position=SPLIT_POSITION,
+                                   split_image_objects=SPLIT_IMAGE_OBJECTS,
+                                   encode_mask=ENCODE_MASK,
+                                   pad_idx=PAD_IDX).to(DEVICE)
+        g = globals()
+        self.loss = ReinforcementLearningLoss(word_to_idx_path=WORD_TO_IDX_PATH,
+                                              pad_idx=PAD_IDX,
+                                              structure_loss_weight=g.get('STRUCTURE_LOSS_WEIGHT', 0.5),
+                                              cider_reward_weight=g.get('CIDER_REWARD_WEIGHT', 1),
+                                              bleu_reward_weight=g.get('BLEU_REWARD_WEIGHT', 1),
+                                              entropy_reward_weight=g.get('ENTROPY_REWARD_WEIGHT', 1),
+                                              self_cider_reward_weight=g.get('SELF_CIDER_REWARD_WEIGHT', 1),
+                                              reward_fn=reward_fn)
+        self.optimizer = torch.optim.Adam((p for p in self.model.parameters() if p.requires_grad), lr=LEARNING_RATE)
+        self.last_loss = None
+
+    def _loss(self, features, positions, captions):
+        model_output = self.model(object_features=features.to(DEVICE), position_features=positions.to(DEVICE),
+                                  target_caption=captions.to(DEVICE))
+        sample_sequence, sample_logprobs = self.model.sample(output=model_output)
+        return self.loss(model_output=model_output, sample_sequence=sample_sequence, sample_logprobs=sample_logprobs,
+                         target=captions)
+
+    def train_step(self, batch_features, batch_positions, batch_captions):
+        self.optimizer.zero_grad()
+        loss = self._loss(batch_features, batch_positions, batch_captions)['loss'].mean()
+        loss.backward()
+        self.optimizer.step()
+        self.last_loss = loss.detach()
+
+    def compute_loss(self, object_features, position_features, target_caption):
+        with torch.no_grad():
+            return self._loss(object_features, position_features, target_caption)

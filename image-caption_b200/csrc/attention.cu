@@ -19,7 +19,7 @@ bool icap_mha_mma_ok(int dtype, int64_t Lq, int64_t Lk, int64_t dk, int64_t dv, 
                      const void* q, const void* k, const void* v);
 int icap_mha_fwd_mma(int64_t B, int64_t H, int64_t Lq, int64_t Lk, const void* q, int64_t ldq, const void* k,
                      int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo, const uint8_t* kvalid, int causal,
-                     float p_drop, uint64_t seed, const int* seed_dev, cudaStream_t st);
+                     float p_drop, uint64_t seed, const int* seed_dev, cudaStream_t st, int kv_static = 0);
 int icap_mha_bwd_mma(int64_t B, int64_t H, int64_t Lq, int64_t Lk, const void* q, int64_t ldq, const void* k,
                      int64_t ldk, const void* v, int64_t ldv, const void* dout, int64_t lddo, void* dq, int64_t lddq,
                      void* dk_out, int64_t lddk, void* dv_out, int64_t lddv, const uint8_t* kvalid, int causal,
@@ -635,18 +635,33 @@ __device__ __forceinline__ void raw_pack_store(float* p, const float (&v)[EPL]) 
 
 
 template <typename T, int EPL, int ROW_UB>      // ROW_UB: cached positions fetched per batch (loads in flight per lane)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(320, 2)
 mha_decode_row_kernel(int rows, int wpr, int Lk, const T* __restrict__ q, int64_t ldq, T* __restrict__ kc, int64_t ldk,
                       T* __restrict__ vc, int64_t ldv, int kv_rows_per_seq, T* __restrict__ o, int64_t ldo,
                       const int* __restrict__ slot, int64_t slot_ld, const int* __restrict__ tokens, int64_t tok_ld,
                       int pad_idx, const T* __restrict__ knew, const T* __restrict__ vnew, int64_t ldn, int pos_new) {
-  pdl_prologue();
   constexpr int LPH = 64 / EPL;                       // lanes per head
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int row = gw / wpr, part = gw % wpr;          // part: which 32*EPL-wide slice of the row this warp owns
-  if (row >= rows) return;
+  const bool live = row < rows;
   const int col = (part * 32 + lane) * EPL;           // first element of this lane within a K / V / q / o row
+  // lane l: physical cache row of position l, or -1 (position masked / beyond Lk).  The token buffer, the slot table and
+  // the cached positions 0..pos_new-1 were written by EARLIER decode steps (not by the kernel that produces q): they are
+  // read -- and the cache lines are pulled into L2 -- BEFORE the grid dependency resolves, i.e. while the QKV projection
+  // of this step is still running on the tensor cores (its HBM traffic is small, this kernel's is all there is).
+  int myrow = -1;
+  if (live && lane < Lk && tokens[(int64_t)row * tok_ld + lane] != pad_idx)
+    myrow = (slot ? slot[(int64_t)row * slot_ld + lane] : row) * kv_rows_per_seq + lane;
+  for (int j = 0; j < Lk; ++j) {
+    const int r = __shfl_sync(0xffffffffu, myrow, j);
+    if (r >= 0 && j != pos_new) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(kc + (int64_t)r * ldk + col));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(vc + (int64_t)r * ldv + col));
+    }
+  }
+  pdl_prologue();
+  if (!live) return;
   float qv[EPL];
   {
     RawVec<T, EPL> r;
@@ -666,10 +681,6 @@ mha_decode_row_kernel(int rows, int wpr, int Lk, const T* __restrict__ q, int64_
       reinterpret_cast<uint4*>(vc + crow * ldv + col)[i] = vnew_r.w[i];
     }
   }
-  // lane l: physical cache row of position l, or -1 (position masked / beyond Lk)
-  int myrow = -1;
-  if (lane < Lk && tokens[(int64_t)row * tok_ld + lane] != pad_idx)
-    myrow = (slot ? slot[(int64_t)row * slot_ld + lane] : row) * kv_rows_per_seq + lane;
   // ---- one pass over the cached positions, ROW_UB at a time: K and V of a batch are fetched together (2 * ROW_UB
   // independent loads in flight per lane), scores go through an online softmax (running max m / sum l, rescaled
   // accumulator), so there is a single memory round trip per batch instead of one for Q.K^T and one for P.V
@@ -736,6 +747,188 @@ mha_decode_row_kernel(int rows, int wpr, int Lk, const T* __restrict__ q, int64_
     for (int e = 0; e < EPL; ++e) acc[e] *= inv;
   }
   raw_pack_store<EPL>(o + (int64_t)row * ldo + col, acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cross-attention of a decode step, ONE CTA PER IMAGE (bf16, head dim 64, K | V rows contiguous as the packed
+// projection [B*R, dk_tot + dv_tot] leaves them): the G beam rows of an image attend the image's Lk region keys.
+//   * the image's K|V block is ONE contiguous range of global memory: a single `cp.async.bulk` (TMA, 1-D) per chunk of
+//     rows brings it into shared memory -- 72 KB in flight per CTA, two or three CTAs per SM, instead of 4096 tiny
+//     (image, head) blocks with a few dependent 16-byte loads each (r2 timeline: 24 us per launch, 14 us exposed);
+//   * only rows up to the last valid region are fetched (padded regions are a suffix in the reference's data);
+//   * K/V of the regions are produced once per decode, long before this launch, so the first chunk is requested BEFORE
+//     `griddepcontrol.wait`: it streams in while the kernel that produces q is still running;
+//   * warp h owns head h: lane = (key slot 0..3, 16-byte chunk 0..7); every key slot keeps its own online-softmax state
+//     (m, l, acc) over the keys j = slot (mod 4); the four states are merged once at the end (flash-decoding merge).
+// Replaces ScaledDotProductAttention for the decoder->region attention inside the decode loops (modules.py:16-27,196-200).
+constexpr int XI_MAXK = 128;            // keys per image
+constexpr int XI_SMEM_MAX = 96 * 1024;  // K|V rows staged per chunk
+
+__device__ __forceinline__ void xi_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+
+template <int G>
+__global__ void __launch_bounds__(512)
+mha_cross_img_kernel(int H, int Lk, const bf16* __restrict__ q, int64_t ldq, const bf16* __restrict__ kv, int64_t ldkv,
+                     int dk_tot, bf16* __restrict__ o, int64_t ldo, const uint8_t* __restrict__ kvalid, int chunk_rows) {
+  extern __shared__ __align__(128) uint8_t xi_smem[];
+  __shared__ __align__(8) unsigned long long xi_bar;
+  __shared__ uint8_t s_valid[XI_MAXK];
+  __shared__ int s_nlast;
+  const int img = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&xi_bar);
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(xi_smem);
+  const int row_bytes = (int)ldkv * 2;
+  // kvalid is written once per decode (encoder prologue), like K/V: safe to read before the grid dependency resolves
+  if (threadIdx.x < XI_MAXK) s_valid[threadIdx.x] = (threadIdx.x < Lk && (!kvalid || kvalid[(int64_t)img * Lk + threadIdx.x])) ? 1 : 0;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 0) {
+    int last = 0;
+    for (int j = lane; j < Lk; j += 32) if (s_valid[j]) last = j + 1;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, off));
+    if (lane == 0) {
+      s_nlast = last;
+      const int rows0 = min(last, chunk_rows);
+      if (rows0 > 0) {
+        const uint32_t bytes = (uint32_t)(rows0 * row_bytes);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(sbase), "l"(kv + (int64_t)img * Lk * ldkv), "r"(bytes), "r"(bar) : "memory");
+      }
+    }
+  }
+  pdl_prologue();                       // q (and the buffer o is recycled from) depends on the preceding kernels
+  __syncthreads();
+  const int nlast = s_nlast;
+  const int sub = lane >> 3, ch = lane & 7;
+  float qv[G][8], acc[G][8], m_run[G], l_run[G];
+  if (warp < H) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const uint4 t = __ldg(reinterpret_cast<const uint4*>(q + (int64_t)(img * G + g) * ldq + warp * 64 + ch * 8));
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        qv[g][2 * i] = __low2float(h2[i]) * 0.125f;           // 1 / sqrt(64) on q, as modules.py:18
+        qv[g][2 * i + 1] = __high2float(h2[i]) * 0.125f;
+      }
+      m_run[g] = -INFINITY; l_run[g] = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[g][e] = 0.f;
+    }
+  }
+  int chunk = 0;
+  for (int j0 = 0; j0 < nlast; j0 += chunk_rows, ++chunk) {
+    const int cr = min(chunk_rows, nlast - j0);
+    if (chunk > 0) {
+      __syncthreads();                  // every warp is done with the previous chunk
+      if (threadIdx.x == 0) {
+        const uint32_t bytes = (uint32_t)(cr * row_bytes);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(sbase), "l"(kv + ((int64_t)img * Lk + j0) * ldkv), "r"(bytes), "r"(bar) : "memory");
+      }
+    }
+    xi_mbar_wait(bar, (uint32_t)(chunk & 1));
+    if (warp < H) {
+      for (int i = 0; i < cr; i += 4) {
+        const int jl = i + sub, j = j0 + jl;
+        const bool valid = jl < cr && s_valid[j];
+        // every lane runs the same instruction stream (full-mask shuffles): an idle key slot multiplies zeros and
+        // leaves its state alone
+        uint4 kr = make_uint4(0u, 0u, 0u, 0u), vr = make_uint4(0u, 0u, 0u, 0u);
+        if (valid) {
+          const uint32_t ka = sbase + (uint32_t)(jl * row_bytes + (warp * 64 + ch * 8) * 2);
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(kr.x), "=r"(kr.y), "=r"(kr.z), "=r"(kr.w) : "r"(ka));
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(vr.x), "=r"(vr.y), "=r"(vr.z), "=r"(vr.w)
+                       : "r"(ka + (uint32_t)dk_tot * 2u));
+        }
+        float kf[8], vf[8];
+        const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kr);
+        const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vr);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          kf[2 * t] = __low2float(k2[t]); kf[2 * t + 1] = __high2float(k2[t]);
+          vf[2 * t] = __low2float(v2[t]); vf[2 * t + 1] = __high2float(v2[t]);
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          float sc = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) sc = fmaf(qv[g][e], kf[e], sc);
+          sc += __shfl_xor_sync(0xffffffffu, sc, 1);          // over the 8 lanes of this key slot
+          sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+          sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+          if (valid) {
+            const float m_new = fmaxf(m_run[g], sc);
+            const float scale = __expf(m_run[g] - m_new), pj = __expf(sc - m_new);     // exp(-inf) = 0 on the first key
+            l_run[g] = l_run[g] * scale + pj;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[g][e] = fmaf(pj, vf[e], acc[g][e] * scale);
+            m_run[g] = m_new;
+          }
+        }
+      }
+    }
+  }
+  if (warp < H) {
+    // merge the four key-slot states (lanes l, l^8, l^16, l^24 hold the same dims of the same head)
+    __syncwarp();
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+#pragma unroll
+      for (int off = 8; off <= 16; off <<= 1) {
+        const float mo = __shfl_xor_sync(0xffffffffu, m_run[g], off), lo = __shfl_xor_sync(0xffffffffu, l_run[g], off);
+        const float m_new = fmaxf(m_run[g], mo);
+        const float sa = (m_run[g] == -INFINITY) ? 0.f : __expf(m_run[g] - m_new);
+        const float sb = (mo == -INFINITY) ? 0.f : __expf(mo - m_new);
+        l_run[g] = l_run[g] * sa + lo * sb;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float ao = __shfl_xor_sync(0xffffffffu, acc[g][e], off);
+          acc[g][e] = acc[g][e] * sa + ao * sb;
+        }
+        m_run[g] = m_new;
+      }
+      if (sub == 0) {
+        const float inv = 1.f / l_run[g];             // all keys masked -> inf/NaN exactly like the reference's softmax
+        float ov[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ov[e] = acc[g][e] * inv;
+        st8(o + (int64_t)(img * G + g) * ldo + warp * 64 + ch * 8, ov);
+      }
+    }
+  }
+}
+
+template <int G>
+int launch_cross_img(int64_t images, int64_t H, int64_t Lk, const void* q, int64_t ldq, const void* kv, int64_t ldkv,
+                     int64_t dk_tot, void* o, int64_t ldo, const uint8_t* kvalid, cudaStream_t st) {
+  const int row_bytes = (int)ldkv * 2;
+  int chunk_rows = XI_SMEM_MAX / row_bytes;
+  if (chunk_rows > Lk) chunk_rows = (int)Lk;
+  const size_t smem = (size_t)chunk_rows * row_bytes;
+  static size_t cur = 48 * 1024;
+  if (int rc = ensure_smem(mha_cross_img_kernel<G>, smem, &cur)) return rc;
+  icap_launch(mha_cross_img_kernel<G>, (unsigned)images, (unsigned)(32 * H), smem, st, (int)H, (int)Lk, (const bf16*)q, ldq,
+              (const bf16*)kv, ldkv, (int)dk_tot, (bf16*)o, ldo, kvalid, chunk_rows);
+  ICAP_LAUNCH_CHECK("icap_mha_decode(cross, image per CTA)");
+  return 0;
 }
 
 template <typename T, int G>
@@ -844,14 +1037,31 @@ extern "C" int icap_mha_decode(int dtype, int64_t rows, int64_t H, int64_t Lk, i
   const bool al = ((uintptr_t)q % 16 == 0) && ((uintptr_t)kc % 16 == 0) && ((uintptr_t)vc % 16 == 0) &&
                   ((uintptr_t)o % 16 == 0) && (ldq * esz) % 16 == 0 && (ldk * esz) % 16 == 0 && (ldv * esz) % 16 == 0 &&
                   (ldo * esz) % 16 == 0;
+  // cross-attention, K | V rows contiguous (the packed projection), head dim 64: one CTA per image, TMA bulk staging
+  if (tokens == nullptr && attn_mean == nullptr && dtype == ICAP_BF16 && dk == 64 && dv == 64 && al && H <= 16 &&
+      Lk <= XI_MAXK && kv_rows_per_seq == Lk && rows % rows_per_image == 0 && ldk == ldv &&
+      (const bf16*)vc == (const bf16*)kc + H * dk && ldk * 2 <= XI_SMEM_MAX && (ldk * 2) % 16 == 0 &&
+      (rows_per_image <= 5 || rows_per_image == 8) && env_flag<7>("ICAP_DECODE_IMG_CROSS")) {
+    const int64_t images = rows / rows_per_image;
+#define XIMG(GG) return launch_cross_img<GG>(images, H, Lk, q, ldq, kc, ldk, H * dk, o, ldo, kvalid, st)
+    switch (rows_per_image) {
+      case 1: XIMG(1);
+      case 2: XIMG(2);
+      case 3: XIMG(3);
+      case 4: XIMG(4);
+      case 5: XIMG(5);
+      default: XIMG(8);
+    }
+#undef XIMG
+  }
   // cross-attention of a beam group = a tiny full attention (Lq = beams, Lk = regions, shared K/V): tensor-core
   // kernel (mma.sync), ~5x fewer instructions than the SIMT path for 5 beams x 36 regions x 64 dims
   if (tokens == nullptr && attn_mean == nullptr && rows_per_image >= 2 && rows % rows_per_image == 0 &&
       kv_rows_per_seq == Lk && ldo % 8 == 0 && (uintptr_t)o % 16 == 0 &&
-      icap_mha_mma_ok(dtype, rows_per_image, Lk, dk, dv, ldq, ldk, ldv, q, kc, vc) && !getenv("ICAP_DECODE_NO_MMA"))
+      icap_mha_mma_ok(dtype, rows_per_image, Lk, dk, dv, ldq, ldk, ldv, q, kc, vc) && !env_flag<0>("ICAP_DECODE_NO_MMA"))
     return icap_mha_fwd_mma(rows / rows_per_image, H, rows_per_image, Lk, q, ldq, kc, ldk, vc, ldv, o, ldo, kvalid, 0, 0.f,
-                            0, nullptr, st);
-  if (dk == 64 && dv == 64 && al && !getenv("ICAP_DECODE_SLOW")) {
+                            0, nullptr, st, /*kv_static=*/1);
+  if (dk == 64 && dv == 64 && al && !env_flag<1>("ICAP_DECODE_SLOW")) {
     // group size: beams of one image share K/V in cross-attention; self-attention rows are independent
     int64_t G = tokens ? 1 : rows_per_image;
     if (G > 8 || rows % G != 0 || (G > 5 && G != 8)) G = 1;
@@ -898,7 +1108,7 @@ extern "C" int icap_mha_decode_self(int dtype, int64_t rows, int64_t H, int64_t 
                                     int64_t ldq, const void* k_new, const void* v_new, int64_t ld_new, void* kc,
                                     int64_t ldk, void* vc, int64_t ldv, int64_t kv_rows_per_seq, void* o, int64_t ldo,
                                     const int* slot, int64_t slot_ld, const int* tokens, int64_t tok_ld, int pad_idx,
-                                    void* stream) {
+                                    int64_t rows_per_image, void* stream) {
   if (int rc = check_dims("icap_mha_decode_self", rows, H, 1, pos + 1, dk, dv)) return rc;
   ICAP_ARG(pos >= 0 && pos < kv_rows_per_seq && pos + 1 <= 128, "icap_mha_decode_self: position %lld out of range", (long long)pos);
   ICAP_ARG(tokens && k_new && v_new && kc && vc, "icap_mha_decode_self: null argument");
@@ -908,16 +1118,24 @@ extern "C" int icap_mha_decode_self(int dtype, int64_t rows, int64_t H, int64_t 
                   ((uintptr_t)o % 16 == 0) && ((uintptr_t)k_new % 16 == 0) && ((uintptr_t)v_new % 16 == 0) &&
                   (ldq * esz) % 16 == 0 && (ldk * esz) % 16 == 0 && (ldv * esz) % 16 == 0 && (ldo * esz) % 16 == 0 &&
                   (ld_new * esz) % 16 == 0;
-  if (dk == 64 && dv == 64 && al && pos + 1 <= 32 && (H * 64) % 256 == 0 && !getenv("ICAP_DECODE_SLOW") &&
-      !getenv("ICAP_DECODE_NO_ROW")) {
+  if (dk == 64 && dv == 64 && al && pos + 1 <= 32 && (H * 64) % 256 == 0 && !env_flag<1>("ICAP_DECODE_SLOW") &&
+      !env_flag<2>("ICAP_DECODE_NO_ROW")) {
     // row-per-warp kernel: EPL elements per lane, wpr warps per row
-    static const int ub_env = getenv("ICAP_DECODE_UB") ? atoi(getenv("ICAP_DECODE_UB")) : 4;
+    static IcapEnv e_ub;
+    const int ub_env = e_ub.geti("ICAP_DECODE_UB", 4);
     const int width = (int)(H * 64);
     constexpr int epl = 8;
     const int wpr = width / (32 * epl);
-    const unsigned grid = (unsigned)ceil_div64(rows * wpr, 8);
+    // Block = the rows of whole images (beams of an image share most of their prefix through the slot table: the same
+    // physical cache lines are then fetched by warps of ONE block at about the same time and hit in L1); 8 warps
+    // otherwise.  The kernel derives (row, part) from the global warp number, so any block size works.
+    int wpb = 8;
+    if (rows_per_image > 1 && rows % rows_per_image == 0 && rows_per_image * wpr <= 10 && !env_flag<5>("ICAP_DECODE_NO_IMG_BLOCKS"))
+      wpb = (int)rows_per_image * wpr;
+    const unsigned grid = (unsigned)ceil_div64(rows * wpr, wpb);
+    const unsigned nthr = (unsigned)(32 * wpb);
 #define ROWK(T, U)                                                                                                   \
-  icap_launch(mha_decode_row_kernel<T, 8, U>, grid, 256, 0, st, (int)rows, wpr, (int)(pos + 1), (const T*)q, ldq,    \
+  icap_launch(mha_decode_row_kernel<T, 8, U>, grid, nthr, 0, st, (int)rows, wpr, (int)(pos + 1), (const T*)q, ldq,   \
               (T*)kc, ldk, (T*)vc, ldv, (int)kv_rows_per_seq, (T*)o, ldo, slot, slot_ld, tokens, tok_ld, pad_idx,    \
               (const T*)k_new, (const T*)v_new, ld_new, (int)pos)
     if (dtype == ICAP_F32) { if (ub_env == 8) ROWK(float, 8); else ROWK(float, 4); }
@@ -926,7 +1144,7 @@ extern "C" int icap_mha_decode_self(int dtype, int64_t rows, int64_t H, int64_t 
     ICAP_LAUNCH_CHECK("icap_mha_decode_self(row)");
     return 0;
   }
-  if (dk == 64 && dv == 64 && al && !getenv("ICAP_DECODE_SLOW")) {
+  if (dk == 64 && dv == 64 && al && !env_flag<1>("ICAP_DECODE_SLOW")) {
     if (dtype == ICAP_F32)
       return launch_decode64<float, 1>(rows, H, pos + 1, q, ldq, kc, ldk, vc, ldv, kv_rows_per_seq, o, ldo, slot, slot_ld,
                                        tokens, tok_ld, pad_idx, nullptr, nullptr, st, k_new, v_new, ld_new, (int)pos);

@@ -208,18 +208,26 @@ __global__ void __launch_bounds__(256)
 mha_fwd_mma_kernel(const bf16* __restrict__ q, int64_t ldq, const bf16* __restrict__ k, int64_t ldk,
                    const bf16* __restrict__ v, int64_t ldv, bf16* __restrict__ o, int64_t ldo,
                    const uint8_t* __restrict__ kvalid, int H, int Lq, int Lk, int causal, float p_drop, uint32_t thresh,
-                   uint64_t seed, const int* __restrict__ seed_dev) {
-  pdl_prologue();
+                   uint64_t seed, const int* __restrict__ seed_dev, int kv_static) {
   extern __shared__ __align__(128) uint8_t smem[];
-  if (seed_dev) seed += (uint64_t)(*seed_dev) * 0x9E3779B97F4A7C15ull;
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nthreads = blockDim.x;
   const int LqP = (Lq + 15) & ~15;
   constexpr int LkP = NT8 * 8;
   const uint32_t sQ = smem_u32(smem), sK = sQ + LqP * ROWB, sV = sK + LkP * ROWB;
+  // kv_static (decode cross-attention): K / V / kvalid were produced once per decode, long before this launch -- their
+  // tiles are requested BEFORE the grid dependency resolves and stream in while the kernel that produces q still runs
+  if (kv_static) {
+    load_tile(sK, k + (int64_t)b * Lk * ldk + h * D, ldk, Lk, LkP, nthreads);
+    load_tile(sV, v + (int64_t)b * Lk * ldv + h * D, ldv, Lk, LkP, nthreads);
+  }
+  pdl_prologue();
+  if (seed_dev) seed += (uint64_t)(*seed_dev) * 0x9E3779B97F4A7C15ull;
   load_tile(sQ, q + (int64_t)b * Lq * ldq + h * D, ldq, Lq, LqP, nthreads);
-  load_tile(sK, k + (int64_t)b * Lk * ldk + h * D, ldk, Lk, LkP, nthreads);
-  load_tile(sV, v + (int64_t)b * Lk * ldv + h * D, ldv, Lk, LkP, nthreads);
+  if (!kv_static) {
+    load_tile(sK, k + (int64_t)b * Lk * ldk + h * D, ldk, Lk, LkP, nthreads);
+    load_tile(sV, v + (int64_t)b * Lk * ldv + h * D, ldv, Lk, LkP, nthreads);
+  }
   load_tiles_wait();
   __syncthreads();
   const int m0 = warp * 16;
@@ -354,7 +362,7 @@ int ensure_smem(K kern, size_t smem, size_t* cur) {
 
 bool icap_mha_mma_ok(int dtype, int64_t Lq, int64_t Lk, int64_t dk, int64_t dv, int64_t ldq, int64_t ldk, int64_t ldv,
                      const void* q, const void* k, const void* v) {
-  if (getenv("ICAP_MHA_SIMT")) return false;
+  if (env_flag<3>("ICAP_MHA_SIMT")) return false;
   return dtype == ICAP_BF16 && dk == D && dv == D && Lq <= 128 && Lk <= 128 && ldq % 8 == 0 && ldk % 8 == 0 &&
          ldv % 8 == 0 && (uintptr_t)q % 16 == 0 && (uintptr_t)k % 16 == 0 && (uintptr_t)v % 16 == 0;
 }
@@ -370,7 +378,7 @@ bool icap_mha_mma_ok(int dtype, int64_t Lq, int64_t Lk, int64_t dk, int64_t dv, 
 
 int icap_mha_fwd_mma(int64_t B, int64_t H, int64_t Lq, int64_t Lk, const void* q, int64_t ldq, const void* k,
                      int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo, const uint8_t* kvalid, int causal,
-                     float p_drop, uint64_t seed, const int* seed_dev, cudaStream_t st) {
+                     float p_drop, uint64_t seed, const int* seed_dev, cudaStream_t st, int kv_static) {
   const int LqP = (int)((Lq + 15) & ~15);
   const int nthreads = 32 * (LqP / 16);
   const uint32_t th = dropout_threshold(p_drop);
@@ -381,7 +389,7 @@ int icap_mha_fwd_mma(int64_t B, int64_t H, int64_t Lq, int64_t Lk, const void* q
     if (int rc = ensure_smem(mha_fwd_mma_kernel<NT>, smem, &cur)) return rc;                                       \
     icap_launch(mha_fwd_mma_kernel<NT>, (unsigned)(B * H), nthreads, smem, st,                                              \
         (const bf16*)q, ldq, (const bf16*)k, ldk, (const bf16*)v, ldv, (bf16*)o, ldo, kvalid, (int)H, (int)Lq,     \
-        (int)Lk, causal, p_drop, th, seed, seed_dev);                                                              \
+        (int)Lk, causal, p_drop, th, seed, seed_dev, kv_static);                                                   \
   }
   DISPATCH_NT8(Lk, CALL);
 #undef CALL

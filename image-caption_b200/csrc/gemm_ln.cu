@@ -333,6 +333,280 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Small-footprint variant for the latency-bound decode steps (no dropout, no saved sum / statistics): same cluster
+// scheme (CL CTAs x 128 columns per 128-row block, statistics through DSMEM), but built like gemm_small.cu so that
+// TWO CTAs fit an SM and consecutive launches of a stream overlap: 192 threads (warp 0 TMA, warp 1 MMA, warps 2-5
+// epilogue), 3-stage 32 KB ring, 128 TMEM columns, `griddepcontrol.launch_dependents` right after the prologue and the
+// first W stages fetched BEFORE `griddepcontrol.wait` (W, bias, gamma, beta are model parameters).  The epilogue makes
+// TWO passes over the accumulator, which simply stays in TMEM: pass 1 row statistics (Chan-combined per 32-column
+// chunk), pass 2 normalise + store -- 80 registers instead of a 64-value row slice per thread.
+constexpr int S_STAGES = 3, S_BN = 128, S_THREADS = 192;
+constexpr int S_STAGE_BYTES = A_TILE_BYTES + S_BN * BK * 2;
+constexpr int S_STATS_BYTES = MAX_CL * BM * 8;
+constexpr int S_PAR_BYTES = 3 * S_BN * 4;
+constexpr int S_SMEM_BYTES = S_STAGES * S_STAGE_BYTES + S_STATS_BYTES + S_PAR_BYTES + 128 + 1024;
+
+template <int CL>
+__global__ void __launch_bounds__(S_THREADS, 2)
+gemm_ln_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmY, const LnArgs g) {
+  constexpr int BN = S_BN, STAGES = S_STAGES, B_TILE_BYTES = BN * BK * 2, STAGE_BYTES = S_STAGE_BYTES, BOX = 4096;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem_base, sB = sA + STAGES * A_TILE_BYTES;
+  const uint32_t sStats = sB + STAGES * B_TILE_BYTES, sPar = sStats + S_STATS_BYTES, bars = sPar + S_PAR_BYTES;
+  const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES, tfull_bar = bars + 16 * STAGES;
+  const uint32_t rfull_bar = tfull_bar + 8, slot_addr = rfull_bar + 8;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_raw + (slot_addr - smem_u32(smem_raw)));
+  const float2* const stats = reinterpret_cast<const float2*>(smem_raw + (sStats - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
+  const int n0 = (int)rank * BN, m0 = (int)blockIdx.y * BM;
+  const int nkb = (g.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
+    if (g.res) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmR) : "memory");
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(full_bar + 8 * i, 1);
+      mbar_init(empty_bar + 8 * i, 1);
+    }
+    mbar_init(tfull_bar, 1);
+    mbar_init(rfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_addr), "n"(BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  if constexpr (CL > 1) cluster_arrive();          // phase 1: "this CTA is running" (waited for before the first DSMEM store)
+  pdl_launch_dependents();
+
+  // residual: ring "k-blocks" nkb, nkb+1 (B parts); box b = jb * 4 + q (jb: 64-column box, q: 32-row quarter)
+  auto res_box = [&](int b) { return sB + (uint32_t)(((nkb + b / 4) % STAGES) * B_TILE_BYTES + (b % 4) * BOX); };
+  auto y_box = [&](int b) { return sA + (uint32_t)(b * BOX); };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ TMA producer
+      const int npre = nkb < STAGES ? nkb : STAGES;
+      for (int i = 0; i < npre; ++i) {                // weights first: they do not depend on the preceding kernel
+        mbar_expect_tx(full_bar + 8 * i, STAGE_BYTES);
+        tma_load_2d(sB + i * B_TILE_BYTES, &tmB, i * BK, n0, full_bar + 8 * i);
+      }
+      pdl_wait();
+      for (int i = 0; i < npre; ++i) tma_load_2d(sA + i * A_TILE_BYTES, &tmA, i * BK, m0, full_bar + 8 * i);
+      for (int i = npre; i < nkb; ++i) {
+        const int s = i % STAGES, r = i / STAGES;
+        mbar_wait(empty_bar + 8 * s, (uint32_t)((r & 1) ^ 1));
+        mbar_expect_tx(full_bar + 8 * s, STAGE_BYTES);
+        tma_load_2d(sA + s * A_TILE_BYTES, &tmA, i * BK, m0, full_bar + 8 * s);
+        tma_load_2d(sB + s * B_TILE_BYTES, &tmB, i * BK, n0, full_bar + 8 * s);
+      }
+      if (g.res) {
+        mbar_expect_tx(rfull_bar, BM * BN * 2);
+        for (int e = 0; e < 2; ++e) {
+          const int i = nkb + e, s = i % STAGES, r = i / STAGES;
+          mbar_wait(empty_bar + 8 * s, (uint32_t)((r & 1) ^ 1));
+          for (int bb = 0; bb < 4; ++bb)
+            tma_load_2d(res_box(e * 4 + bb), &tmR, n0 + e * 64, m0 + bb * 32, rfull_bar);     // box {64 cols, 32 rows}
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES, r = i / STAGES;
+        mbar_wait(full_bar + 8 * s, (uint32_t)(r & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t aS = sA + s * A_TILE_BYTES, bS = sB + s * B_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k)
+          umma_bf16(tmem_base, make_sdesc(aS + k * 32, 16, 1024), make_sdesc(bS + k * 32, 16, 1024), idesc,
+                    (i > 0 || k > 0) ? 1u : 0u);
+        umma_commit(empty_bar + 8 * s);
+      }
+      umma_commit(tfull_bar);
+    }
+    __syncwarp();
+  }
+
+  const int q = warp & 3, r_in = q * 32 + lane, row = m0 + r_in;
+  const uint32_t sw = (uint32_t)(lane & 7), my_row = (uint32_t)lane * 128u;
+  const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16);
+  // one 32-column chunk of s = acc + bias + residual for this thread's row
+  auto load_chunk = [&](int c, float (&v)[32]) {
+    uint32_t r[32];
+    tmem_ld32(tacc + (uint32_t)(32 * c), r);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (g.bias) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b = lds_f4(sPar + (uint32_t)(2 * BN + 32 * c + j) * 4);
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    }
+    if (g.res) {
+      const uint32_t box = res_box((c >> 1) * 4 + q) + my_row;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        uint4 rj;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rj.x), "=r"(rj.y), "=r"(rj.z), "=r"(rj.w)
+                     : "r"(box + ((((uint32_t)((c & 1) * 4 + t)) ^ sw) << 4)));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rj);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[t * 8 + 2 * i] += __low2float(h[i]); v[t * 8 + 2 * i + 1] += __high2float(h[i]); }
+      }
+    }
+  };
+
+  if (warp >= 2) {
+    // ---------------------------------------------------------------- epilogue pass 1: row statistics of this CTA's 128 columns
+    const int t128 = (int)threadIdx.x - 64;
+    {
+      float* const par = reinterpret_cast<float*>(smem_raw + (sPar - smem_u32(smem_raw)));
+      par[t128] = __ldg(g.gamma + n0 + t128);
+      par[BN + t128] = __ldg(g.beta + n0 + t128);
+      par[2 * BN + t128] = g.bias ? __ldg(g.bias + n0 + t128) : 0.f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    mbar_wait(tfull_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (g.res) mbar_wait(rfull_bar, 0);
+    float mean = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < BN / 32; ++c) {
+      float v[32];
+      load_chunk(c, v);
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sum += v[j];
+      const float cm = sum * (1.f / 32.f);
+      float cm2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { const float dlt = v[j] - cm; cm2 += dlt * dlt; }
+      // Chan: combine (32*c values, mean, m2) with (32 values, cm, cm2)
+      const float dlt = cm - mean, nn = (float)(32 * (c + 1));
+      mean += dlt * (32.f / nn);
+      m2 += cm2 + dlt * dlt * ((float)(32 * c) * 32.f / nn);
+    }
+    const uint32_t slot = sStats + (uint32_t)((int)rank * BM + r_in) * 8u;
+    if constexpr (CL > 1) {
+      cluster_wait();                                             // every CTA of the cluster has started
+#pragma unroll
+      for (int dst = 0; dst < CL; ++dst) st_cluster_f2(map_to_cta(slot, (uint32_t)dst), mean, m2);
+    } else {
+      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(slot), "f"(mean), "f"(m2) : "memory");
+    }
+  }
+  if constexpr (CL > 1) {
+    if (warp < 2) cluster_wait();
+    cluster_arrive();                                             // phase 2: all partial statistics are published
+    cluster_wait();
+  } else {
+    __syncthreads();
+  }
+  if (warp >= 2) {
+    // ---------------------------------------------------------------- epilogue pass 2: combine, normalise, store
+    float mp[CL], mean = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < CL; ++i) {
+      const float2 p = stats[i * BM + r_in];
+      mp[i] = p.x;
+      mean += p.x;
+      m2 += p.y;
+    }
+    mean *= 1.f / (float)CL;
+#pragma unroll
+    for (int i = 0; i < CL; ++i) { const float dlt = mp[i] - mean; m2 += (float)BN * dlt * dlt; }
+    const float rstd = rsqrtf(m2 / (float)(BN * CL) + g.eps);
+    const float rs = (row < g.M && g.rowscale) ? __ldg(g.rowscale + row) : 1.f;
+    const int row0 = m0 + q * 32;
+#pragma unroll
+    for (int c = 0; c < BN / 32; ++c) {
+      float v[32];
+      load_chunk(c, v);
+      const uint32_t box = y_box((c >> 1) * 4 + q);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float4 g0 = lds_f4(sPar + (uint32_t)(32 * c + 8 * t) * 4), g1 = lds_f4(sPar + (uint32_t)(32 * c + 8 * t + 4) * 4);
+        const float4 b0 = lds_f4(sPar + (uint32_t)(BN + 32 * c + 8 * t) * 4), b1 = lds_f4(sPar + (uint32_t)(BN + 32 * c + 8 * t + 4) * 4);
+        float o[8];
+        o[0] = ((v[8 * t + 0] - mean) * rstd * g0.x + b0.x) * rs;
+        o[1] = ((v[8 * t + 1] - mean) * rstd * g0.y + b0.y) * rs;
+        o[2] = ((v[8 * t + 2] - mean) * rstd * g0.z + b0.z) * rs;
+        o[3] = ((v[8 * t + 3] - mean) * rstd * g0.w + b0.w) * rs;
+        o[4] = ((v[8 * t + 4] - mean) * rstd * g1.x + b1.x) * rs;
+        o[5] = ((v[8 * t + 5] - mean) * rstd * g1.y + b1.y) * rs;
+        o[6] = ((v[8 * t + 6] - mean) * rstd * g1.z + b1.z) * rs;
+        o[7] = ((v[8 * t + 7] - mean) * rstd * g1.w + b1.w) * rs;
+        const uint4 o4 = pack8(o);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(box + my_row + ((((uint32_t)((c & 1) * 4 + t)) ^ sw) << 4)),
+                     "r"(o4.x), "r"(o4.y), "r"(o4.z), "r"(o4.w) : "memory");
+      }
+      if (c & 1) {                                                // one 64-column box complete: hand it to the TMA engine
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0 && row0 < g.M) {
+          tma_store_2d(&tmY, box, n0 + (c >> 1) * 64, row0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+}
+
+template <int CL>
+int launch_ln_small(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const CUtensorMap& ty,
+                    const LnArgs& g, cudaStream_t st) {
+  static bool attr_done = false;
+  auto kern = gemm_ln_small_kernel<CL>;
+  if (!attr_done) {
+    ICAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM_BYTES));
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)CL, (unsigned)ceil_div64(g.M, BM));
+  cfg.blockDim = dim3(S_THREADS);
+  cfg.dynamicSmemBytes = S_SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CL > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CL;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (icap_g_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  ICAP_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tr, ty, g));
+  return 0;
+}
+
 template <int CL, int BN>
 int launch_ln(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tr, const CUtensorMap& ty,
               const CUtensorMap& ts, const LnArgs& g, cudaStream_t st) {
@@ -391,7 +665,17 @@ extern "C" int icap_gemm_ln(int64_t M, int64_t N, int64_t K, const void* A, int6
   // training row counts.  ICAP_GEMM_LN_BN=128|256 forces it.
   const int64_t tiles_m = ceil_div64(M, BM);
   int bn = (N == 128 || tiles_m * (N / 128) <= (int64_t)(icap_num_sms() * 3) / 4) ? 128 : 256;
-  if (const char* e = getenv("ICAP_GEMM_LN_BN")) { const int f = atoi(e); if ((f == 128 || f == 256) && N % f == 0) bn = f; }
+  static IcapEnv e_bn;
+  if (const char* e = e_bn.get("ICAP_GEMM_LN_BN")) { const int f = atoi(e); if ((f == 128 || f == 256) && N % f == 0) bn = f; }
+  // inference form at latency-bound row counts: optionally the small-footprint kernel (two CTAs per SM).  Measured on
+  // B200 (beam-5 decode of 512 images): 14.8 ms against 13.8 ms with the 320-thread kernel below -- its two-pass,
+  // four-warp epilogue sits on the critical path of every launch -- so it is OFF by default (ICAP_GEMM_LN_SMALL=1
+  // automatic, =2 every eligible call).
+  static IcapEnv e_small;
+  const int small_mode = e_small.geti("ICAP_GEMM_LN_SMALL", 0);
+  const bool small = small_mode != 0 && sum_out == nullptr && mean_out == nullptr && p_drop == 0.f && N / 128 <= MAX_CL &&
+                     (small_mode == 2 || tiles_m * (N / 128) <= (int64_t)icap_num_sms() * 9 / 4);
+  if (small) bn = 128;
   CUtensorMap ta, tb;
   int rc;
   if ((rc = icap_make_tmap_2d(&ta, A, M, K, lda, BM, ICAP_BF16))) return rc;
@@ -409,7 +693,14 @@ extern "C" int icap_gemm_ln(int64_t M, int64_t N, int64_t K, const void* A, int6
   g.mean = mean_out; g.rstd = rstd_out;
   g.eps = eps; g.p_drop = p_drop; g.thresh = dropout_threshold(p_drop); g.seed = seed; g.seed_dev = seed_dev;
   cudaStream_t st = (cudaStream_t)stream;
-  if (bn == 128) {
+  if (small) {
+    switch (N / 128) {
+      case 1: rc = launch_ln_small<1>(ta, tb, tr, ty, g, st); break;
+      case 2: rc = launch_ln_small<2>(ta, tb, tr, ty, g, st); break;
+      case 4: rc = launch_ln_small<4>(ta, tb, tr, ty, g, st); break;
+      default: rc = launch_ln_small<8>(ta, tb, tr, ty, g, st); break;
+    }
+  } else if (bn == 128) {
     switch (N / 128) {
       case 1: rc = launch_ln<1, 128>(ta, tb, tr, ty, ts, g, st); break;
       case 2: rc = launch_ln<2, 128>(ta, tb, tr, ty, ts, g, st); break;

@@ -80,7 +80,14 @@ struct GemmArgs {
   int kb_per_split, splits, tiles_m, tiles_n;
   int vec_ok, store_mode;   // store_mode: 0 direct global stores, 1 TMA store, 2 TMA reduce-add
   int debug;                // timing experiments only (ICAP_GEMM_DEBUG): 1 = no TMA loads, 2 = no MMAs, 3 = no epilogue stores
+  unsigned long long* trace; // timing experiments (icap_debug_trace): %globaltimer stamps of CTA 0, else null
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 template <int BN, bool TWO, bool A_KMAJOR, bool B_KMAJOR, typename TO>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -105,6 +112,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t rank = TWO ? cluster_ctarank() : 0u;            // 0 = leader of the pair
   const int worker = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int nworkers = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  unsigned long long* const tr = (g.trace && blockIdx.x == 0) ? g.trace : nullptr;
+  if (tr && threadIdx.x == 0) tr[0] = gtimer();
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -135,7 +144,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if constexpr (TWO) cluster_sync_all(); else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  if (tr && threadIdx.x == 0) tr[1] = gtimer();
   pdl_prologue();    // everything above overlaps the previous kernel's tail when launched with PDL
+  if (tr && threadIdx.x == 0) tr[2] = gtimer();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -202,6 +213,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
         for (int i = 0; i < nkb; ++i) {
           mbar_wait_t<TWO>(full_bar + 8 * s, ph);
+          if (tr && it == 0 && i == 0) tr[4] = gtimer();
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t aS = sA + s * A_TILE_BYTES, bS = sB + s * CF::B_TILE_BYTES;
 #pragma unroll
@@ -220,6 +232,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         // accumulator complete
         if constexpr (TWO) umma_commit_2sm(tfull_bar + 8 * as); else umma_commit(tfull_bar + 8 * as);
+        if (tr && it == 0) tr[5] = gtimer();
       }
     }
   } else {
@@ -255,6 +268,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                  N - n0 - c_begin * 32);
       mbar_wait_t<TWO>(tfull_bar + 8 * as, aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (tr && it == 0 && ew == 0 && lane == 0) tr[6] = gtimer();
       if (c_begin >= nchunks) {                 // ragged N: nothing to drain, just hand the stage back
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
@@ -376,6 +390,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     if (g.store_mode != 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (tr && ew == 0 && lane == 0) tr[7] = gtimer();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   if constexpr (TWO) cluster_sync_all(); else __syncthreads();    // pair: the peer may still signal our barriers / read our smem
@@ -385,6 +400,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     else
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(CF::TMEM_COLS) : "memory");
   }
+  if (tr && threadIdx.x == 0) tr[8] = gtimer();
 }
 
 // ------------------------------------------------------------------ host side
@@ -414,7 +430,8 @@ int make_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int6
   cuuint64_t gstride[1] = {(cuuint64_t)ld * esz};
   cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
-  static const int promo_env = getenv("ICAP_TMA_L2_PROMOTION") ? atoi(getenv("ICAP_TMA_L2_PROMOTION")) : 256;
+  static IcapEnv e_promo;
+  const int promo_env = e_promo.geti("ICAP_TMA_L2_PROMOTION", 256);
   const CUtensorMapL2promotion promo = promo_env == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
                                        : promo_env == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                                        : promo_env == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
@@ -427,17 +444,18 @@ int make_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int6
   return 0;
 }
 
-int g_num_sms = 0;
+int g_num_sms = 0, g_num_sms_gen = -1;
 
 int num_sms() {
-  if (g_num_sms == 0) {
+  if (g_num_sms == 0 || g_num_sms_gen != icap_g_env_gen) {
+    g_num_sms_gen = icap_g_env_gen;
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) == cudaSuccess &&
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
       g_num_sms = n;
     else
       g_num_sms = 148;
-    if (const char* e = getenv("ICAP_GEMM_SMS")) { int v = atoi(e); if (v > 0) g_num_sms = v; }
+    if (const char* e = getenv("ICAP_GEMM_SMS")) { int v = atoi(e); if (v > 0) g_num_sms = v; }   // once per env generation
   }
   return g_num_sms;
 }
@@ -496,10 +514,20 @@ int icap_make_tmap_2d(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t co
 }
 int icap_num_sms() { return num_sms(); }
 
+unsigned long long* icap_trace_slot();
+bool icap_gemm_small_eligible(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, int c_dtype, int epi,
+                              int accumulate, int split_k, const void* C, int64_t ldc);
+int icap_gemm_small_launch(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
+                           int64_t ldc, const float* bias, int relu, int b_static, cudaStream_t st);
+
 int icap_gemm_bf16_launch(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
                           const void* B, int64_t ldb, void* C, int64_t ldc, int c_dtype, const float* bias, int epi,
                           const void* aux, int64_t ldaux, int accumulate, int split_k, cudaStream_t st) {
   ICAP_ARG((uintptr_t)A % 16 == 0 && (uintptr_t)B % 16 == 0, "icap_gemm(bf16): A/B must be 16-byte aligned");
+  // latency-bound shapes (decode steps): the small-footprint kernel that overlaps with its neighbours in the stream
+  if (icap_gemm_small_eligible(a_kmajor, b_kmajor, M, N, K, c_dtype, epi, accumulate, split_k, C, ldc))
+    return icap_gemm_small_launch(M, N, K, A, lda, B, ldb, C, ldc, bias, (epi & 15) == 1, (epi & 16) != 0, st);
+  epi &= 15;
   ICAP_ARG(lda % 8 == 0 && ldb % 8 == 0, "icap_gemm(bf16): lda/ldb must be multiples of 8 (TMA 16-byte strides)");
   ICAP_ARG(!(a_kmajor == 0 && b_kmajor == 1), "icap_gemm(bf16): (A MN-major, B K-major) is not instantiated");
   const int sms = num_sms();
@@ -508,7 +536,10 @@ int icap_gemm_bf16_launch(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int6
   // ---- tile configuration and split-K factor: split_k <= 0 = automatic (fill the SMs, >= 4 k-blocks per split)
   int best_cfg = 0, best_split = 1;
   double best_cost = 1e30;
-  const char* force_bn = getenv("ICAP_GEMM_BN");          // "128" | "256" | "pair"
+  static IcapEnv e_bn, e_nopair, e_direct, e_dbg;
+  const char* force_bn = e_bn.get("ICAP_GEMM_BN");                     // "128" | "256" | "pair"
+  const bool no_pair = e_nopair.get("ICAP_GEMM_NO_PAIR") != nullptr;
+  const bool direct_epi = e_direct.get("ICAP_GEMM_DIRECT_EPILOGUE") != nullptr;
   for (int c = 2; c >= 0; --c) {
     if (force_bn) {
       const int want = force_bn[0] == 'p' ? 2 : (atoi(force_bn) == 256 ? 1 : 0);
@@ -516,7 +547,7 @@ int icap_gemm_bf16_launch(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int6
     }
     const int bn = c == 0 ? 128 : 256, bm = c == 2 ? 256 : 128;
     if (c >= 1 && N <= 128 && !force_bn) continue;
-    if (c == 2 && !force_bn && (M <= 128 || getenv("ICAP_GEMM_NO_PAIR"))) continue;
+    if (c == 2 && !force_bn && (M <= 128 || no_pair)) continue;
     const int64_t tiles = ceil_div64(M, bm) * ceil_div64(N, bn);
     const int workers = c == 2 ? sms / 2 : sms;
     int split = split_k;
@@ -563,7 +594,7 @@ int icap_gemm_bf16_launch(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int6
   int vec_ok = ((uintptr_t)C % 16 == 0) && ((ldc * esz) % 16 == 0);
   // staged TMA epilogue whenever C satisfies the TMA alignment rules; accumulation = TMA reduce-add
   int store_mode = vec_ok ? (accumulate ? 2 : 1) : 0;
-  if (getenv("ICAP_GEMM_DIRECT_EPILOGUE")) store_mode = 0;
+  if (direct_epi) store_mode = 0;
   if (epi == 2) vec_ok = vec_ok && ((uintptr_t)aux % 16 == 0) && ((ldaux * esz) % 16 == 0);
   CUtensorMap tc = ta;
   if (store_mode && (rc = make_tmap(&tc, C, M, N, ldc, 32, c_dtype))) return rc;
@@ -573,7 +604,8 @@ int icap_gemm_bf16_launch(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int6
   g.kb_per_split = kb_per; g.splits = split_k;
   g.tiles_m = (int)ceil_div64(M, two ? 2 * BM : BM); g.tiles_n = (int)ceil_div64(N, BN);
   g.vec_ok = vec_ok; g.store_mode = store_mode;
-  { const char* e = getenv("ICAP_GEMM_DEBUG"); g.debug = e ? atoi(e) : 0; }
+  g.debug = e_dbg.geti("ICAP_GEMM_DEBUG", 0);
+  g.trace = icap_trace_slot();
 #define GO2(BNV, TW, AK, BKM)                                                                          \
   (c_dtype == ICAP_F32 ? launch<BNV, TW, AK, BKM, float>(ta, tb, tc, g, st)                              \
                        : launch<BNV, TW, AK, BKM, bf16>(ta, tb, tc, g, st))

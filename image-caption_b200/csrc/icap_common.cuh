@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #define ICAP_F32 0
 #define ICAP_BF16 1
@@ -64,6 +65,24 @@ __device__ __forceinline__ void pdl_prologue() { pdl_wait(); pdl_launch_dependen
 #endif
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- environment switches: read ONCE (not per launch); icap_reload_env() (tests / tools that change os.environ in
+// the running process) invalidates every cached value.
+extern int icap_g_env_gen;
+struct IcapEnv {
+  int gen = -1;
+  const char* v = nullptr;
+  const char* get(const char* name) {
+    if (gen != icap_g_env_gen) { v = getenv(name); gen = icap_g_env_gen; }
+    return v;
+  }
+  int geti(const char* name, int dflt) { const char* s = get(name); return s ? atoi(s) : dflt; }
+};
+// is the switch set?  (ID: one cache slot per call-site family; the same ID must always be used with the same name)
+template <int ID> static inline bool env_flag(const char* name) {
+  static IcapEnv e;
+  return e.get(name) != nullptr;
+}
 
 // ---- dtype helpers -----------------------------------------------------------------------------
 typedef __nv_bfloat16 bf16;

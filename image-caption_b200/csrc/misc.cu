@@ -16,6 +16,8 @@ void icap_set_error(const char* fmt, ...) {
 extern "C" const char* icap_last_error() { return g_err; }
 int icap_g_pdl = 0;       // launch attribute for every kernel of the library, see icap_launch()
 extern "C" int icap_set_pdl(int on) { icap_g_pdl = on ? 1 : 0; return 0; }
+int icap_g_env_gen = 0;   // generation of the cached ICAP_* environment switches (IcapEnv, icap_common.cuh)
+extern "C" int icap_reload_env(void) { ++icap_g_env_gen; return 0; }
 
 extern "C" int icap_version() { return 100; }
 
@@ -528,14 +530,15 @@ extern "C" int icap_gemm(int ab_dtype, int a_kmajor, int b_kmajor, int64_t M, in
                          int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int c_dtype, const float* bias,
                          int epilogue, const void* aux, int64_t ldaux, int accumulate, int split_k, void* stream) {
   ICAP_ARG(M > 0 && N > 0 && K > 0 && A && B && C, "icap_gemm: null/empty argument");
-  ICAP_ARG(epilogue >= 0 && epilogue <= 2 && (epilogue != 2 || aux), "icap_gemm: bad epilogue %d", epilogue);
+  ICAP_ARG(epilogue >= 0 && (epilogue & 15) <= 2 && (epilogue & ~31) == 0 && ((epilogue & 15) != 2 || aux),
+           "icap_gemm: bad epilogue %d", epilogue);
   ICAP_ARG(accumulate >= 0 && accumulate <= 1, "icap_gemm: accumulate must be 0 or 1");
   ICAP_ARG(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "icap_gemm: dimension too large");
   cudaStream_t st = (cudaStream_t)stream;
   if (ab_dtype == ICAP_F32) {
     ICAP_ARG(c_dtype == ICAP_F32, "icap_gemm(fp32): C must be fp32");
     return icap_gemm_f32_launch(a_kmajor, b_kmajor, M, N, K, (const float*)A, lda, (const float*)B, ldb, (float*)C, ldc,
-                                bias, epilogue, (const float*)aux, ldaux, accumulate, split_k, st);
+                                bias, epilogue & 15, (const float*)aux, ldaux, accumulate, split_k, st);
   }
   return icap_gemm_bf16_launch(a_kmajor, b_kmajor, M, N, K, A, lda, B, ldb, C, ldc, c_dtype, bias, epilogue, aux, ldaux,
                                accumulate, split_k, st);

@@ -500,8 +500,9 @@ extern "C" int icap_add_ln_fwd(int a_dtype, int act_dtype, int64_t M, int64_t d,
   dim3 grid((unsigned)ceil_div64(M, 8));
   const uint32_t th = dropout_threshold(p_drop);
   if (d % 8 == 0 && M * (d / 8) < (1ll << 30) && aligned16(a) && aligned16(res) && aligned16(y) && aligned16(gamma) &&
-      aligned16(beta) && !getenv("ICAP_LN_NARROW")) {
-    static const int rpw = getenv("ICAP_LN_RPW") ? atoi(getenv("ICAP_LN_RPW")) : 1;     // rows per warp (1 or 2)
+      aligned16(beta) && !env_flag<4>("ICAP_LN_NARROW")) {
+    static IcapEnv e_rpw;
+    const int rpw = e_rpw.geti("ICAP_LN_RPW", 1);     // rows per warp (1 or 2)
     dim3 grid8((unsigned)ceil_div64(M, 8 * (rpw == 1 ? 1 : 2)));
 #define GO8R(NIT, R, TA, TR, TY)                                                                                  \
   icap_launch(add_ln_fwd8_kernel<NIT, R, TA, TR, TY>, grid8, 256, 0, st, (int)M, (int)d, (TA*)a, (const TR*)res, \
@@ -567,11 +568,13 @@ static int add_ln_bwd_impl(int which, int act_dtype, int64_t M, int64_t d, const
   const void* dab = da ? da : ds;       // dbias2 sums the GEMM-branch gradient
   ICAP_ARG(dbias2 == nullptr || dab != nullptr, "icap_add_ln_bwd: dbias2 needs ds or da");
   if (d % 8 == 0 && M * (d / 8) < (1ll << 30) && aligned16(dy1) && aligned16(dy2) && aligned16(s) && aligned16(ds) &&
-      aligned16(da) && aligned16(gamma) && !getenv("ICAP_LN_NARROW")) {
-    static const int rpw = getenv("ICAP_LN_RPW") ? atoi(getenv("ICAP_LN_RPW")) : 1;     // rows per warp (1 or 2)
+      aligned16(da) && aligned16(gamma) && !env_flag<4>("ICAP_LN_NARROW")) {
+    static IcapEnv e_rpw;
+    const int rpw = e_rpw.geti("ICAP_LN_RPW", 1);     // rows per warp (1 or 2)
     const unsigned row_blocks8 = (unsigned)ceil_div64(M, 8 * (rpw == 1 ? 1 : 2));
     const int64_t col_blocks8 = ceil_div64(d, 256);
-    static const int cols_waves = getenv("ICAP_LN_COLS_WAVES") ? atoi(getenv("ICAP_LN_COLS_WAVES")) : 3;
+    static IcapEnv e_cw;
+    const int cols_waves = e_cw.geti("ICAP_LN_COLS_WAVES", 3);
     int64_t splits8 = ceil_div64(148 * cols_waves, col_blocks8);
     if (splits8 > ceil_div64(M, 16)) splits8 = ceil_div64(M, 16);
     const int rpb8 = (int)ceil_div64(M, splits8);

@@ -186,23 +186,12 @@ class CaptionEngine:
         self._side: Optional[torch.cuda.Stream] = None
         self._warm: Optional[torch.cuda.Stream] = None       # warm-up stream of the graph captures (see warm_stream)
         self._bwd_side: Optional[torch.cuda.Stream] = None
-        # optional (ICAP_ADAM_IN_BWD=1): Adam in slices on the side stream as the gradients of a suffix of the flat
-        # buffer complete during the backward.  Measured on B200: 4.91 vs 4.77 ms/step -- the 1.7 GB of optimizer
-        # traffic slows the L2-bound GEMMs it overlaps more than it saves -- so it is off by default.
-        self.adam_in_backward = os.environ.get("ICAP_ADAM_IN_BWD", "0") == "1"
-        self._adam_plan = None           # (lr, b1, b2, eps, gscale_dev, gscale, prev_lo) while such a backward runs
         # cross-attention K|V projections of all decoder layers (forward) and their dgrad into the encoder-output
         # gradient (backward) depend only on the encoder output: launched on the side stream
         self.xkv_side = os.environ.get("ICAP_XKV_SIDE", "1") != "0"
         # projection + dropout + residual + LayerNorm as one cluster kernel: 0 never, 1 inference passes, 2 training too
         # (measured on B200: beam-5 decode 17.0 -> 15.8 ms, training step 4.53 -> 4.44 ms)
         self.gemm_ln_mode = int(os.environ.get("ICAP_GEMM_LN", "2"))
-        # micro-batching (train_step_mb): the batch is cut into slices whose forward + backward run on separate
-        # streams and accumulate into the shared gradient buffer
-        self._mb_active = False
-        self._mb_streams: List[torch.cuda.Stream] = []
-        self._mb_sides: List[torch.cuda.Stream] = []
-        self._mb_inv = None
         self.p16 = torch.empty(self.n_flat, dtype=torch.bfloat16, device=self.dev) if precision == "bf16" else None
         self.shadow_fresh = False
         self.adam_m: Optional[torch.Tensor] = None
@@ -212,6 +201,7 @@ class CaptionEngine:
         self.pos_table_act = self.pos_table32.to(self.tdt)
         self.base_seed = 0x1234ABCD
         self.tape: Optional[List[Callable[[], None]]] = None
+        self.tape_gen = 0                # bumped by every recorded forward: autograd wrappers check they run THEIR tape
         self.gr: Dict[int, List[torch.Tensor]] = {}
         self.keep: List[torch.Tensor] = []
         self.training = False
@@ -283,8 +273,12 @@ class CaptionEngine:
              out: torch.Tensor, ldc: Optional[int] = None, bias: Optional[int] = None, epi: int = 0,
              aux: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: int = 1,
              lda: Optional[int] = None, a_ptr: Optional[int] = None, c_ptr: Optional[int] = None,
-             c_dtype: Optional[int] = None, side: bool = False) -> None:
+             c_dtype: Optional[int] = None, side: bool = False, b_static: bool = False) -> None:
+        """b_static: B (and bias) are model weights that the kernel launched just before does not write -- the
+        small-footprint kernel may then fetch them before its grid dependency resolves (ICAP_EPI_B_STATIC)."""
         ab = BF16 if self.precision == "bf16" else F32
+        if b_static:
+            epi |= N.EPI_B_STATIC
         if c_dtype is None:
             c_dtype = F32 if out.dtype == torch.float32 else BF16
         args = (ab, int(a_kmajor), int(b_kmajor), M, Nn, K,
@@ -444,7 +438,7 @@ class CaptionEngine:
     # ------------------------------------------------------------------ blocks
     def mha_block(self, prefix: str, xq: torch.Tensor, xkv: torch.Tensor, B: int, Lq: int, Lk: int, H: int,
                   dk_tot: int, dv_tot: int, kvalid: Optional[torch.Tensor], causal: bool,
-                  attn_mean: Optional[torch.Tensor] = None, kv_pre=None) -> torch.Tensor:
+                  attn_mean: Optional[torch.Tensor] = None, kv_pre=None, report_lo: bool = True) -> torch.Tensor:
         """MultiHeadAttention.forward (modules.py:67-92) with q = xq, k = v = xkv.
         kv_pre = (tensor, event): the packed K|V projection of xkv was already launched on another stream."""
         cfg = self.cfg
@@ -457,20 +451,20 @@ class CaptionEngine:
         if self_attn:
             nqkv = 2 * dk_tot + dv_tot
             qkv = self.new(Mq, nqkv)
-            self.gemm(xq, True, self.w(wq), d, True, Mq, nqkv, d, qkv)      # packed [Wq;Wk;Wv]
+            self.gemm(xq, True, self.w(wq), d, True, Mq, nqkv, d, qkv, b_static=True)      # packed [Wq;Wk;Wv]
             q_ptr, k_ptr, v_ptr = qkv.data_ptr(), qkv.data_ptr() + dk_tot * qkv.element_size(), \
                 qkv.data_ptr() + 2 * dk_tot * qkv.element_size()
             ldq = ldk = ldv = nqkv
             kvb = None
         else:
             qkv = self.new(Mq, dk_tot)
-            self.gemm(xq, True, self.w(wq), d, True, Mq, dk_tot, d, qkv)
+            self.gemm(xq, True, self.w(wq), d, True, Mq, dk_tot, d, qkv, b_static=True)
             if kv_pre is not None:
                 kvb = kv_pre[0]
                 torch.cuda.current_stream(self.dev).wait_event(kv_pre[1])
             else:
                 kvb = self.new(Mk, dk_tot + dv_tot)
-                self.gemm(xkv, True, self.w(wk), d, True, Mk, dk_tot + dv_tot, d, kvb)   # packed [Wk;Wv]
+                self.gemm(xkv, True, self.w(wk), d, True, Mk, dk_tot + dv_tot, d, kvb, b_static=True)   # packed [Wk;Wv]
             q_ptr, k_ptr, v_ptr = qkv.data_ptr(), kvb.data_ptr(), kvb.data_ptr() + dk_tot * kvb.element_size()
             ldq, ldk, ldv = dk_tot, dk_tot + dv_tot, dk_tot + dv_tot
         att = self.new(Mq, dv_tot)
@@ -522,12 +516,15 @@ class CaptionEngine:
                         dxkv = self.new(Mk, d)
                         self.gemm(dkv, True, self.w(wk), d, False, Mk, d, dk_tot + dv_tot, dxkv, side=on_side)
                         gl.append(dxkv)
-            bwd.lo = self.offsets[wq]          # lowest flat offset this closure writes gradients to (DP buckets)
+            # lowest flat offset this closure writes gradients to (DP buckets: everything from there to the end of the
+            # flat buffer must be FINAL when it returns -- callers whose parameters are registered before tensors that
+            # complete later pass report_lo=False)
+            bwd.lo = self.offsets[wq] if report_lo else None
             self.tape.append(bwd)
         return y
 
     def ffn_block(self, prefix: str, x: torch.Tensor, hidden: int, rowscale: Optional[torch.Tensor],
-                  norm: Optional[str] = None, x_in: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  norm: Optional[str] = None, x_in: Optional[torch.Tensor] = None, report_lo: bool = True) -> torch.Tensor:
         """FeedForward.forward (modules.py:110-122) [+ `*= non_pad_mask`, modules.py:154-155,203-204].
         x_in (move_first_image_feature tail, model.py:451-457): GEMM input differs from the residual."""
         cfg = self.cfg
@@ -537,7 +534,7 @@ class CaptionEngine:
         w2, b2 = prefix + ".position_wise_2.weight", prefix + ".position_wise_2.bias"
         gin = x if x_in is None else x_in
         h = self.new(M, hidden)
-        self.gemm(gin, True, self.w(w1), d, True, M, hidden, d, h, bias=self.p(b1), epi=N.EPI_RELU)
+        self.gemm(gin, True, self.w(w1), d, True, M, hidden, d, h, bias=self.p(b1), epi=N.EPI_RELU, b_static=True)
         y, f, mean, rstd, seed_l, p_l = self.proj_add_ln(h, w2, hidden, self.p(b2), x, norm, rowscale, cfg.dropout)
 
         if self.tape is not None:
@@ -552,7 +549,9 @@ class CaptionEngine:
                 dx = self.new(M, d)
                 self.gemm(dh, True, self.w(w1), d, False, M, d, hidden, dx)
                 self.add_grad(gin, dx)
-            bwd.lo = self.offsets[w1] if prefix != "decoder" else None     # the move_first tail completes out of order
+            # the move_first tail completes out of order; image_encoder.* is registered BEFORE encoder.feature_embedding /
+            # encoder.norm, whose gradients are only final at the very end of the backward (report_lo=False)
+            bwd.lo = self.offsets[w1] if (prefix != "decoder" and report_lo) else None
             self.tape.append(bwd)
         return y
 
@@ -586,7 +585,7 @@ class CaptionEngine:
     def _unpack_embed_grads(self, dwcat: torch.Tensor) -> None:
         cfg = self.cfg
         d, Df, Dp, Kc = cfg.encode_input_size, cfg.encode_dim_features, cfg.encode_dim_positions, self._cat_width()
-        acc = 2 if self._mb_active else 1           # micro-batches on several streams share g32: atomic accumulate
+        acc = 1
         call("icap_copy2d", dwcat.data_ptr(), F32, Kc, self.g("encoder.feature_embedding.weight"), F32, Df, d, Df, acc,
              self._s())
         if cfg.split_position:
@@ -686,8 +685,8 @@ class CaptionEngine:
             self.tape.append(bwd_embed2)
         pre = "encoder.image_encoder"
         z = self.mha_block(pre + ".multihead_attention", y2, y2, M, 2, 2, H, cfg.encode_q_k_dim, cfg.encode_v_dim,
-                           kvalid2, True)
-        z = self.ffn_block(pre + ".feed_forward", z, cfg.encode_hidden_size, rowscale2)
+                           kvalid2, True, report_lo=False)
+        z = self.ffn_block(pre + ".feed_forward", z, cfg.encode_hidden_size, rowscale2, report_lo=False)
         # embedded_feature = output[:, 1]; embedded_position = position_embedding(position)[:, 1]  (model.py:290-292)
         tok1 = self.new(M, d)
         call("icap_copy2d", z.data_ptr() + d * esz, self.act, 2 * d, tok1.data_ptr(), self.act, d, M, d, 0, self._s())
@@ -794,8 +793,15 @@ class CaptionEngine:
             feats = feats.to(self.dev, torch.float32, non_blocking=True).contiguous()
             pos = pos.to(self.dev, torch.float32, non_blocking=True).contiguous()
         if captions is not None:
-            captions = captions.to(self.dev, non_blocking=True).contiguous()
             assert captions.dtype in (torch.int32, torch.int64)
+            if not captions.is_cuda and captions.numel():
+                # the kernels index the embedding table / logits with these ids unchecked (the reference would raise a
+                # device assert): validate host batches here, where it costs nothing
+                lo, hi = int(captions.min()), int(captions.max())
+                if lo < 0 or hi >= self.cfg.num_vocab:
+                    raise N.IcapError(f"caption token ids must lie in [0, {self.cfg.num_vocab}): got [{lo}, {hi}] "
+                                      "(vocabulary / checkpoint mismatch?)")
+            captions = captions.to(self.dev, non_blocking=True).contiguous()
         return feats, pos, captions
 
     def forward_logits(self, feats, pos, captions, record: bool):
@@ -805,6 +811,8 @@ class CaptionEngine:
         self.refresh_shadow()
         self._site = 0
         self.tape = [] if record else None
+        if record:
+            self.tape_gen += 1
         self.gr, self.keep = {}, []
         B, R, _ = feats.shape
         L = captions.shape[1]
@@ -825,7 +833,8 @@ class CaptionEngine:
         V, d = cfg.num_vocab, cfg.decode_input_size
         ldl = (V + 7) // 8 * 8
         logits = self.new(M, ldl)
-        self.gemm(dec, True, self.w("classifer.weight"), d, True, M, V, d, logits, ldc=ldl, bias=self.p("classifer.bias"))
+        self.gemm(dec, True, self.w("classifer.weight"), d, True, M, V, d, logits, ldc=ldl, bias=self.p("classifer.bias"),
+                  b_static=True)
         return logits, tgt, count2, dec
 
     def loss_from_logits(self, logits, tgt, count2, dec, record: bool) -> torch.Tensor:
@@ -841,8 +850,7 @@ class CaptionEngine:
         call("icap_xent", self.act, M, V, logits.data_ptr(), ldl, tgt.data_ptr(), cfg.pad_idx, grad_scale.data_ptr(),
              row_loss.data_ptr(), int(record), self._s())
         if self.dp_unnormalized and record:
-            call("icap_copy2d", count2.data_ptr(), F32, 1, self.g32.data_ptr() + 4 * self.n_flat, F32, 1, 1, 1,
-                 2 if self._mb_active else 1, self._s())
+            call("icap_copy2d", count2.data_ptr(), F32, 1, self.g32.data_ptr() + 4 * self.n_flat, F32, 1, 1, 1, 1, self._s())
         call("icap_xent_finalize", M, row_loss.data_ptr(), inv_count.data_ptr(), int(cfg.focal), out2.data_ptr(),
              self._s())
         if record:
@@ -884,16 +892,11 @@ class CaptionEngine:
                 self._side = torch.cuda.Stream(device=self.dev)
             self._bwd_side = self._side
             self._bwd_side.wait_stream(main)          # g32 has been zeroed / the forward is complete
-        if self._bwd_side is None:
-            self._adam_plan = None
         try:
             for fn in reversed(self.tape):
                 fn()
-                lo = getattr(fn, "lo", None)
                 if self.bucket_hook is not None:
-                    self.bucket_hook(lo)
-                if self._adam_plan is not None and lo is not None:
-                    self._adam_slice(lo)
+                    self.bucket_hook(getattr(fn, "lo", None))
         finally:
             if self._bwd_side is not None:
                 main.wait_stream(self._bwd_side)      # every weight gradient has landed in g32
@@ -912,106 +915,14 @@ class CaptionEngine:
              _ptr(gscale_dev), gscale, self._s())
         self.shadow_fresh = True
 
-    ADAM_SLICE_ELEMS = 6 << 20          # ~24 MB of fp32 gradients per slice
-
-    def _adam_slice(self, lo: int, final: bool = False) -> None:
-        """Adam over the completed gradient suffix [lo, prev_lo) of the flat buffers (side stream during backward)."""
-        lr, b1, b2, eps, gs_dev, gs, prev_lo = self._adam_plan
-        if lo >= prev_lo or (not final and prev_lo - lo < self.ADAM_SLICE_ELEMS):
-            return
-        n = prev_lo - lo
-        args = ("icap_adam_step", n, self.p32.data_ptr() + 4 * lo, self.g32.data_ptr() + 4 * lo,
-                self.adam_m.data_ptr() + 4 * lo, self.adam_v.data_ptr() + 4 * lo,
-                (self.p16.data_ptr() + 2 * lo) if self.p16 is not None else None, lr, b1, b2, eps,
-                self.step_dev.data_ptr(), 2, _ptr(gs_dev), gs)
-        if final:
-            call(*args, self._s())
-        else:
-            self.side_call(*args)
-        self._adam_plan = (lr, b1, b2, eps, gs_dev, gs, lo)
-
     def train_step(self, feats, pos, captions, lr: float = 5e-4, train_mode: bool = True,
                    betas=(0.9, 0.999), eps: float = 1e-8) -> torch.Tensor:
         """zero_grad -> forward -> backward -> Adam (core/models.py:115-126), all on the current stream.
         Returns the device tensor [loss, dloss/dce] (no host sync).  train_mode=False keeps dropout off
         (the reference's eval-mode arithmetic, used by the parity tests)."""
-        fused = (self.adam_in_backward and self.wgrad_side_stream and self.precision == "bf16" and self._prof is None
-                 and self.bucket_hook is None)
-        if not fused:
-            out2 = self.forward_backward(feats, pos, captions, train_mode)
-            self.adam_step(lr, betas=betas, eps=eps, gscale_dev=out2[1:2] if self.cfg.focal else None)
-            return out2
-        if self.adam_m is None:
-            self.adam_m = torch.zeros_like(self.p32)
-            self.adam_v = torch.zeros_like(self.p32)
-        self.training = train_mode
-        self.g32.zero_()
-        logits, tgt, count2, dec = self.forward_logits(feats, pos, captions, record=True)
-        out2 = self.loss_from_logits(logits, tgt, count2, dec, record=True)
-        self._adam_plan = (lr, betas[0], betas[1], eps, out2[1:2] if self.cfg.focal else None, 1.0, self.n_flat)
-        try:
-            self.backward(zero_grads=False)            # Adam slices ride on the side stream; joined at its end
-            if self._adam_plan is not None:
-                self._adam_slice(0, final=True)        # what is left (encoder front), on the main stream
-            else:                                      # the backward ran without a side stream
-                self.adam_step(lr, betas=betas, eps=eps, gscale_dev=out2[1:2] if self.cfg.focal else None)
-                return out2
-        finally:
-            self._adam_plan = None
-        call("icap_step_tick", self.step_dev.data_ptr(), self._s())
-        self.shadow_fresh = True
+        out2 = self.forward_backward(feats, pos, captions, train_mode)
+        self.adam_step(lr, betas=betas, eps=eps, gscale_dev=out2[1:2] if self.cfg.focal else None)
         return out2
-
-    def train_step_mb(self, feats, pos, captions, n_mb: int = 2, lr: float = 5e-4, train_mode: bool = True,
-                      betas=(0.9, 0.999), eps: float = 1e-8) -> torch.Tensor:
-        """Same arithmetic as train_step (one optimizer step on the whole batch, loss = mean over ALL non-pad
-        targets), but the batch is cut into n_mb slices whose forward + backward are enqueued on separate streams:
-        while one slice runs a tensor-core GEMM on part of the SMs, another runs its LayerNorm / attention kernels.
-        Uses the data-parallel normalisation: every slice back-propagates the SUM of its token losses and adds its
-        token count to the tail slot of g32; Adam divides by the total.  Returns [mean loss, 1]."""
-        B = feats.shape[0]
-        assert not self.cfg.focal, "micro-batching does not support FocalLoss (its gradient scale needs the global mean)"
-        assert B % n_mb == 0
-        dev = self.dev
-        main = torch.cuda.current_stream(dev)
-        while len(self._mb_streams) < n_mb:
-            self._mb_streams.append(torch.cuda.Stream(device=dev))
-            self._mb_sides.append(torch.cuda.Stream(device=dev))
-        if self._mb_inv is None:
-            self._mb_inv = torch.zeros(1, dtype=torch.float32, device=dev)
-        self.refresh_shadow()
-        self.g32.zero_()
-        saved = (self.dp_unnormalized, self._side, self.base_seed)
-        self.dp_unnormalized, self._mb_active = True, True
-        self.training = train_mode
-        bs = B // n_mb
-        outs, keep_all = [], []
-        try:
-            for i in range(n_mb):
-                st = self._mb_streams[i]
-                st.wait_stream(main)
-                self._side = self._mb_sides[i]
-                self.base_seed = (saved[2] + 0x51ED27 * (i + 1)) & 0xFFFFFFFF       # different dropout masks per slice
-                with torch.cuda.stream(st):
-                    sl = slice(i * bs, (i + 1) * bs)
-                    logits, tgt, count2, dec = self.forward_logits(feats[sl], None if pos is None else pos[sl], captions[sl], record=True)
-                    out2 = self.loss_from_logits(logits, tgt, count2, dec, record=True)
-                    keep_all.append(self.keep)              # backward() drops self.keep: hold the activations
-                    self.backward(zero_grads=False)
-                    outs.append((out2, count2))
-            for i in range(n_mb):
-                main.wait_stream(self._mb_streams[i])
-        finally:
-            self.dp_unnormalized, self._side, self.base_seed = saved
-            self._mb_active = False
-        call("icap_reciprocal", self.g32.data_ptr() + 4 * self.n_flat, self._mb_inv.data_ptr(), 1.0, self._s())
-        self.adam_step(lr, betas=betas, eps=eps, gscale_dev=self._mb_inv)
-        # mean loss over all non-pad targets = sum_i loss_i * n_i / sum_i n_i
-        num = sum(o[0][0] * o[1][0] for o in outs)
-        den = sum(o[1][0] for o in outs)
-        res = torch.stack([num / den, torch.ones((), device=dev)])
-        del keep_all
-        return res
 
     def forward_backward(self, feats, pos, captions, train_mode: bool = True) -> torch.Tensor:
         """zero_grad + forward + backward; gradients land in g32 (data parallel: all-reduce them next)."""
@@ -1023,20 +934,7 @@ class CaptionEngine:
         return out2
 
     def _proj_res_ln(self, att: torch.Tensor, resid: torch.Tensor, prefix: str, rows: int, d: int, dv_tot: int):
-        """joint_linear -> (+ residual) -> LayerNorm of an attention block in a decode step (modules.py:86-90, eval):
-        one fused launch for small row counts in bf16 (the GEMM and the LayerNorm are both latency bound there),
-        otherwise GEMM + add_ln."""
-        # (measured on B200, rows = 2560: the fused mma.sync kernel takes ~18 us against 8.5 + 5.6 us for the tcgen05 GEMM
-        #  + LayerNorm pair -- 80 CTAs of legacy tensor-core throughput lose to 148 SMs of tcgen05 -- so it is opt-in)
-        fused = (self.precision == "bf16" and d in (256, 512) and dv_tot % 64 == 0 and rows <= 8192
-                 and os.environ.get("ICAP_FUSED_PROJ_LN", "0") == "1")
-        if fused:
-            y = self.new(rows, d)
-            call("icap_linear_res_ln", rows, d, dv_tot, att.data_ptr(), dv_tot,
-                 self.w(prefix + ".joint_linear.weight"), dv_tot, None, resid.data_ptr(), d,
-                 self.p(prefix + ".layer_norm.weight"), self.p(prefix + ".layer_norm.bias"), None, y.data_ptr(), d,
-                 LN_EPS, self._s())
-            return y
+        """joint_linear -> (+ residual) -> LayerNorm of an attention block in a decode step (modules.py:86-90, eval)."""
         y, *_ = self.proj_add_ln(att, prefix + ".joint_linear.weight", dv_tot, None, resid, prefix + ".layer_norm", None,
                                  0.0)
         return y
@@ -1110,7 +1008,8 @@ class CaptionEngine:
                 last = i == cfg.decode_num_blocks - 1
                 # --- masked self-attention over the cache (modules.py:190-194)
                 qkv = self.new(rows, nqkv)
-                self.gemm(x, True, self.w(pre + ".self_attention.q_linear.weight"), d, True, rows, nqkv, d, qkv)
+                self.gemm(x, True, self.w(pre + ".self_attention.q_linear.weight"), d, True, rows, nqkv, d, qkv,
+                          b_static=True)
                 cache = caches[i]
                 att = self.new(rows, dv_tot)
                 # K/V of position t are appended to the cache inside the attention kernel
@@ -1126,11 +1025,12 @@ class CaptionEngine:
                     call("icap_mha_decode_self", self.act, rows, H, t, dk, dv, qkv.data_ptr(), nqkv,
                          qkv.data_ptr() + dk_tot * esz, qkv.data_ptr() + 2 * dk_tot * esz, nqkv, cache.data_ptr(), nkv,
                          cache.data_ptr() + dk_tot * esz, nkv, T, att.data_ptr(), dv_tot, sl, Tmax, tk.data_ptr(), Tmax,
-                         cfg.pad_idx, s())
+                         cfg.pad_idx, k, s())
                 x1 = self._proj_res_ln(att, x, pre + ".self_attention", rows, d, dv_tot)
                 # --- cross-attention over the image regions (modules.py:196-200)
                 q2 = self.new(rows, dk_tot)
-                self.gemm(x1, True, self.w(pre + ".encode_attention.q_linear.weight"), d, True, rows, dk_tot, d, q2)
+                self.gemm(x1, True, self.w(pre + ".encode_attention.q_linear.weight"), d, True, rows, dk_tot, d, q2,
+                          b_static=True)
                 att2 = self.new(rows, dv_tot)
                 call("icap_mha_decode", self.act, rows, H, R, dk, dv, q2.data_ptr(), dk_tot, cross[i].data_ptr(), nkv,
                      cross[i].data_ptr() + dk_tot * esz, nkv, R, att2.data_ptr(), dv_tot, None, 0, None, 0, cfg.pad_idx,
@@ -1141,7 +1041,8 @@ class CaptionEngine:
             if cfg.move_first_image_feature:
                 x = self._move_first_tail(x, enc, B, 1, R, rows_per_image=k)
             logits = self.new(rows, ldl)
-            self.gemm(x, True, self.w("classifer.weight"), d, True, rows, V, d, logits, ldc=ldl, bias=self.p("classifer.bias"))
+            self.gemm(x, True, self.w("classifer.weight"), d, True, rows, V, d, logits, ldc=ldl,
+                      bias=self.p("classifer.bias"), b_static=True)
             if k == 1:
                 call("icap_argmax", self.act, rows, V, logits.data_ptr(), ldl, tk.data_ptr() + 4 * (t + 1), Tmax,
                      gaps[t].data_ptr() if gaps is not None else None, s())

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 from torch.utils.data import DataLoader
 
-from core.models import DEVICE, TRANSFORMER
+from core.models import DEVICE, TRANSFORMER, SelfCriticNetwork
 from core.config import *          # noqa: F401,F403
 from core.dataset import IndexedCaptions, SyntheticCaptionDataset, TestDataset, TrainDataset
 from core.utils import save_pickle
@@ -21,7 +21,8 @@ MODEL = None
 def _model():
     global MODEL
     if MODEL is None:
-        MODEL = TRANSFORMER()      # the reference builds it at import time (main.py:19-22)
+        # the reference builds it at import time (main.py:19-22)
+        MODEL = TRANSFORMER() if CAPTION_MODEL == 'Transformer' else SelfCriticNetwork()
     return MODEL
 
 
@@ -51,6 +52,7 @@ def train(num_images=64, max_iters=None, region_cache=REGION_CACHE):
     os.makedirs(target_dir, exist_ok=True)
     train_ds = _dataset(True, num_images, 'train')
     valid_ds = _dataset(True, max(num_images // 4, BATCH_SIZE // 5 + 1), 'valid')
+    region_cache = region_cache and hasattr(model, 'cache_regions')     # the RL wrapper feeds tensors, as the reference
     if region_cache:
         t_cache = model.cache_regions(train_ds.data['features'], train_ds.data['positions'])
         v_cache = model.cache_regions(valid_ds.data['features'], valid_ds.data['positions'])
@@ -111,6 +113,7 @@ def evaluation(split='test', epoch=90, beam_size=None, num_images=64, region_cac
     ds = _dataset(False, num_images, split)
     captions_out = [''] * ds.len_image
     t0 = time.time()
+    region_cache = region_cache and hasattr(model, 'cache_regions')
     if region_cache:        # every image once (the reference decodes it once per ground-truth caption, dataset.py:36-43)
         cache = model.cache_regions(ds.data['features'], ds.data['positions'])
         loader = DataLoader(IndexedCaptions(ds, with_captions=False, unique_images=True), batch_size=BATCH_SIZE,
@@ -144,8 +147,8 @@ def demo(image_path=None, beam_size=None, epoch=90, save_img=False, max_obj=Fals
         blob = torch.load(features_path)
         feature, position = blob['features'].unsqueeze(0), blob['positions'].unsqueeze(0)
     else:
-        ds = _dataset(False, 1)
-        feature, position = ds.features[:1], ds.positions[:1]
+        ds = _dataset(False, 1)                # TestDataset (COCO artefacts) or SyntheticCaptionDataset: first image
+        feature, position = (torch.as_tensor(np.asarray(x)).unsqueeze(0) for x in ds[0][:2])
     model_path = os.path.join(OUTPUT_PATH, f'model/model_{epoch}.pt')
     if os.path.exists(model_path):
         model.load(path=model_path)

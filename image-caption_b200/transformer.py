@@ -47,6 +47,14 @@ def _set_nested(root: nn.Module, dotted: str, value, is_buffer: bool) -> None:
         mod.register_parameter(parts[-1], value)
 
 
+def _check_tape(eng: CaptionEngine, gen: int) -> None:
+    """The engine keeps ONE backward tape (the reference's train loop is forward -> backward -> step): a second recorded
+    forward, a decode or a no_grad pass between a forward and its backward() replaces / drops it."""
+    if eng.tape is None or eng.tape_gen != gen:
+        raise IcapError("backward() of a stale forward: another forward / decode ran on this model since (the engine "
+                        "keeps one tape -- call backward() right after the forward it belongs to)")
+
+
 class _LossFn(torch.autograd.Function):
     """Lets `loss.backward()` (core/models.py:125) drive the explicit backward of the engine."""
 
@@ -58,7 +66,7 @@ class _LossFn(torch.autograd.Function):
         f, p, c = eng.prepare_inputs(feats, pos, captions)
         logits, tgt, count2, dec = eng.forward_logits(f, p, c, record=record)
         out2 = eng.loss_from_logits(logits, tgt, count2, dec, record=record)
-        ctx.model, ctx.out2, ctx.recorded = model, out2, record
+        ctx.model, ctx.out2, ctx.recorded, ctx.gen = model, out2, record, eng.tape_gen
         return out2[0].clone()
 
     @staticmethod
@@ -66,6 +74,7 @@ class _LossFn(torch.autograd.Function):
         model, eng = ctx.model, ctx.model._engine()
         if not ctx.recorded:
             raise IcapError("backward() called on a forward that did not record (no_grad / frozen parameters)")
+        _check_tape(eng, ctx.gen)
         params = [q for _, q in model.named_parameters()]
         fresh = all(q.grad is None for q in params)
         eng.backward(zero_grads=fresh)                 # existing .grad views => accumulate like autograd does
@@ -93,7 +102,7 @@ class _LogitsFn(torch.autograd.Function):
         logits, tgt, count2, dec = eng.forward_logits(f, p, c, record=record)
         if record:
             eng._append_classifier_bwd(logits, dec)
-        ctx.model, ctx.logits, ctx.recorded = model, logits, record
+        ctx.model, ctx.logits, ctx.recorded, ctx.gen = model, logits, record, eng.tape_gen
         B, T = c.shape[0], c.shape[1] - 1
         ctx.shape = (B, T, model.num_vocab)
         # a copy: the engine overwrites its logits buffer with d loss / d logits in the backward
@@ -104,6 +113,7 @@ class _LogitsFn(torch.autograd.Function):
         model, eng = ctx.model, ctx.model._engine()
         if not ctx.recorded:
             raise IcapError("backward() called on a forward that did not record (no_grad / frozen parameters)")
+        _check_tape(eng, ctx.gen)
         params = [q for _, q in model.named_parameters()]
         fresh = all(q.grad is None for q in params)
         eng.set_dlogits(ctx.logits, grad_out)
@@ -112,6 +122,37 @@ class _LogitsFn(torch.autograd.Function):
             off = eng.offsets[name]
             q.grad = eng.g32[off:off + q.numel()].view_as(q)
         return (None,) * (5 + len(params))
+
+
+class _SampleFn(torch.autograd.Function):
+    """PolicyNetwork.sample (model_RL.py:93-97): log_softmax over the vocabulary + arg-max, one fused kernel; the
+    log-probabilities stay differentiable (the self-critical loss gathers them, loss.py:145-158)."""
+
+    @staticmethod
+    def forward(ctx, output):
+        from ._native import call
+        if not output.is_cuda:
+            raise IcapError("PolicyNetwork.sample runs on the GPU only (there is no CPU fallback)")
+        x = output.detach().to(torch.float32).contiguous()
+        B, T, V = x.shape
+        logp = torch.empty_like(x)
+        seq = torch.empty(B, T, dtype=torch.int64, device=x.device)
+        call("icap_log_softmax_argmax", B * T, V, x.data_ptr(), V, logp.data_ptr(), V, seq.data_ptr(),
+             torch.cuda.current_stream(x.device).cuda_stream)
+        ctx.save_for_backward(logp)
+        ctx.mark_non_differentiable(seq)
+        return seq, logp
+
+    @staticmethod
+    def backward(ctx, _gseq, glogp):
+        from ._native import call
+        logp, = ctx.saved_tensors
+        B, T, V = logp.shape
+        g = glogp.to(torch.float32).contiguous()
+        dx = torch.empty_like(logp)
+        call("icap_log_softmax_bwd", B * T, V, logp.data_ptr(), V, g.data_ptr(), V, dx.data_ptr(), V,
+             torch.cuda.current_stream(logp.device).cuda_stream)
+        return dx
 
 
 class Transformer(nn.Module):
@@ -205,6 +246,10 @@ class Transformer(nn.Module):
     # ------------------------------------------------------------------ flat storage upkeep
     def _apply(self, fn, *args, **kwargs):
         super()._apply(fn, *args, **kwargs)            # moves every parameter separately ...
+        first = next(iter(self.parameters()))
+        if (first.dtype == torch.float32 and first.device == self._flat.device
+                and first.untyped_storage().data_ptr() == self._flat.untyped_storage().data_ptr()):
+            return self                                # .to() of the device it already lives on: views, Adam state, graphs stay
         self._reflatten()                              # ... so re-pack them into one buffer
         return self
 
@@ -396,9 +441,8 @@ class PolicyNetwork(Transformer):
 
     @staticmethod
     def sample(output):
-        """model_RL.py:93-97."""
-        log_probs = torch.nn.functional.log_softmax(output, dim=2)
-        return torch.argmax(log_probs, dim=2), log_probs
+        """model_RL.py:93-97 -> (sequence [B, T] int64, log_probs [B, T, V] fp32, differentiable)."""
+        return _SampleFn.apply(output)
 
 
 class GradBuckets:
@@ -440,6 +484,10 @@ class DataParallel:
     def __init__(self, model: "Transformer", dist, bucket_mb: Optional[float] = None, overlap: bool = True):
         self.dist = dist
         self.world = dist.get_world_size()
+        if model.cfg.focal:
+            # d focal / d ce depends on the GLOBAL mean CE; this protocol all-reduces gradients of the summed token
+            # losses and the token count only.  Refuse instead of silently training with plain-CE gradients.
+            raise IcapError("DataParallel does not support FocalLoss output names ('FocalLoss' in output_name)")
         eng = model._engine()
         eng.dp_unnormalized = True
         dist.broadcast(eng.p32, src=0)          # identical replicas
@@ -498,14 +546,14 @@ class DataParallel:
         call("icap_reciprocal", eng.g32.data_ptr() + 4 * eng.n_flat, self.inv.data_ptr(), 1.0, eng._s())
         eng.adam_step(lr, gscale_dev=self.inv)
 
-    def step_eager(self, eng: CaptionEngine, feats, pos, cap, lr: float) -> torch.Tensor:
+    def step_eager(self, eng: CaptionEngine, feats, pos, cap, lr: float, train_mode: bool = True) -> torch.Tensor:
         """One data-parallel train step without CUDA graphs."""
         if self.overlap:
             self.begin(eng)
-            out2 = eng.forward_backward(feats, pos, cap)
+            out2 = eng.forward_backward(feats, pos, cap, train_mode)
             self.end(eng)
         else:
-            out2 = eng.forward_backward(feats, pos, cap)
+            out2 = eng.forward_backward(feats, pos, cap, train_mode)
             self.reduce(eng)
         self.finish(eng, lr)
         return out2
@@ -620,14 +668,8 @@ class GraphedTrainStep:
         self.warmup = warmup
         self.launches_per_step = 0
         self.single_graph_dp = False
-        # ICAP_MICRO_BATCHES=n: forward + backward of n batch slices on n streams inside the graph (engine.train_step_mb)
-        self.micro_batches = 1 if (dp is not None or model.cfg.focal) else max(1, int(os.environ.get("ICAP_MICRO_BATCHES", "1")))
-        if batch % self.micro_batches:
-            self.micro_batches = 1
 
     def _one_step(self) -> torch.Tensor:
-        if self.micro_batches > 1:
-            return self.eng.train_step_mb(self.feats, self.pos, self.cap, n_mb=self.micro_batches, lr=self.lr)
         return self.eng.train_step(self.feats, self.pos, self.cap, lr=self.lr, train_mode=self.train_mode)
 
     def load(self, feats: torch.Tensor, pos: Optional[torch.Tensor], cap: torch.Tensor) -> None:

@@ -30,6 +30,9 @@ extern "C" {
 #define ICAP_EPI_NONE 0
 #define ICAP_EPI_RELU 1      /* C = relu(AB + bias)            FeedForward position_wise_1 + ReLU, modules.py:113-114 */
 #define ICAP_EPI_RELU_MASK 2 /* C = (AB) * (aux > 0)           backward of that ReLU                                   */
+/* flag, OR-ed into `epilogue`: B and bias are WEIGHTS that the kernel launched immediately before on this stream does
+ * not write; the small-footprint kernel then fetches its first B stages before its grid dependency has resolved. */
+#define ICAP_EPI_B_STATIC 16
 
 int icap_version(void);
 const char* icap_last_error(void);
@@ -49,6 +52,12 @@ int icap_set_pdl(int on);
 int icap_gemm(int ab_dtype, int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
               const void* B, int64_t ldb, void* C, int64_t ldc, int c_dtype, const float* bias, int epilogue,
               const void* aux, int64_t ldaux, int accumulate, int split_k, void* stream);
+/* The library reads its ICAP_* environment switches once; call this after changing the environment of the running
+ * process (tests, tools).  icap_debug_trace (tools/, not used by the product path): record %globaltimer stamps of CTA 0
+ * of every following tcgen05 GEMM launch into buf (device memory, 16 x uint64 per slot, slot = launch number % nslots;
+ * buf = NULL: off). */
+int icap_reload_env(void);
+int icap_debug_trace(unsigned long long* buf, int nslots);
 
 /* Fused multi-head attention over packed projections (one CTA per (batch, head)).
  *   q rows b*Lq+i at q + row*ldq + h*dk; k/v rows b*Lk+j likewise; o rows at o + row*ldo + h*dv.
@@ -104,15 +113,6 @@ int icap_gemm_ln(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, co
                  const float* bias, const void* res, int64_t ldr, const float* gamma, const float* beta,
                  const float* rowscale, void* y, int64_t ldy, void* sum_out, int64_t lds, float* mean_out,
                  float* rstd_out, float eps, float p_drop, uint64_t seed, const int* seed_dev, void* stream);
-/* y[M,N] = (LayerNorm(A[M,K] . W[N,K]^T + bias + res[M,N]) * gamma + beta) * rowscale[row]  -- bf16 in / out, fp32
- * accumulation and statistics, no dropout (eval).  One launch instead of icap_gemm + icap_add_ln_fwd for the output
- * projections of a decode step (joint_linear + residual + LayerNorm, modules.py:86-90), where the row count
- * (batch * beam) is small and both kernels are latency bound.  N in {256, 512}, K % 64 == 0; returns -2 for shapes
- * it does not cover (use the two-kernel path then). */
-int icap_linear_res_ln(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* W, int64_t ldw,
-                       const float* bias, const void* res, int64_t ldr, const float* gamma, const float* beta,
-                       const float* rowscale, void* y, int64_t ldy, float eps, void* stream);
-
 /* Fused log-softmax + NLL per row; with write_grad=1 the logits are overwritten IN PLACE by
  * (softmax - onehot) * inv_count[0] (zero rows for ignored targets).  row_loss: fp32 [M].
  * Replaces CrossEntropyLoss(ignore_index=pad_idx, 'mean'), model.py:76,93-96. */
@@ -132,6 +132,14 @@ int icap_argmax(int dtype, int64_t M, int64_t V, const void* logits, int64_t ldl
 int icap_beam_select(int dtype, int64_t B, int64_t kin, int64_t V, const void* logits, int64_t ldl,
                      const float* prev_score, int64_t kout, float* out_score, int* out_parent, int* out_token,
                      float* gap, int log_domain, void* stream);
+/* PolicyNetwork.sample (model_RL.py:93-97) on fp32 logits [M, V]: logp = log_softmax(x) per row, idx[row] (int64,
+ * nullable) = arg-max (lowest index on ties, as torch.argmax on the CPU).  icap_log_softmax_bwd is its backward:
+ * dx = dlogp - exp(logp) * rowsum(dlogp)  (the self-critical loss gathers log-probabilities, loss.py:90-103,145-158). */
+int icap_log_softmax_argmax(int64_t M, int64_t V, const float* x, int64_t ldx, float* logp, int64_t ldo, long long* idx,
+                            void* stream);
+int icap_log_softmax_bwd(int64_t M, int64_t V, const float* logp, int64_t ldp, const float* dlogp, int64_t ldd, float* dx,
+                         int64_t ldx, void* stream);
+
 /* Reorder token buffer (and KV-cache slot table) by parent and append the new token: model.py:194-198. */
 int icap_beam_reorder(int64_t B, int64_t k, int64_t Tmax, int64_t t, const int* parent, const int* token,
                       const int* tok_in, int* tok_out, const int* slot_in, int* slot_out, void* stream);
@@ -140,7 +148,9 @@ int icap_beam_reorder(int64_t B, int64_t k, int64_t Tmax, int64_t t, const int* 
  *   self-attention (tokens != NULL): keys/values of positions 0..Lk-1 live in the cache at physical row
  *                    slot[row*slot_ld+j] (own row when slot == NULL); position j is masked iff
  *                    tokens[row*tok_ld+j] == pad_idx  (model.py:421-430).
- *   cross-attention (tokens == NULL): keys are the Lk regions of image row / rows_per_image, masked by kvalid.
+ *   cross-attention (tokens == NULL): keys are the Lk regions of image row / rows_per_image, masked by kvalid;
+ *                    kc / vc / kvalid must NOT be written by the kernel launched just before on this stream (they are
+ *                    produced once per decode): the kernel fetches them before its grid dependency has resolved.
  *   cache rows: k at kc + (slot*Tmax_or_Lk + j)*ldk + h*dk. */
 int icap_mha_decode(int dtype, int64_t rows, int64_t H, int64_t Lk, int64_t dk, int64_t dv, const void* q, int64_t ldq,
                     const void* kc, int64_t ldk, const void* vc, int64_t ldv, int64_t kv_rows_per_seq, void* o,
@@ -150,11 +160,15 @@ int icap_mha_decode(int dtype, int64_t rows, int64_t H, int64_t Lk, int64_t dk, 
 /* Self-attention decode step with the KV-cache append fused in: the key / value of position `pos` (rows of k_new /
  * v_new, leading dimension ld_new) are written to the row's own cache line (kc/vc + (row*kv_rows_per_seq + pos)*ld)
  * and attended together with the cached positions 0..pos-1 (slot table / pad-token mask as in icap_mha_decode).
+ * rows_per_image (>= 1, beam width): consecutive rows that belong to one image -- a scheduling hint only (their cache
+ * lines overlap through the slot table, so they are processed by one thread block).  tokens, slot and the cached
+ * positions 0..pos-1 must not be written by the kernel launched just before on this stream (they come from earlier
+ * decode steps): they are read / prefetched into L2 before the grid dependency has resolved.
  * Replaces the per-step prefix recomputation of model.py:114-122,169-180 (decoder self-attention, modules.py:190-194). */
 int icap_mha_decode_self(int dtype, int64_t rows, int64_t H, int64_t pos, int64_t dk, int64_t dv, const void* q,
                          int64_t ldq, const void* k_new, const void* v_new, int64_t ld_new, void* kc, int64_t ldk, void* vc,
                          int64_t ldv, int64_t kv_rows_per_seq, void* o, int64_t ldo, const int* slot, int64_t slot_ld,
-                         const int* tokens, int64_t tok_ld, int pad_idx, void* stream);
+                         const int* tokens, int64_t tok_ld, int pad_idx, int64_t rows_per_image, void* stream);
 
 /* dst[r][c] (+)= convert(src[r][c]) : operand packing / dtype casts / gradient unpacking.
  * accumulate: 0 = store, 1 = dst += src, 2 = atomic dst += src (fp32 dst; concurrent accumulation from several streams). */

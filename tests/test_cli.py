@@ -52,6 +52,19 @@ def test_train_evaluation_demo_synthetic(tmp_path):
     assert r.returncode == 0 and "Generated Caption:" in r.stdout
 
 
+@pytest.mark.gpu
+def test_train_rl_transformer_synthetic(tmp_path):
+    """CAPTION_MODEL='RL_Transformer' (the reference's shipped default, config.py:14): SelfCriticNetwork = PolicyNetwork
+    logits + log-softmax/arg-max sampler + self-critical loss with the injectable reward, through the same CLI."""
+    env = {"ICAP_CAPTION_MODEL": "RL_Transformer"}
+    r = _run(["train", "--num-images", "16", "--max-iters", "3"], tmp_path, env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "loss" in r.stdout
+    r = _run(["evaluation", "--split", "test", "--epoch", "1", "--beam-size", "3", "--num-images", "16"], tmp_path, env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "16 captions" in r.stdout
+
+
 def _write_split(root, split, n_img, R, Dp, L, vocab, seed, caps_per_image=2):
     """data/<MODEL_NAME>/<split>/ in the reference's layout (utils.py:32-64), arrays as .npy (hickle is not installed)."""
     import pickle

@@ -19,6 +19,18 @@ def dev():
     return torch.device("cuda:0")
 
 
+@pytest.fixture(autouse=True)
+def _fresh_env():
+    """libicap caches its ICAP_* switches; tests that monkeypatch the environment re-read them (and again on exit)."""
+    yield
+    N.call("icap_reload_env")
+
+
+def setenv(monkeypatch, key, value):
+    monkeypatch.setenv(key, value)
+    N.call("icap_reload_env")
+
+
 def S():
     return torch.cuda.current_stream().cuda_stream
 
@@ -45,9 +57,9 @@ def _gemm_case(ab, a_k, b_k, M, Nn, K, c_dtype=F32, bias=False, epi=0, accumulat
     if bias:
         ref = ref + bias_t.double()
     aux = None
-    if epi == 1:
+    if (epi & 15) == 1:
         ref = ref.clamp_min(0)
-    if epi == 2:
+    if (epi & 15) == 2:
         aux = torch.randn(M, Nn, device=dev(), generator=g).to(dt(c_dtype))
         ref = ref * (aux.double() > 0)
     C = torch.randn(M, Nn, device=dev(), generator=g).to(dt(c_dtype)) if accumulate else \
@@ -98,7 +110,8 @@ def test_gemm_bf16_persistent_multi_tile(bn, monkeypatch):
     """More tiles than SMs: every CTA loops over several tiles (TMEM accumulator double buffering, smem ring
     phases carried across tiles), all tile configurations (128x128, 128x256, cta_group::2 pair 256x256), every
     epilogue, automatic split-K."""
-    monkeypatch.setenv("ICAP_GEMM_BN", bn)
+    setenv(monkeypatch, "ICAP_GEMM_BN", bn)
+    setenv(monkeypatch, "ICAP_GEMM_SMALL", "0")
     assert _gemm_case(BF16, 1, 1, 9216, 2048, 512, c_dtype=BF16, bias=True, epi=1) < 6e-3      # FFN1 forward
     assert _gemm_case(BF16, 1, 0, 9216, 2048, 512, c_dtype=BF16, epi=2) < 6e-3                 # FFN2 dgrad + ReLU mask
     assert _gemm_case(BF16, 1, 1, 5376, 10000, 512, c_dtype=BF16, bias=True) < 6e-3            # classifier
@@ -108,10 +121,27 @@ def test_gemm_bf16_persistent_multi_tile(bn, monkeypatch):
     assert _gemm_case(BF16, 0, 0, 2048, 512, 9216, accumulate=1, split_k=0) < 1e-5             # wgrad, auto split
     assert _gemm_case(BF16, 0, 0, 10000, 512, 5376, accumulate=1, split_k=0) < 1e-5            # classifier wgrad
     assert _gemm_case(BF16, 0, 0, 512, 2136, 9216, accumulate=1, split_k=0) < 1e-5             # embedding wgrad
-    monkeypatch.setenv("ICAP_GEMM_DIRECT_EPILOGUE", "1")
+    setenv(monkeypatch, "ICAP_GEMM_DIRECT_EPILOGUE", "1")
     assert _gemm_case(BF16, 1, 1, 3000, 1000, 200, c_dtype=BF16, bias=True, epi=1) < 6e-3
     assert _gemm_case(BF16, 1, 0, 3000, 1000, 200, c_dtype=BF16, epi=2) < 6e-3
     assert _gemm_case(BF16, 0, 0, 520, 392, 5000, accumulate=1, split_k=0) < 1e-5
+
+
+@pytest.mark.parametrize("mode", ["0", "2"])
+def test_gemm_bf16_small_footprint_kernel(mode, monkeypatch):
+    """The small-footprint 128x128 one-tile-per-CTA kernel (gemm_small.cu: decode-step shapes, 2 CTAs per SM, weight
+    prefetch before the grid dependency) against the persistent kernel on the same shapes: ragged M / N / K, bias,
+    ReLU, the B_STATIC flag, K shorter and longer than the 3-stage ring, more CTAs than fit at once (mode 2)."""
+    setenv(monkeypatch, "ICAP_GEMM_SMALL", mode)
+    for epi in (0, N.EPI_B_STATIC):
+        assert _gemm_case(BF16, 1, 1, 2560, 1536, 512, c_dtype=BF16, epi=epi) < 6e-3            # decode QKV
+        assert _gemm_case(BF16, 1, 1, 2560, 2048, 512, c_dtype=BF16, bias=True, epi=1 | epi) < 6e-3   # decode FFN1
+        assert _gemm_case(BF16, 1, 1, 2560, 512, 2048, c_dtype=BF16, bias=True, epi=epi) < 6e-3
+        assert _gemm_case(BF16, 1, 1, 260, 136, 96, c_dtype=BF16, bias=True, epi=1 | epi) < 6e-3
+        assert _gemm_case(BF16, 1, 1, 37, 1000, 64, c_dtype=BF16, bias=True, epi=epi) < 6e-3
+        assert _gemm_case(BF16, 1, 1, 515, 392, 200, c_dtype=BF16, epi=epi) < 6e-3
+    if mode == "2":
+        assert _gemm_case(BF16, 1, 1, 5376, 10000, 512, c_dtype=BF16, bias=True, epi=N.EPI_B_STATIC) < 6e-3
 
 
 def test_gemm_bf16_vocab_shapes():
@@ -141,7 +171,7 @@ def test_gemm_bf16_vocab_shapes():
 def test_mha_decode_self_fused_append():
     """icap_mha_decode_self (KV-cache append fused into the attention) == explicit append + icap_mha_decode, for the
     head-dim-64 fast path and the generic path, with beam slot indirection and pad-token masking."""
-    for act, dh in ((BF16, 64), (F32, 64), (F32, 16)):
+    for act, dh, rpi in ((BF16, 64, 1), (BF16, 64, 3), (F32, 64, 1), (F32, 64, 4), (F32, 16, 1)):
         g = torch.Generator(device="cuda").manual_seed(9 + dh)
         tdt = dt(act)
         rows, H, T, t = 24, 4, 9, 5
@@ -162,15 +192,20 @@ def test_mha_decode_self_fused_append():
         o = torch.empty(rows, d, device=dev(), dtype=tdt)
         N.call("icap_mha_decode_self", act, rows, H, t, dh, dh, q.data_ptr(), 3 * d, q.data_ptr() + d * esz,
                q.data_ptr() + 2 * d * esz, 3 * d, cache.data_ptr(), 2 * d, cache.data_ptr() + d * esz, 2 * d, T,
-               o.data_ptr(), d, slot.data_ptr(), T + 1, tok.data_ptr(), T + 1, 0, S())
+               o.data_ptr(), d, slot.data_ptr(), T + 1, tok.data_ptr(), T + 1, 0, rpi, S())
         torch.cuda.synchronize()
         assert torch.equal(cache, ref_cache)
         assert rel_err(o, o_ref) < (1e-5 if act == F32 else 1e-2)
 
 
-@pytest.mark.parametrize("M,Nn,K", [(2560, 512, 512), (77, 512, 512), (512, 256, 256), (33, 512, 2048)])
-def test_linear_res_ln_fused(M, Nn, K):
-    """Fused output projection + residual + LayerNorm of a decode step == fp64 reference (bf16 inputs)."""
+@pytest.mark.parametrize("small", ["0", "2"])
+@pytest.mark.parametrize("M,Nn,K", [(2560, 512, 512), (77, 512, 512), (300, 256, 256), (129, 1024, 1024),
+                                    (640, 512, 2048), (9216, 512, 512), (50, 128, 72), (130, 512, 64), (200, 256, 128)])
+def test_gemm_ln_small_footprint(M, Nn, K, small, monkeypatch):
+    """Inference form of icap_gemm_ln (no dropout, nothing saved): the small-footprint two-pass kernel (192 threads,
+    3-stage ring, accumulator re-read from TMEM, two CTAs per SM) and the original kernel against fp64; K shorter than
+    the ring (the residual boxes then land in never-used ring slots), with and without bias / residual / row scale."""
+    setenv(monkeypatch, "ICAP_GEMM_LN_SMALL", small)
     g = torch.Generator(device="cuda").manual_seed(M + K)
     A = torch.randn(M, K, device=dev(), generator=g).bfloat16()
     W = (torch.randn(Nn, K, device=dev(), generator=g) / math.sqrt(K)).bfloat16()
@@ -179,12 +214,12 @@ def test_linear_res_ln_fused(M, Nn, K):
     gamma = torch.randn(Nn, device=dev(), generator=g)
     beta = torch.randn(Nn, device=dev(), generator=g)
     rs = (torch.rand(M, device=dev(), generator=g) > 0.2).float()
-    y = torch.full((M, Nn), float("nan"), device=dev(), dtype=torch.bfloat16)
-    for use_bias, use_rs in ((True, True), (False, False)):
-        N.call("icap_linear_res_ln", M, Nn, K, A.data_ptr(), K, W.data_ptr(), K, bias.data_ptr() if use_bias else None,
-               res.data_ptr(), Nn, gamma.data_ptr(), beta.data_ptr(), rs.data_ptr() if use_rs else None, y.data_ptr(), Nn,
-               1e-6, S())
-        x = A.double() @ W.double().t() + res.double() + (bias.double() if use_bias else 0.0)
+    for use_bias, use_rs, use_res in ((True, True, True), (False, False, True), (True, False, False)):
+        y = torch.full((M, Nn), float("nan"), device=dev(), dtype=torch.bfloat16)
+        N.call("icap_gemm_ln", M, Nn, K, A.data_ptr(), K, W.data_ptr(), K, bias.data_ptr() if use_bias else None,
+               res.data_ptr() if use_res else None, Nn, gamma.data_ptr(), beta.data_ptr(),
+               rs.data_ptr() if use_rs else None, y.data_ptr(), Nn, None, 0, None, None, 1e-6, 0.0, 0, None, S())
+        x = A.double() @ W.double().t() + (res.double() if use_res else 0.0) + (bias.double() if use_bias else 0.0)
         ref = torch.nn.functional.layer_norm(x, (Nn,), gamma.double(), beta.double(), 1e-6)
         if use_rs:
             ref = ref * rs.double()[:, None]
@@ -201,7 +236,8 @@ def test_gemm_ln_cluster_fused(M, Nn, K, bn, monkeypatch):
     if bn != "auto":
         if Nn % int(bn):
             pytest.skip("width not a multiple of the forced tile")
-        monkeypatch.setenv("ICAP_GEMM_LN_BN", bn)
+        setenv(monkeypatch, "ICAP_GEMM_LN_BN", bn)
+        setenv(monkeypatch, "ICAP_GEMM_LN_SMALL", "0")
     g = torch.Generator(device="cuda").manual_seed(M + K)
     A = torch.randn(M, K, device=dev(), generator=g).bfloat16()
     W = (torch.randn(Nn, K, device=dev(), generator=g) / math.sqrt(K)).bfloat16()
@@ -490,6 +526,42 @@ def test_mha_decode_matches_full_attention():
         assert rel_err(am, att.mean(1).squeeze(1)) < (1e-5 if act == F32 else 1.5e-2)
 
 
+@pytest.mark.parametrize("k,H,R", [(1, 8, 36), (3, 8, 37), (5, 8, 36), (5, 16, 100), (8, 4, 5), (2, 8, 128)])
+def test_mha_decode_cross_image_per_cta(k, H, R):
+    """Cross-attention of a decode step, bf16 / head dim 64 / packed K|V rows: the one-CTA-per-image kernel (TMA bulk
+    staging of the image's K|V block, per-key-slot online softmax merged at the end) against fp64 -- beam widths 1..8,
+    16 heads (model C), region counts that need several staging chunks (100 x 4 KB rows), padded regions as a suffix
+    and in the middle, one image with a single valid region."""
+    B, dh = 7, 64
+    rows, d = B * k, H * dh
+    g = torch.Generator(device="cuda").manual_seed(100 * k + R)
+    q = torch.randn(rows, d, device=dev(), generator=g).bfloat16()
+    kvb = torch.randn(B * R, 2 * d, device=dev(), generator=g).bfloat16()
+    kvalid = torch.ones(B, R, dtype=torch.uint8, device=dev())
+    kvalid[1, R // 2:] = 0                                  # padded suffix
+    if R > 3:
+        kvalid[2, 1] = 0                                    # hole in the middle
+        kvalid[2, R - 2:] = 0
+    kvalid[3, 1:] = 0                                       # a single valid region (region 0 = whole image)
+    o = torch.full((rows, d), float("nan"), device=dev(), dtype=torch.bfloat16)
+    N.call("icap_mha_decode", BF16, rows, H, R, dh, dh, q.data_ptr(), d, kvb.data_ptr(), 2 * d, kvb.data_ptr() + d * 2, 2 * d,
+           R, o.data_ptr(), d, None, 0, None, 0, 0, kvalid.data_ptr(), k, None, S())
+    img = torch.arange(rows, device=dev()) // k
+    kk = kvb.view(B, R, 2 * d)[img][:, :, :d].double().view(rows, R, H, dh).transpose(1, 2)
+    vv = kvb.view(B, R, 2 * d)[img][:, :, d:].double().view(rows, R, H, dh).transpose(1, 2)
+    qq = q.double().view(rows, 1, H, dh).transpose(1, 2)
+    att = ((qq / math.sqrt(dh)) @ kk.transpose(2, 3)).masked_fill((kvalid[img] == 0).view(rows, 1, 1, R), float("-inf")).softmax(-1)
+    ref = (att @ vv).transpose(1, 2).reshape(rows, d)
+    torch.cuda.synchronize()
+    assert rel_err(o, ref) < 1.5e-2
+    # kvalid = NULL: every region is a key
+    N.call("icap_mha_decode", BF16, rows, H, R, dh, dh, q.data_ptr(), d, kvb.data_ptr(), 2 * d, kvb.data_ptr() + d * 2, 2 * d,
+           R, o.data_ptr(), d, None, 0, None, 0, 0, None, k, None, S())
+    ref = (((qq / math.sqrt(dh)) @ kk.transpose(2, 3)).softmax(-1) @ vv).transpose(1, 2).reshape(rows, d)
+    torch.cuda.synchronize()
+    assert rel_err(o, ref) < 1.5e-2
+
+
 # ------------------------------------------------------------------------------------------ loss / selection
 @pytest.mark.parametrize("act", [F32, BF16])
 @pytest.mark.parametrize("M,V", [(50, 397), (64, 10000), (8, 60000)])
@@ -562,7 +634,8 @@ def test_beam_select(log_domain, kin, kout, V):
 
 
 @pytest.mark.parametrize("log_domain", [0, 1])
-@pytest.mark.parametrize("case", ["flat", "one_beam_dominates", "ties", "tiny_vocab", "bf16_flat"])
+@pytest.mark.parametrize("case", ["flat", "one_beam_dominates", "ties", "tiny_vocab", "bf16_flat", "bf16_one_beam_dominates",
+                                  "bf16_ties", "bf16_tiny_vocab", "bf16_random"])
 def test_beam_select_degenerate_distributions(log_domain, case):
     """The candidate threshold must stay exact when the distribution is nearly uniform, when one beam's previous score
     dwarfs the others (all winners from one row -- the additive probability scores of model.py:176-181 make this the
@@ -571,11 +644,16 @@ def test_beam_select_degenerate_distributions(log_domain, case):
     B, kin, kout, V = 9, 5, 5, 10000
     g = torch.Generator(device="cuda").manual_seed(11)
     dtype, code = torch.float32, F32
-    if case in ("flat", "bf16_flat"):
+    if case.startswith("bf16_"):            # bf16 rows that fit 100 KB are staged in shared memory (one memory pass)
+        dtype, code = torch.bfloat16, BF16
+        case = case[5:]
+    if case == "flat":
         logits = torch.randn(B * kin, V, device=dev(), generator=g) * 1e-2
         prev = torch.rand(B, kin, device=dev(), generator=g) * 1e-3
-        if case == "bf16_flat":
-            dtype, code = torch.bfloat16, BF16
+    elif case == "random":
+        V = 9999                                                   # not a multiple of 8: partial last chunk
+        logits = torch.randn(B * kin, V, device=dev(), generator=g) * 3
+        prev = torch.rand(B, kin, device=dev(), generator=g)
     elif case == "one_beam_dominates":
         logits = torch.randn(B * kin, V, device=dev(), generator=g) * 0.3
         prev = torch.rand(B, kin, device=dev(), generator=g) * 1e-4
@@ -588,7 +666,10 @@ def test_beam_select_degenerate_distributions(log_domain, case):
         V = 300                                                    # threads 38.. of the block see nothing
         logits = torch.randn(B * kin, V, device=dev(), generator=g)
         prev = torch.rand(B, kin, device=dev(), generator=g) * 0.1
-    logits = logits.to(dtype).contiguous()
+    ldl = (V + 7) // 8 * 8
+    store = torch.zeros(B * kin, ldl, device=dev(), dtype=dtype)
+    store[:, :V] = logits.to(dtype)
+    logits = store[:, :V]
     x = logits.float()
     sm = torch.log_softmax(x, 1) if log_domain else torch.softmax(x, 1)
     cand = (sm.view(B, kin, V) + prev[:, :, None]).view(B, kin * V)
@@ -596,7 +677,7 @@ def test_beam_select_degenerate_distributions(log_domain, case):
     op = torch.empty(B, kout, dtype=torch.int32, device=dev())
     ot = torch.empty(B, kout, dtype=torch.int32, device=dev())
     gap = torch.empty(B, device=dev())
-    N.call("icap_beam_select", code, B, kin, V, logits.data_ptr(), V, prev.data_ptr(), kout, os_.data_ptr(), op.data_ptr(),
+    N.call("icap_beam_select", code, B, kin, V, logits.data_ptr(), ldl, prev.data_ptr(), kout, os_.data_ptr(), op.data_ptr(),
            ot.data_ptr(), gap.data_ptr(), log_domain, S())
     torch.cuda.synchronize()
     idx = op.long() * V + ot.long()
@@ -611,7 +692,8 @@ def test_beam_select_degenerate_distributions(log_domain, case):
         assert torch.allclose(got, ref_s[:, :kout], rtol=1e-6, atol=1e-9)
         assert torch.allclose(os_, ref_s[:, :kout], rtol=1e-5, atol=1e-7)
         assert len({tuple(r) for r in idx.tolist()}) >= 1 and all(len(set(r)) == kout for r in idx.tolist())
-        assert torch.allclose(gap, ref_s[:, kout - 1] - ref_s[:, kout], rtol=1e-2, atol=1e-7)
+        # log domain: scores are ~ -ln(V) = -9.2, one fp32 ulp there is 1e-6 -- the gap is a difference of two of them
+        assert torch.allclose(gap, ref_s[:, kout - 1] - ref_s[:, kout], rtol=1e-2, atol=5e-6 if log_domain else 1e-7)
 
 
 def test_beam_reorder():
