@@ -22,6 +22,7 @@ SIGNATURES = {
     "icap_set_pdl": [I],
     "icap_gemm": [I, I, I, L, L, L, P, L, P, L, P, L, I, P, I, P, L, I, I, P],
     "icap_reload_env": [],
+    "icap_set_gemm_sms": [I],
     "icap_debug_trace": [P, I],
     "icap_mha_fwd": [I, L, L, L, L, L, L, P, L, P, L, P, L, P, L, P, I, F, U, P, P, P],
     "icap_mha_bwd": [I, L, L, L, L, L, L, P, L, P, L, P, L, P, L, P, L, P, L, P, L, P, I, F, U, P, P],
@@ -52,6 +53,11 @@ SIGNATURES = {
     "icap_step_tick": [P, P],
     "icap_scale": [P, L, P, F, P],
     "icap_reciprocal": [P, P, F, P],
+    "icap_im2col_nhwc": [I, P, L, L, L, L, I, I, I, I, P, L, P],
+    "icap_bn_scale_shift": [I, P, L, L, P, P, P, P, P, F, F, I, P, P, P],
+    "icap_bn_act": [I, P, L, L, P, P, P, I, P, P],
+    "icap_maxpool_nhwc": [I, P, L, L, L, L, I, I, I, P, P],
+    "icap_avgpool_nhwc": [I, P, L, L, L, P, P],
 }
 
 

@@ -122,7 +122,10 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
   // phase 1 of the cluster barrier: "this CTA is running" -- waited for right before the first DSMEM store
   if constexpr (CL > 1) cluster_arrive();
-  pdl_prologue();    // everything above overlaps the previous kernel's tail when launched with PDL
+  // PDL: the next kernel of the stream may become resident now (it waits for OUR completion itself); this kernel's own
+  // grid dependency is resolved by the TMA producer below, AFTER it has requested the first stages of W -- the weights
+  // (like bias / gamma / beta) are model parameters, never written by the kernel launched just before
+  pdl_launch_dependents();
 
   float v[NCOL];     // epilogue threads: one row x NCOL columns of s
   const int q = warp & 3, half = warp >= 6 ? 1 : 0;              // TMEM lane quarter / column half of an epilogue warp
@@ -143,11 +146,19 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       // ------------------------------------------------------------ TMA producer
       int s = 0, ph = 0;
+      const int npre = nkb < STAGES ? nkb : STAGES;
+      for (int i = 0; i < npre; ++i) {                                             // W tiles of the first ring round
+        mbar_expect_tx(full_bar + 8 * i, STAGE_BYTES);
+        tma_load_2d(sB + i * B_TILE_BYTES, &tmB, i * BK, n0, full_bar + 8 * i);    // box {64 k, BN n}
+      }
+      pdl_wait();                                                                  // A / residual come from the predecessor
       for (int i = 0; i < nkb; ++i) {
-        mbar_wait(empty_bar + 8 * s, ph ^ 1);
-        mbar_expect_tx(full_bar + 8 * s, STAGE_BYTES);
+        if (i >= npre) {
+          mbar_wait(empty_bar + 8 * s, ph ^ 1);
+          mbar_expect_tx(full_bar + 8 * s, STAGE_BYTES);
+          tma_load_2d(sB + s * B_TILE_BYTES, &tmB, i * BK, n0, full_bar + 8 * s);
+        }
         tma_load_2d(sA + s * A_TILE_BYTES, &tmA, i * BK, m0, full_bar + 8 * s);    // box {64 k, 128 m}
-        tma_load_2d(sB + s * B_TILE_BYTES, &tmB, i * BK, n0, full_bar + 8 * s);    // box {64 k, BN n}
         if (++s == STAGES) { s = 0; ph ^= 1; }
       }
       if (g.res) {

@@ -81,6 +81,7 @@ struct GemmArgs {
   int vec_ok, store_mode;   // store_mode: 0 direct global stores, 1 TMA store, 2 TMA reduce-add
   int debug;                // timing experiments only (ICAP_GEMM_DEBUG): 1 = no TMA loads, 2 = no MMAs, 3 = no epilogue stores
   unsigned long long* trace; // timing experiments (icap_debug_trace): %globaltimer stamps of CTA 0, else null
+  int b_static;             // B / bias are weights the preceding kernel does not write: fetch B before griddepcontrol.wait
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -145,7 +146,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   if (tr && threadIdx.x == 0) tr[1] = gtimer();
-  pdl_prologue();    // everything above overlaps the previous kernel's tail when launched with PDL
+  // PDL: everything above overlaps the previous kernel's tail.  The next kernel of the stream may become resident from
+  // here on (it waits for OUR completion itself); our own grid dependency is resolved by the TMA producer -- with
+  // b_static only after it has requested the B (weight) tiles of its first ring round -- and by the epilogue warps
+  // before they touch C / aux.
+  pdl_launch_dependents();
+  if (warp != 0) pdl_wait();
   if (tr && threadIdx.x == 0) tr[2] = gtimer();
 
   if (warp == 0) {
@@ -153,15 +159,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ------------------------------------------------------------ TMA producer (one per CTA)
       const uint32_t full_leader = TWO ? map_to_cta(full_bar, 0) : full_bar;
       int s = 0, ph = 0;
+      // b_static (single-CTA tiles): the B tiles of the first ring round of this CTA's first tile are requested before
+      // the grid dependency resolves; `pre_b` stages already carry their expect_tx and their B bytes
+      int pre_b = 0;
+      if constexpr (!TWO) {
+        if (g.b_static && (g.debug & 7) != 1 && worker < total_tiles) {
+          const int n0 = (worker % g.tiles_n) * BN;
+          const int kb0 = (worker / (g.tiles_n * g.tiles_m)) * g.kb_per_split;
+          const int nkb = min(g.kb_per_split, nkb_total - kb0);
+          pre_b = min(nkb, STAGES);
+          for (int i = 0; i < pre_b; ++i) {
+            const int k0 = (kb0 + i) * BK;
+            const uint32_t dB = sB + i * CF::B_TILE_BYTES;
+            mbar_expect_tx(full_bar + 8 * i, CF::STAGE_BYTES);
+            if (B_KMAJOR) tma_load_2d(dB, &tmB, k0, n0, full_bar + 8 * i);
+            else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(dB + j * 8192, &tmB, n0 + 64 * j, k0, full_bar + 8 * i);
+            }
+          }
+        }
+      }
+      pdl_wait();
       for (int tile = worker; tile < total_tiles; tile += nworkers) {
         const int n0 = (tile % g.tiles_n) * BN + (int)rank * CF::B_ROWS;       // this CTA's share of the B tile
         const int m0 = ((tile / g.tiles_n) % g.tiles_m) * (BM * NCTA) + (int)rank * BM;
         const int kb0 = (tile / (g.tiles_n * g.tiles_m)) * g.kb_per_split;
         const int nkb = min(g.kb_per_split, nkb_total - kb0);
         for (int i = 0; i < nkb; ++i) {
-          mbar_wait_t<TWO>(empty_bar + 8 * s, ph ^ 1);
           const int k0 = (kb0 + i) * BK;
           const uint32_t dA = sA + s * A_TILE_BYTES, dB = sB + s * CF::B_TILE_BYTES;
+          if (pre_b > 0) {                       // first ring round of the first tile: B is already on its way
+            --pre_b;
+            if (A_KMAJOR) tma_load_2d(dA, &tmA, k0, m0, full_bar + 8 * s);
+            else {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d(dA + j * 8192, &tmA, m0 + 64 * j, k0, full_bar + 8 * s);
+            }
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+            continue;
+          }
+          mbar_wait_t<TWO>(empty_bar + 8 * s, ph ^ 1);
           if ((g.debug & 7) == 1) {                    // timing experiment: barriers only, operands are garbage
             if (rank == 0) mbar_arrive(full_bar + 8 * s);
           } else if constexpr (TWO) {
@@ -444,9 +482,14 @@ int make_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t cols, int6
   return 0;
 }
 
-int g_num_sms = 0, g_num_sms_gen = -1;
+int g_num_sms = 0, g_num_sms_gen = -1, g_sms_limit = 0;
 
+int num_sms_all();
 int num_sms() {
+  const int n = num_sms_all();
+  return (g_sms_limit > 0 && g_sms_limit < n) ? g_sms_limit : n;
+}
+int num_sms_all() {
   if (g_num_sms == 0 || g_num_sms_gen != icap_g_env_gen) {
     g_num_sms_gen = icap_g_env_gen;
     int dev = 0, n = 0;
@@ -513,6 +556,9 @@ int icap_make_tmap_2d(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t co
   return make_tmap(tm, ptr, rows, cols, ld, box_rows, dtype);
 }
 int icap_num_sms() { return num_sms(); }
+// Persistent-grid width of the following icap_gemm(bf16) launches (0 = every SM).  Data parallel: the backward leaves
+// a few SMs to the NCCL all-reduce kernels that run beside it (a 226 KB-smem GEMM CTA cannot share its SM with them).
+extern "C" int icap_set_gemm_sms(int n) { g_sms_limit = n; return 0; }
 
 unsigned long long* icap_trace_slot();
 bool icap_gemm_small_eligible(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int64_t K, int c_dtype, int epi,
@@ -527,6 +573,8 @@ int icap_gemm_bf16_launch(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int6
   // latency-bound shapes (decode steps): the small-footprint kernel that overlaps with its neighbours in the stream
   if (icap_gemm_small_eligible(a_kmajor, b_kmajor, M, N, K, c_dtype, epi, accumulate, split_k, C, ldc))
     return icap_gemm_small_launch(M, N, K, A, lda, B, ldb, C, ldc, bias, (epi & 15) == 1, (epi & 16) != 0, st);
+  static IcapEnv e_nopre;
+  const int b_static = ((epi & 16) != 0 && !e_nopre.get("ICAP_GEMM_NO_B_PREFETCH")) ? 1 : 0;
   epi &= 15;
   ICAP_ARG(lda % 8 == 0 && ldb % 8 == 0, "icap_gemm(bf16): lda/ldb must be multiples of 8 (TMA 16-byte strides)");
   ICAP_ARG(!(a_kmajor == 0 && b_kmajor == 1), "icap_gemm(bf16): (A MN-major, B K-major) is not instantiated");
@@ -605,6 +653,7 @@ int icap_gemm_bf16_launch(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int6
   g.tiles_m = (int)ceil_div64(M, two ? 2 * BM : BM); g.tiles_n = (int)ceil_div64(N, BN);
   g.vec_ok = vec_ok; g.store_mode = store_mode;
   g.debug = e_dbg.geti("ICAP_GEMM_DEBUG", 0);
+  g.b_static = b_static;
   g.trace = icap_trace_slot();
 #define GO2(BNV, TW, AK, BKM)                                                                          \
   (c_dtype == ICAP_F32 ? launch<BNV, TW, AK, BKM, float>(ta, tb, tc, g, st)                              \

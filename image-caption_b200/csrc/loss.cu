@@ -183,35 +183,14 @@ template <typename T>
 __global__ void __launch_bounds__(NT)
 beam_select_kernel(int kin, int V, const T* __restrict__ logits, int64_t ldl, const float* __restrict__ prev,
                    int kout, float* __restrict__ out_score, int* __restrict__ out_parent, int* __restrict__ out_token,
-                   float* __restrict__ gap, int log_domain, int stage_ld) {
+                   float* __restrict__ gap, int log_domain) {
   pdl_prologue();
-  // stage_ld > 0: the kin rows of this image are first copied into shared memory with cp.async -- every thread has
-  // ~24 independent 16-byte copies in flight, ONE memory round trip -- and the statistics pass, the candidate pass and
-  // the rare exact pass below all read the staged copy.  (Straight from global memory each pass is a chain of ~5
-  // dependent 16-byte loads per thread and row: 54-60 us per decode step at 512 images x 5 beams, r2 timeline.)
-  extern __shared__ __align__(16) uint8_t bs_stage[];
-  if (stage_ld > 0) {
-    const int cpr = stage_ld / 8;                       // 16-byte chunks per staged row (stage_ld = V rounded up to 8)
-    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(bs_stage);
-    for (int idx = threadIdx.x; idx < kin * cpr; idx += NT) {
-      const int r = idx / cpr, c = idx - r * cpr;
-      const T* src = logits + ((int64_t)blockIdx.x * kin + r) * ldl + c * 8;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + (uint32_t)idx * 16u), "l"(src) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-  }
-  auto row_ptr = [&](int r) -> const T* {
-    return stage_ld > 0 ? reinterpret_cast<const T*>(bs_stage) + (int64_t)r * stage_ld
-                        : logits + ((int64_t)blockIdx.x * kin + r) * ldl;
-  };
   __shared__ float red[NT / 32];
   __shared__ float s_mx[KMAX], s_den[KMAX];
   __shared__ float h_s[NT];
   __shared__ int h_i[NT], h_t[NT];
   const int b = blockIdx.x;
-  const bool vec = stage_ld > 0 || (((uintptr_t)logits % 16 == 0) && (ldl * sizeof(T)) % 16 == 0);
+  const bool vec = ((uintptr_t)logits % 16 == 0) && (ldl * sizeof(T)) % 16 == 0;
   const int L = kout + 1;
   __shared__ float s_w1[KMAX][NT / 32], s_w2[KMAX][NT / 32];   // two largest logits of every (row, warp)
   __shared__ float s_we[KMAX][NT / 32];
@@ -220,7 +199,7 @@ beam_select_kernel(int kin, int V, const T* __restrict__ logits, int64_t ldl, co
   __shared__ int c_n;
   __shared__ float s_tau;
   for (int r = 0; r < kin; ++r) {
-    const T* x = row_ptr(r);
+    const T* x = logits + ((int64_t)b * kin + r) * ldl;
     // ONE pass: the thread's two largest logits (t1 >= t2) and its online softmax sum  es = sum exp(x - t1)
     float t1 = -INFINITY, t2 = -INFINITY, es = 0.f;
     for (int j = threadIdx.x * 8; j < V; j += NT * 8) {
@@ -312,7 +291,7 @@ beam_select_kernel(int kin, int V, const T* __restrict__ logits, int64_t ldl, co
     __syncthreads();
     const float tau = s_tau;
     for (int r = 0; r < kin; ++r) {
-      const T* x = row_ptr(r);
+      const T* x = logits + ((int64_t)b * kin + r) * ldl;
       const float mx = s_mx[r], den = s_den[r], pv = prev ? prev[b * kin + r] : 0.f;
       float tl;                                        // logit whose score is tau, minus a safety margin
       if (log_domain) tl = tau - pv + mx + den;
@@ -375,7 +354,7 @@ beam_select_kernel(int kin, int V, const T* __restrict__ logits, int64_t ldl, co
   float worst_s = -INFINITY;               // == lst[L-1]: the entry a candidate has to beat
   int worst_i = 0x7fffffff;
   for (int r = 0; r < kin; ++r) {
-    const T* x = row_ptr(r);
+    const T* x = logits + ((int64_t)b * kin + r) * ldl;
     const float mx = s_mx[r], den = s_den[r], pv = prev ? prev[b * kin + r] : 0.f;
     // Cheap pre-filter in the logit domain: the score is monotonic in the logit, so only logits above
     //   tl = logit whose score equals the current worst list entry (minus a 1e-3 safety margin)
@@ -578,25 +557,12 @@ extern "C" int icap_beam_select(int dtype, int64_t B, int64_t kin, int64_t V, co
   ICAP_ARG(kin >= 1 && kin <= KMAX && kout >= 1 && kout <= KMAX, "icap_beam_select: beam width must be in [1, %d]", KMAX);
   ICAP_ARG(kin * V > kout, "icap_beam_select: fewer candidates than beams");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == ICAP_F32) {
+  if (dtype == ICAP_F32)
     icap_launch(beam_select_kernel<float>, (unsigned)B, NT, 0, st, (int)kin, (int)V, (const float*)logits, ldl, prev_score,
-                                                          (int)kout, out_score, out_parent, out_token, gap, log_domain, 0);
-  } else {
-    // bf16 rows that fit (kin * V * 2 <= 100 KB, two blocks per SM) are staged in shared memory: one memory pass
-    const int64_t stage_ld = (V + 7) / 8 * 8;
-    size_t smem = (size_t)(kin * stage_ld * 2);
-    const bool staged = smem <= 100 * 1024 && (uintptr_t)logits % 16 == 0 && ldl % 8 == 0 && ldl >= stage_ld &&
-                        !env_flag<6>("ICAP_BEAM_SELECT_NO_STAGE");
-    if (!staged) smem = 0;
-    static size_t cur = 0;
-    if (smem > cur) {
-      ICAP_CUDA(cudaFuncSetAttribute(beam_select_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      cur = 100 * 1024;
-    }
-    icap_launch(beam_select_kernel<bf16>, (unsigned)B, NT, smem, st, (int)kin, (int)V, (const bf16*)logits, ldl, prev_score,
-                                                         (int)kout, out_score, out_parent, out_token, gap, log_domain,
-                                                         staged ? (int)stage_ld : 0);
-  }
+                                                          (int)kout, out_score, out_parent, out_token, gap, log_domain);
+  else
+    icap_launch(beam_select_kernel<bf16>, (unsigned)B, NT, 0, st, (int)kin, (int)V, (const bf16*)logits, ldl, prev_score,
+                                                         (int)kout, out_score, out_parent, out_token, gap, log_domain);
   ICAP_LAUNCH_CHECK("icap_beam_select");
   return 0;
 }

@@ -210,6 +210,9 @@ class CaptionEngine:
         # data parallel: called after every backward closure with the lowest flat offset it wrote (or None);
         # gradients complete from the END of the flat buffer towards its start (reverse registration order)
         self.bucket_hook: Optional[Callable[[Optional[int]], None]] = None
+        # data parallel: persistent-GEMM grid width during the backward (None = all SMs); the SMs left over run the
+        # NCCL all-reduce kernels of the gradient buckets (DataParallel sets it)
+        self.bwd_gemm_sms: Optional[int] = None
         for k in ("encode_q_k_dim", "encode_v_dim", "decode_q_k_dim", "decode_v_dim"):
             assert getattr(cfg, k) % 8 == 0, f"{k} must be a multiple of 8"
         assert cfg.encode_input_size == cfg.decode_input_size, \
@@ -481,7 +484,8 @@ class CaptionEngine:
                 self.add_grad(xq, ds)
                 self.wgrad(da, att, self.g(prefix + ".joint_linear.weight"), d, dv_tot, Mq)
                 datt = self.new(Mq, dv_tot)
-                self.gemm(da, True, self.w(prefix + ".joint_linear.weight"), dv_tot, False, Mq, dv_tot, d, datt)
+                self.gemm(da, True, self.w(prefix + ".joint_linear.weight"), dv_tot, False, Mq, dv_tot, d, datt,
+                          b_static=True)
                 esz = qkv.element_size()
                 if self_attn:
                     dqkv = self.new(Mq, nqkv)
@@ -491,7 +495,7 @@ class CaptionEngine:
                          self.step_dev.data_ptr(), self._s())
                     self.wgrad(dqkv, xq, self.g(wq), nqkv, d, Mq)
                     dx = self.new(Mq, d)
-                    self.gemm(dqkv, True, self.w(wq), d, False, Mq, d, nqkv, dx)
+                    self.gemm(dqkv, True, self.w(wq), d, False, Mq, d, nqkv, dx, b_static=True)
                     self.add_grad(xq, dx)
                 else:
                     dq = self.new(Mq, dk_tot)
@@ -502,7 +506,7 @@ class CaptionEngine:
                          self.step_dev.data_ptr(), self._s())
                     self.wgrad(dq, xq, self.g(wq), dk_tot, d, Mq)
                     dx = self.new(Mq, d)
-                    self.gemm(dq, True, self.w(wq), d, False, Mq, d, dk_tot, dx)
+                    self.gemm(dq, True, self.w(wq), d, False, Mq, d, dk_tot, dx, b_static=True)
                     self.add_grad(xq, dx)
                     self.wgrad(dkv, xkv, self.g(wk), dk_tot + dv_tot, d, Mk)
                     # all decoder layers accumulate into ONE gradient buffer of the encoder output
@@ -543,11 +547,11 @@ class CaptionEngine:
                 self.add_grad(x, ds)
                 self.wgrad(da, h, self.g(w2), d, hidden, M)
                 dh = self.new(M, hidden)
-                self.gemm(da, True, self.w(w2), hidden, False, M, hidden, d, dh, epi=N.EPI_RELU_MASK, aux=h)
+                self.gemm(da, True, self.w(w2), hidden, False, M, hidden, d, dh, epi=N.EPI_RELU_MASK, aux=h, b_static=True)
                 self.side_call("icap_colsum", self.act, M, hidden, dh.data_ptr(), hidden, self.g(b1))
                 self.wgrad(dh, gin, self.g(w1), hidden, d, M)
                 dx = self.new(M, d)
-                self.gemm(dh, True, self.w(w1), d, False, M, d, hidden, dx)
+                self.gemm(dh, True, self.w(w1), d, False, M, d, hidden, dx, b_static=True)
                 self.add_grad(gin, dx)
             # the move_first tail completes out of order; image_encoder.* is registered BEFORE encoder.feature_embedding /
             # encoder.norm, whose gradients are only final at the very end of the backward (report_lo=False)
@@ -867,7 +871,7 @@ class CaptionEngine:
             self.wgrad(logits, dec, self.g("classifer.weight"), V, d, M, ld_dy=ldl)
             self.side_call("icap_colsum", self.act, M, V, logits.data_ptr(), ldl, self.g("classifer.bias"))
             dx = self.new(M, d)
-            self.gemm(logits, True, self.w("classifer.weight"), d, False, M, d, V, dx, lda=ldl)
+            self.gemm(logits, True, self.w("classifer.weight"), d, False, M, d, V, dx, lda=ldl, b_static=True)
             self.add_grad(dec, dx)
         bwd.lo = self.offsets["classifer.weight"]
         self.tape.append(bwd)
@@ -892,12 +896,17 @@ class CaptionEngine:
                 self._side = torch.cuda.Stream(device=self.dev)
             self._bwd_side = self._side
             self._bwd_side.wait_stream(main)          # g32 has been zeroed / the forward is complete
+        limit = self.bwd_gemm_sms if self.bucket_hook is not None else None
+        if limit:
+            call("icap_set_gemm_sms", int(limit))
         try:
             for fn in reversed(self.tape):
                 fn()
                 if self.bucket_hook is not None:
                     self.bucket_hook(getattr(fn, "lo", None))
         finally:
+            if limit:
+                call("icap_set_gemm_sms", 0)
             if self._bwd_side is not None:
                 main.wait_stream(self._bwd_side)      # every weight gradient has landed in g32
                 self._bwd_side = None

@@ -496,6 +496,11 @@ class DataParallel:
         self.inv = torch.zeros(1, dtype=torch.float32, device=eng.dev)
         if bucket_mb is None:
             bucket_mb = float(os.environ.get("ICAP_DP_BUCKET_MB", "48"))
+        # SMs left to NCCL while the backward's persistent GEMMs run (0 = none reserved)
+        reserve = int(os.environ.get("ICAP_DP_RESERVE_SMS", "0"))
+        if reserve > 0:
+            sms = torch.cuda.get_device_properties(eng.dev).multi_processor_count
+            eng.bwd_gemm_sms = max(16, sms - reserve)
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
         self.overlap = overlap and os.environ.get("ICAP_DP_OVERLAP", "1") != "0"
         self.comm: Optional[torch.cuda.Stream] = None

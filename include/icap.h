@@ -57,6 +57,9 @@ int icap_gemm(int ab_dtype, int a_kmajor, int b_kmajor, int64_t M, int64_t N, in
  * of every following tcgen05 GEMM launch into buf (device memory, 16 x uint64 per slot, slot = launch number % nslots;
  * buf = NULL: off). */
 int icap_reload_env(void);
+/* Width of the persistent grid of the following icap_gemm(bf16) launches (0 = all SMs): data parallel training leaves a
+ * few SMs to the NCCL all-reduce kernels that overlap the backward. */
+int icap_set_gemm_sms(int n);
 int icap_debug_trace(unsigned long long* buf, int nslots);
 
 /* Fused multi-head attention over packed projections (one CTA per (batch, head)).
@@ -106,6 +109,8 @@ int icap_add_ln_bwd_params(int act_dtype, int64_t M, int64_t d, const void* dy1,
  * with its own TMA -> tcgen05.mma main loop; the row statistics are exchanged through distributed shared memory.
  * sum_out (nullable) receives the pre-norm sum, mean_out / rstd_out (nullable, fp32 [M]) the statistics: exactly
  * what icap_add_ln_fwd(write_sum=1) leaves for icap_add_ln_bwd, with the same dropout decisions (seed, element).
+ * W, bias, gamma, beta are model parameters: they must not be written by the kernel launched just before on this stream
+ * (the kernel requests its first W stages before its grid dependency has resolved).
  * Returns -2 (nothing launched) for other shapes / unaligned rows: call icap_gemm + icap_add_ln_fwd instead.
  * Replaces joint_linear / position_wise_2 -> Dropout -> LayerNorm(out + residual) [-> *= non_pad_mask],
  * modules.py:86-90,117-120,154-155,203-204. */
@@ -220,6 +225,28 @@ int icap_step_tick(int* step_dev, void* stream);
 int icap_scale(float* x, int64_t n, const float* s_dev, float s, void* stream);
 /* out[0] = numerator / x[0]  (data parallel: 1 / all-reduced token count, consumed by icap_adam_step as gscale_dev). */
 int icap_reciprocal(const float* x, float* out, float numerator, void* stream);
+
+/* ---- region feature extractor (ResNet-101 trunk over the region crops, core/preprocess.py:26-62).
+ * Activations are NHWC matrices [N*H*W, C]; every convolution is icap_gemm over the activation matrix itself (1x1) or
+ * over the patch matrix gathered by icap_im2col_nhwc (3x3, 7x7, strided 1x1):
+ *   out[(n, ho, wo), (ky, kx, c)] = x[n, ho*stride - pad + ky, wo*stride - pad + kx, c], zero outside the image and in
+ *   the columns kh*kw*C .. ldo-1 (ldo = kh*kw*C rounded up to 8 so that TMA can read the rows).
+ * icap_bn_scale_shift: per-channel scale = gamma / sqrt(var + eps), shift = beta - mean * scale.  train != 0: mean / var
+ *   are the statistics of the M rows of x (what the reference's extractor uses: it never calls .eval(),
+ *   preprocess.py:35-40), accumulated in the zero-initialised fp64 scratch sums[2*C] (left zeroed again), running
+ *   statistics updated with `momentum` like nn.BatchNorm2d; train == 0: running statistics.
+ * icap_bn_act: y = act(x * scale[c] + shift[c] + residual) (residual nullable, act = ReLU when relu != 0).
+ * icap_maxpool_nhwc / icap_avgpool_nhwc: the 3x3/2 max pool after the stem and the global average pool (fp32 out). */
+int icap_im2col_nhwc(int dtype, const void* x, int64_t N, int64_t H, int64_t W, int64_t C, int kh, int kw, int stride,
+                     int pad, void* out, int64_t ldo, void* stream);
+int icap_bn_scale_shift(int dtype, const void* x, int64_t M, int64_t C, double* sums, const float* gamma, const float* beta,
+                        float* running_mean, float* running_var, float momentum, float eps, int train, float* scale,
+                        float* shift, void* stream);
+int icap_bn_act(int dtype, const void* x, int64_t M, int64_t C, const float* scale, const float* shift, const void* residual,
+                int relu, void* y, void* stream);
+int icap_maxpool_nhwc(int dtype, const void* x, int64_t N, int64_t H, int64_t W, int64_t C, int k, int stride, int pad,
+                      void* y, void* stream);
+int icap_avgpool_nhwc(int dtype, const void* x, int64_t N, int64_t HW, int64_t C, float* y, void* stream);
 
 #ifdef __cplusplus
 }

@@ -113,3 +113,26 @@ def test_product_never_imports_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, fn)).read()
                 assert "oracle" not in src.replace("# oracle", ""), os.path.join(dirpath, fn)
+
+
+def test_resnet_extractor_state_dict_matches_torchvision():
+    """the drop-in ResnetExtractor exposes exactly the parameter / buffer names and shapes of the
+    reference's nn.Sequential(*resnet101.children()[:9]) (preprocess.py:37-40), so pretrained trunks load unchanged."""
+    import sys
+    tv = pytest.importorskip("torchvision")
+    pkg_dir = os.path.join(ROOT, "image-caption_b200")
+    sys.path.insert(0, pkg_dir)
+    try:
+        from core.preprocess import ResnetExtractor
+        ext = ResnetExtractor()
+        ref = torch.nn.Sequential(*list(tv.models.resnet101(weights=None).children())[:9])
+        ours, theirs = ext.submodule.state_dict(), ref.state_dict()
+        assert list(ours.keys()) == list(theirs.keys())
+        for k in ours:
+            assert tuple(ours[k].shape) == tuple(theirs[k].shape), k
+        ext.submodule.load_state_dict(theirs)
+        assert ext.image_size == 224 and ext.training
+    finally:
+        sys.path.remove(pkg_dir)
+        for m in [k for k in sys.modules if k == "core" or k.startswith("core.")]:
+            sys.modules.pop(m)

@@ -144,6 +144,24 @@ def test_gemm_bf16_small_footprint_kernel(mode, monkeypatch):
         assert _gemm_case(BF16, 1, 1, 5376, 10000, 512, c_dtype=BF16, bias=True, epi=N.EPI_B_STATIC) < 6e-3
 
 
+def test_gemm_bf16_limited_grid_and_weight_prefetch(monkeypatch):
+    """icap_set_gemm_sms (data parallel: the backward's persistent GEMMs leave SMs to NCCL) and the B_STATIC flag on the
+    persistent kernel (weight tiles of the first ring round requested before the grid dependency): same results."""
+    setenv(monkeypatch, "ICAP_GEMM_SMALL", "0")
+    try:
+        for sms in (0, 132, 17):
+            N.call("icap_set_gemm_sms", sms)
+            for epi in (0, N.EPI_B_STATIC):
+                assert _gemm_case(BF16, 1, 1, 9216, 2048, 512, c_dtype=BF16, bias=True, epi=1 | epi) < 6e-3
+                assert _gemm_case(BF16, 1, 0, 5376, 512, 2048, c_dtype=BF16, epi=epi) < 6e-3
+                assert _gemm_case(BF16, 1, 0, 4000, 1000, 200, c_dtype=F32, accumulate=1, epi=epi) < 1e-5
+                assert _gemm_case(BF16, 1, 1, 300, 264, 72, c_dtype=BF16, epi=epi) < 6e-3        # K shorter than the ring
+            # fewer SMs -> fewer K splits -> longer fp32 accumulation chains: 9216-term dot products round to ~1e-5
+            assert _gemm_case(BF16, 0, 0, 2048, 512, 9216, accumulate=1, split_k=0) < 3e-5
+    finally:
+        N.call("icap_set_gemm_sms", 0)
+
+
 def test_gemm_bf16_vocab_shapes():
     """classifier-like shapes: N = V not a multiple of the tile, padded leading dimension."""
     M, V, d, ldl = 300, 1000, 512, 1000
@@ -644,7 +662,7 @@ def test_beam_select_degenerate_distributions(log_domain, case):
     B, kin, kout, V = 9, 5, 5, 10000
     g = torch.Generator(device="cuda").manual_seed(11)
     dtype, code = torch.float32, F32
-    if case.startswith("bf16_"):            # bf16 rows that fit 100 KB are staged in shared memory (one memory pass)
+    if case.startswith("bf16_"):            # bf16 logits (the decode path)
         dtype, code = torch.bfloat16, BF16
         case = case[5:]
     if case == "flat":

@@ -450,10 +450,15 @@ def test_train_step_fused_auto_graph_equals_eager(monkeypatch):
         if q.is_floating_point() and q.dim() >= 2:
             assert float((q - out["1"][1][n]).norm()) <= 1e-3 * float(q.norm()), n
     assert out["0"][2]["step"] == out["1"][2]["step"] == len(batches)
+    # The trajectory itself is bimodal at the 4e-3 level, eagerly AND through graphs (tools/graph_eager_repro.py): the
+    # fp32 atomics of the split-K weight gradients round differently from run to run, the weights after step 1 then
+    # differ by <= 6e-8, and ONE ReLU pre-activation of batch 2 sits within that distance of zero -- its mask bit flips
+    # and moves every gradient by ~1e-4.  A leaked warm-up step (what this test is about) adds a whole extra gradient
+    # to the moments: ~0.1-1 of their norm.
     ma, mb = out["0"][2]["exp_avg"], out["1"][2]["exp_avg"]
-    assert float((ma - mb).norm()) <= 1e-4 * float(ma.norm())
+    assert float((ma - mb).norm()) <= 2e-2 * float(ma.norm())
     va, vb = out["0"][2]["exp_avg_sq"], out["1"][2]["exp_avg_sq"]
-    assert float((va - vb).norm()) <= 1e-4 * float(va.norm())
+    assert float((va - vb).norm()) <= 2e-2 * float(va.norm())
 
 
 def test_model_a_bf16_batch256_vs_oracle():
@@ -555,3 +560,57 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(N, "LIB_PATH", "/nonexistent/libicap.so")
     with pytest.raises(N.IcapError):
         N.lib()
+
+
+@pytest.mark.parametrize("mode", ["train_fp32", "eval_fp32", "eval_bf16", "train_bf16"])
+def test_resnet_extractor_vs_torchvision(mode):
+    """the ResNet-101 region feature extractor (core/preprocess.py:26-62) on libicap -- every
+    convolution one icap_gemm over an NHWC (patch) matrix, BatchNorm / ReLU / residual / pooling kernels of conv.cu --
+    against torchvision's resnet101 children[:9] with the same random-init weights on the CPU.  The reference never
+    calls .eval() on its extractor, so the default is batch-statistics BatchNorm ("train"); eval uses running statistics
+    (non-trivial ones here).  fp32 mode: 2e-3 of the feature scale.  bf16 mode (tcgen05 GEMMs, bf16 activations through
+    101 layers): 3e-2 with running statistics; with batch statistics of only 3 crops a random-init trunk is
+    ill-conditioned -- torch's OWN bf16 execution of the same module differs from its fp32 one by 0.31 of the feature
+    scale (cosine 0.988; calibrated on the CPU) -- so that case checks the direction (cosine > 0.97) and a loose bound."""
+    import sys
+    tv = pytest.importorskip("torchvision")
+    pkg_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "image-caption_b200")
+    sys.path.insert(0, pkg_dir)
+    try:
+        from core.preprocess import ResnetExtractor
+        torch.manual_seed(0)
+        ref = torch.nn.Sequential(*list(tv.models.resnet101(weights=None).children())[:9])
+        g = torch.Generator().manual_seed(1)
+        for m_ in ref.modules():                      # non-trivial affine / running statistics
+            if isinstance(m_, torch.nn.BatchNorm2d):
+                m_.weight.data.uniform_(0.5, 1.5, generator=g)
+                m_.bias.data.uniform_(-0.2, 0.2, generator=g)
+                m_.running_mean.uniform_(-0.1, 0.1, generator=g)
+                m_.running_var.uniform_(0.5, 1.5, generator=g)
+        ext = ResnetExtractor()
+        ext.submodule.load_state_dict(ref.state_dict())
+        ext.precision = "bf16" if mode.endswith("bf16") else "fp32"
+        x = torch.randn(3, 3, 224, 224, generator=g)
+        train = mode.startswith("train")
+        ref.train(train)
+        ext.train(train)
+        with torch.no_grad():
+            want = ref(x).flatten(1)
+        got = torch.from_numpy(ext(x))
+        assert got.shape == (3, 2048)
+        err = float((got - want).abs().max() / want.abs().max())
+        print(f"resnet101 trunk [{mode}]: max abs err / max |feature| = {err:.2e}, {ext.launches} launches")
+        cos = float(torch.nn.functional.cosine_similarity(got.flatten().double(), want.flatten().double(), dim=0))
+        if mode == "train_bf16":
+            assert cos > 0.97 and err < 0.6, (cos, err)
+        else:
+            assert err < (3e-2 if mode.endswith("bf16") else 2e-3), err
+        if train and mode != "train_bf16":            # running statistics were updated like nn.BatchNorm2d does
+            sd_o, sd_r = ext.submodule.state_dict(), ref.state_dict()
+            for k in ("1.running_mean", "1.running_var", "7.2.bn3.running_var"):
+                assert torch.allclose(sd_o[k].cpu(), sd_r[k], rtol=5e-2 if mode.endswith("bf16") else 2e-3, atol=1e-3), k
+            assert int(sd_o["1.num_batches_tracked"]) == 1
+    finally:
+        sys.path.remove(pkg_dir)
+        for m_ in [k for k in sys.modules if k == "core" or k.startswith("core.")]:
+            sys.modules.pop(m_)

@@ -65,7 +65,7 @@ def main():
             print(f"   {short:28s} start {s - seg[0][1]:8.2f}  dur {d:7.2f}  gap {g:6.2f}")
     agg = {}
     for n, s, d, g in rows:
-        k = n.split("(")[0][:70]
+        k = n.replace("(anonymous namespace)::", "").replace("void ", "").split("(")[0][:70]
         a = agg.setdefault(k, [0, 0.0, 0.0])
         a[0] += 1; a[1] += d; a[2] += max(0.0, g)
     print("-- whole decode, by kernel: launches, total us, total gap-before us")

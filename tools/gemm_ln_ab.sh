@@ -11,5 +11,5 @@ for cfg in "0 auto" "2 auto" "2 256" "2 128"; do
   set -- $cfg
   echo "== train ICAP_GEMM_LN=$1 BN=$2"
   if [ "$2" = auto ]; then unset ICAP_GEMM_LN_BN; else export ICAP_GEMM_LN_BN=$2; fi
-  ICAP_GEMM_LN=$1 timeout 200 python bench.py --no-decode --no-cpu-baseline --steps 30 2>/dev/null | python tools/_pl.py
+  ICAP_GEMM_LN=$1 timeout 200 python bench.py --no-decode --no-cpu-baseline --steps 30 2>/dev/null 
 done

@@ -1,0 +1,77 @@
+"""Device timeline of ONE replay of the graphed training step (CUPTI through torch.profiler): per-kernel totals, the
+time during which NO kernel is running, and the busy time per stream -- what the 4.4 ms step is made of.
+    python tools/train_timeline.py [--batch 256] [--out gpurun_out/train_timeline.csv]"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import icap_loader  # noqa: E402
+from oracle import caption_oracle as O  # noqa: E402  (synthetic inputs only)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--out", default="gpurun_out/train_timeline.csv")
+    args = ap.parse_args()
+    pkg = icap_loader.load()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    kw = dict(num_vocab=10000, max_length=22, encode_dim_positions=84, encode_dim_features=2048, output_name="bench",
+              dropout=0.2)
+    model = pkg.Transformer(device=dev, **kw).to(dev).train()
+    f, p, c = O.synthetic_batch(args.batch, 36, 2048, 84, 22, 10000, seed=1234)
+    f, p, c = f.to(dev), p.to(dev), c.to(dev)
+    gs = pkg.GraphedTrainStep(model, args.batch, 36, 22, lr=5e-4)
+    gs.load(f, p, c)
+    for _ in range(5):
+        gs.step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        gs.step()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"un-profiled: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per step")
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        gs.step()
+        torch.cuda.synchronize()
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range is not None]
+    evs = [e for e in evs if "memcpy" not in e.name.lower()]
+    evs.sort(key=lambda e: e.time_range.start)
+    t0 = evs[0].time_range.start
+    end = max(e.time_range.end for e in evs)
+    with open(args.out, "w") as fh:
+        fh.write("idx,kernel,start_us,dur_us\n")
+        for i, e in enumerate(evs):
+            fh.write(f"{i},\"{e.name[:100]}\",{e.time_range.start - t0:.2f},{e.time_range.end - e.time_range.start:.2f}\n")
+    # union of busy intervals
+    busy, cur_s, cur_e = 0.0, None, None
+    for e in evs:
+        s, en = e.time_range.start, e.time_range.end
+        if cur_e is None or s > cur_e:
+            if cur_e is not None:
+                busy += cur_e - cur_s
+            cur_s, cur_e = s, en
+        else:
+            cur_e = max(cur_e, en)
+    busy += cur_e - cur_s
+    print(f"{len(evs)} kernels, {end - t0:.1f} us first start -> last end (profiled), some kernel running {busy:.1f} us")
+    agg = {}
+    for e in evs:
+        k = e.name.replace("(anonymous namespace)::", "").replace("void ", "").split("(")[0][:70]
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1
+        a[1] += e.time_range.end - e.time_range.start
+    print("launches  total_us  kernel   (durations include the time a PDL-launched kernel waits for its predecessor)")
+    for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"   {a[0]:5d} {a[1]:9.1f}  {k}")
+
+
+if __name__ == "__main__":
+    main()
