@@ -58,6 +58,10 @@ SIGNATURES = {
     "icap_bn_act": [I, P, L, L, P, P, P, I, P, P],
     "icap_maxpool_nhwc": [I, P, L, L, L, L, I, I, I, P, P],
     "icap_avgpool_nhwc": [I, P, L, L, L, P, P],
+    "icap_p2p_barrier": [P, I, I, P, P, P],
+    "icap_p2p_reduce_scatter": [P, I, I, L, L, I, P],
+    "icap_p2p_all_gather": [P, I, I, L, L, I, P],
+    "icap_p2p_allreduce_nvls": [P, I, I, L, L, I, P],
 }
 
 

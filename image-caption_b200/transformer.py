@@ -451,12 +451,20 @@ class GradBuckets:
     that closure wrote, and answers with the slice [lo, hi) that may be all-reduced now (or None).  Every element
     is handed out exactly once; `flush()` returns the remaining prefix."""
 
-    def __init__(self, total_elems: int, bucket_elems: int):
+    def __init__(self, total_elems: int, bucket_elems: int, tail_elems: Optional[int] = None,
+                 tail_below: Optional[int] = None):
         self.prev_lo = int(total_elems)
         self.bucket_elems = int(bucket_elems)
+        # The last slices of a step cannot hide behind anything (the backward is over): below offset `tail_below` the
+        # bucket threshold drops to `tail_elems`, so that the final flush is a few MB instead of up to a whole bucket.
+        self.tail_elems = int(tail_elems) if tail_elems else self.bucket_elems
+        self.tail_below = int(tail_below) if tail_below else 0
 
     def on_done(self, lo: Optional[int]):
-        if lo is None or lo >= self.prev_lo or self.prev_lo - lo < self.bucket_elems:
+        if lo is None or lo >= self.prev_lo:
+            return None
+        need = self.tail_elems if lo < self.tail_below else self.bucket_elems
+        if self.prev_lo - lo < need:
             return None
         out = (int(lo), self.prev_lo)
         self.prev_lo = int(lo)
@@ -468,6 +476,61 @@ class GradBuckets:
         out = (0, self.prev_lo)
         self.prev_lo = 0
         return out
+
+
+class PeerReduce:
+    """All-reduce of the flat gradient buffer over NVLink peer memory with libicap's own kernels (csrc/p2p.cu) instead of
+    NCCL.  The gradient buffer and a few flag words are allocated as torch symmetric memory (CUDA VMM allocations that
+    `rendezvous` maps into every rank of the group); the kernels get the peers' device pointers.  They need no shared
+    memory, so they run beside the backward's persistent GEMMs."""
+
+    def __init__(self, dist, eng: CaptionEngine):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm_mem
+        self.dist, self.rank, self.world = dist, dist.get_rank(), dist.get_world_size()
+        assert self.world <= 8
+        dev = eng.dev
+        self.g32 = symm_mem.empty(eng.n_flat + 8, dtype=torch.float32, device=dev)
+        self.flags = symm_mem.empty(64, dtype=torch.int32, device=dev)
+        self._hg = symm_mem.rendezvous(self.g32, dist.group.WORLD)
+        self._hf = symm_mem.rendezvous(self.flags, dist.group.WORLD)
+        self.g32.zero_()
+        self.flags.zero_()
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.err = torch.zeros(1, dtype=torch.int32, device=dev)
+        gp, fp = [int(x) for x in self._hg.buffer_ptrs], [int(x) for x in self._hf.buffer_ptrs]
+        assert gp[self.rank] == self.g32.data_ptr() and len(gp) == self.world
+        arr = ctypes.c_void_p * 8
+        self._gp = arr(*(gp + [None] * (8 - self.world)))
+        self._fp = arr(*(fp + [None] * (8 - self.world)))
+        self.gp = ctypes.cast(self._gp, ctypes.c_void_p)
+        self.fp = ctypes.cast(self._fp, ctypes.c_void_p)
+        self.ctas = int(os.environ.get("ICAP_DP_PEER_CTAS", "148"))
+        # NVSwitch multicast mapping of the gradient buffer (0 when the fabric has none): in-switch reduction
+        self.mc = int(getattr(self._hg, "multicast_ptr", 0) or 0)
+        self.use_nvls = self.mc != 0 and os.environ.get("ICAP_DP_PEER_NVLS", "1") != "0"
+        torch.cuda.synchronize(dev)
+        dist.barrier()                                   # every rank's flag words are zero before anyone signals
+
+    def barrier(self, stream: int) -> None:
+        from ._native import call
+        call("icap_p2p_barrier", self.fp, self.rank, self.world, self.epoch.data_ptr(), self.err.data_ptr(), stream)
+
+    def all_reduce(self, lo: int, hi: int, stream: int) -> None:
+        """Reduce [lo, hi) on `stream`; the result may be read after ONE more barrier() (end of the step)."""
+        from ._native import call
+        self.barrier(stream)
+        if self.use_nvls:
+            call("icap_p2p_allreduce_nvls", self.mc, self.rank, self.world, lo, hi, self.ctas, stream)
+            return
+        call("icap_p2p_reduce_scatter", self.gp, self.rank, self.world, lo, hi, self.ctas, stream)
+        self.barrier(stream)
+        call("icap_p2p_all_gather", self.gp, self.rank, self.world, lo, hi, self.ctas, stream)
+
+    def check(self) -> None:
+        e = int(self.err)
+        if e:
+            raise IcapError(f"peer all-reduce: rank {e - 1} never reached a barrier (rank {self.rank} gave up after 2 s)")
 
 
 class DataParallel:
@@ -502,7 +565,21 @@ class DataParallel:
             sms = torch.cuda.get_device_properties(eng.dev).multi_processor_count
             eng.bwd_gemm_sms = max(16, sms - reserve)
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
+        self.tail_elems = int(min(bucket_mb, float(os.environ.get("ICAP_DP_TAIL_MB", "8"))) * (1 << 20) / 4)
         self.overlap = overlap and os.environ.get("ICAP_DP_OVERLAP", "1") != "0"
+        # Gradient exchange dtype: fp32 (default) or, with ICAP_DP_GRAD_DTYPE=bf16, every bucket rounded to bf16 into a
+        # staging buffer, all-reduced there and widened back (half the NVLink bytes; the token count in the tail slot
+        # still travels in fp32).  Measured on 2 x B200: 4.736 vs 4.728 ms/step -- the exposed 0.29 ms is not volume
+        # (profiles/r2_summary.md), so the exact fp32 exchange stays the default.
+        want = os.environ.get("ICAP_DP_GRAD_DTYPE", "fp32")
+        # ICAP_DP_PEER=1: the gradient buckets are reduced by libicap's own NVLink peer-memory kernels (PeerReduce)
+        self.peer: Optional[PeerReduce] = None
+        if os.environ.get("ICAP_DP_PEER", "0") == "1" and self.world <= 8 and eng.dev.type == "cuda":
+            self.peer = PeerReduce(dist, eng)
+            eng.g32 = self.peer.g32                      # the engine's gradient buffer IS the exported one
+            want = "fp32"
+        self.comm_bf16 = want == "bf16"
+        self.g16 = torch.empty(eng.n_flat, dtype=torch.bfloat16, device=eng.dev) if self.comm_bf16 else None
         self.comm: Optional[torch.cuda.Stream] = None
         self.plan: Optional[GradBuckets] = None
         self.n_buckets = 0
@@ -514,6 +591,15 @@ class DataParallel:
         return g32[n_flat:n_flat + 1]
 
     def reduce(self, eng: CaptionEngine) -> None:
+        if self.comm_bf16 or self.peer is not None:      # same exchange as the bucketed path, one slice
+            if self.comm is None:
+                self.comm = torch.cuda.Stream(device=eng.dev)
+            self._fire((0, eng.g32.numel()))
+            if self.peer is not None:
+                with torch.cuda.stream(self.comm):
+                    self.peer.barrier(torch.cuda.current_stream(eng.dev).cuda_stream)
+            torch.cuda.current_stream(eng.dev).wait_stream(self.comm)
+            return
         self.allreduce_flat(self.dist, eng.g32, eng.n_flat)
 
     # ---- bucketed, overlapped with the backward
@@ -521,7 +607,8 @@ class DataParallel:
         """Call before forward_backward: arms the bucket hook."""
         if self.comm is None:
             self.comm = torch.cuda.Stream(device=eng.dev)
-        self.plan = GradBuckets(eng.g32.numel(), self.bucket_elems)     # includes the token-count tail slot
+        self.plan = GradBuckets(eng.g32.numel(), self.bucket_elems, tail_elems=self.tail_elems,
+                                tail_below=2 * self.bucket_elems)       # includes the token-count tail slot
         self.n_buckets = 0
         eng.bucket_hook = self._closure_done
 
@@ -534,7 +621,24 @@ class DataParallel:
         if eng._bwd_side is not None:
             self.comm.wait_stream(eng._bwd_side)  # weight gradients are written by the wgrad side stream
         with torch.cuda.stream(self.comm):
-            self.dist.all_reduce(eng.g32[sl[0]:sl[1]], op=self.dist.ReduceOp.SUM)
+            lo, hi = sl
+            if self.peer is not None:
+                self.peer.all_reduce(lo, hi, torch.cuda.current_stream(eng.dev).cuda_stream)
+            elif not self.comm_bf16:
+                self.dist.all_reduce(eng.g32[lo:hi], op=self.dist.ReduceOp.SUM)
+            else:
+                from ._native import call, F32, BF16
+                n = eng.n_flat
+                hg = min(hi, n)
+                if hg > lo:
+                    st = torch.cuda.current_stream(eng.dev).cuda_stream
+                    call("icap_copy2d", eng.g32.data_ptr() + 4 * lo, F32, hg - lo, self.g16.data_ptr() + 2 * lo, BF16, hg - lo,
+                         1, hg - lo, 0, st)
+                    self.dist.all_reduce(self.g16[lo:hg], op=self.dist.ReduceOp.SUM)
+                    call("icap_copy2d", self.g16.data_ptr() + 2 * lo, BF16, hg - lo, eng.g32.data_ptr() + 4 * lo, F32, hg - lo,
+                         1, hg - lo, 0, st)
+                if hi > n:
+                    self.dist.all_reduce(eng.g32[max(lo, n):hi], op=self.dist.ReduceOp.SUM)
         self.n_buckets += 1
 
     def _closure_done(self, lo: Optional[int]) -> None:
@@ -544,6 +648,9 @@ class DataParallel:
         """Call after forward_backward: reduces what is left and joins the communication stream."""
         eng.bucket_hook = None
         self._fire(self.plan.flush())
+        if self.peer is not None:                        # nobody still reads a buffer that the next step zeroes
+            with torch.cuda.stream(self.comm):
+                self.peer.barrier(torch.cuda.current_stream(eng.dev).cuda_stream)
         torch.cuda.current_stream(eng.dev).wait_stream(self.comm)
 
     def finish(self, eng: CaptionEngine, lr: float) -> None:

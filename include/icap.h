@@ -226,6 +226,23 @@ int icap_scale(float* x, int64_t n, const float* s_dev, float s, void* stream);
 /* out[0] = numerator / x[0]  (data parallel: 1 / all-reduced token count, consumed by icap_adam_step as gscale_dev). */
 int icap_reciprocal(const float* x, float* out, float numerator, void* stream);
 
+/* ---- gradient all-reduce over NVLink peer memory (data parallel): load/store kernels without shared
+ * memory, co-resident with the backward's GEMM CTAs.  `flag_ptrs` / `buf_ptrs`: host arrays of nranks device pointers,
+ * entry q = rank q's flag words (>= nranks uint32, zero-initialised once) / fp32 buffer as mapped into THIS process (CUDA
+ * IPC for q != rank).  One bucket [lo, hi) (element offsets, multiples of 4) is reduced by
+ *   icap_p2p_barrier; icap_p2p_reduce_scatter; icap_p2p_barrier; icap_p2p_all_gather
+ * on one stream, with one more icap_p2p_barrier after the last bucket of a step.  The barrier (a one-warp kernel) bumps
+ * the device-side `epoch`, publishes it into every rank's flag words and waits for all peers; after ~2 s without a peer it
+ * stores 1 + the missing rank into `err` and returns instead of hanging.  Every rank must issue the same call sequence. */
+int icap_p2p_barrier(void* const* flag_ptrs, int rank, int nranks, unsigned int* epoch, int* err, void* stream);
+int icap_p2p_reduce_scatter(void* const* buf_ptrs, int rank, int nranks, int64_t lo, int64_t hi, int ctas, void* stream);
+int icap_p2p_all_gather(void* const* buf_ptrs, int rank, int nranks, int64_t lo, int64_t hi, int ctas, void* stream);
+/* NVSwitch in-switch reduction: `mc_base` is the multicast mapping of the same symmetric buffer (all ranks' copies behind
+ * one address range).  Rank r runs multimem.ld_reduce (sum over the ranks, computed in the switch) + multimem.st
+ * (broadcast) over chunk r of [lo, hi): a one-pass all-reduce.  Sequence per bucket: icap_p2p_barrier;
+ * icap_p2p_allreduce_nvls; one more icap_p2p_barrier before anybody reads the result. */
+int icap_p2p_allreduce_nvls(void* mc_base, int rank, int nranks, int64_t lo, int64_t hi, int ctas, void* stream);
+
 /* ---- region feature extractor (ResNet-101 trunk over the region crops, core/preprocess.py:26-62).
  * Activations are NHWC matrices [N*H*W, C]; every convolution is icap_gemm over the activation matrix itself (1x1) or
  * over the patch matrix gathered by icap_im2col_nhwc (3x3, 7x7, strided 1x1):

@@ -189,10 +189,11 @@ def test_gemm_bf16_vocab_shapes():
 def test_mha_decode_self_fused_append():
     """icap_mha_decode_self (KV-cache append fused into the attention) == explicit append + icap_mha_decode, for the
     head-dim-64 fast path and the generic path, with beam slot indirection and pad-token masking."""
-    for act, dh, rpi in ((BF16, 64, 1), (BF16, 64, 3), (F32, 64, 1), (F32, 64, 4), (F32, 16, 1)):
+    for act, dh, rpi, H in ((BF16, 64, 1, 4), (BF16, 64, 3, 4), (BF16, 64, 4, 8), (BF16, 64, 2, 8), (F32, 64, 1, 4),
+                            (F32, 64, 4, 4), (F32, 16, 1, 4)):
         g = torch.Generator(device="cuda").manual_seed(9 + dh)
         tdt = dt(act)
-        rows, H, T, t = 24, 4, 9, 5
+        rows, T, t = 24, 9, 5
         d = H * dh
         q = torch.randn(rows, 3 * d, device=dev(), generator=g).to(tdt)            # packed [q | k_new | v_new]
         cache = torch.randn(rows, T, 2 * d, device=dev(), generator=g).to(tdt)
@@ -200,6 +201,13 @@ def test_mha_decode_self_fused_append():
         tok[:, 0] = 1
         slot = torch.randint(0, rows, (rows, T + 1), device=dev(), generator=g, dtype=torch.int32)
         slot[:, t] = torch.arange(rows, dtype=torch.int32, device=dev())          # newest position: own row
+        if rpi > 1:     # beams of an image share their oldest positions (one ancestor), as after a few beam steps: the
+            #             image-per-block kernel stages such rows once; tokens of a shared position are the ancestor's
+            first = (torch.arange(rows, device=dev()) // rpi * rpi).int()
+            slot[:, :3] = first[:, None]
+            slot[1::rpi, 3] = slot[0::rpi, 3]
+            tok[:, :3] = tok[first.long(), :3]
+            tok[1::rpi, 3] = tok[0::rpi, 3]
         esz = q.element_size()
         ref_cache = cache.clone()
         ref_cache[:, t, :] = q[:, d:]

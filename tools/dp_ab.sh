@@ -12,8 +12,7 @@ for l in sys.stdin:
     elif 'error' in l.lower() or 'Traceback' in l: print(l.rstrip()[-300:])
 "
 }
-run ICAP_DP_BUCKET_MB=48
-run ICAP_DP_BUCKET_MB=16
-run ICAP_DP_BUCKET_MB=16 ICAP_DP_RESERVE_SMS=8 NCCL_MAX_CTAS=8
-run ICAP_DP_BUCKET_MB=16 ICAP_DP_RESERVE_SMS=16 NCCL_MAX_CTAS=16
-run ICAP_DP_BUCKET_MB=48 ICAP_DP_RESERVE_SMS=16 NCCL_MAX_CTAS=16
+run ICAP_DP_GRAD_DTYPE=fp32
+run ICAP_DP_GRAD_DTYPE=bf16
+run ICAP_DP_GRAD_DTYPE=fp32 ICAP_DP_BUCKET_MB=16
+run ICAP_DP_GRAD_DTYPE=fp32 ICAP_DP_BUCKET_MB=16 ICAP_DP_RESERVE_SMS=8 NCCL_MAX_CTAS=8
