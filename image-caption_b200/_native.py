@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libicap.so")
 
 F32, BF16 = 0, 1
-EPI_NONE, EPI_RELU, EPI_RELU_MASK = 0, 1, 2
+EPI_NONE, EPI_RELU, EPI_RELU_MASK, EPI_ROWSTATS = 0, 1, 2, 3
 EPI_B_STATIC = 16      # flag: B / bias are weights the preceding kernel of the stream does not write
 
 P, I, L, F, U = c_void_p, c_int, c_int64, c_float, c_uint64
@@ -34,7 +34,7 @@ SIGNATURES = {
     "icap_xent": [I, L, L, P, L, P, I, P, P, I, P],
     "icap_xent_finalize": [L, P, P, I, P, P],
     "icap_argmax": [I, L, L, P, L, P, L, P, P],
-    "icap_beam_select": [I, L, L, L, P, L, P, L, P, P, P, P, I, P],
+    "icap_beam_select": [I, L, L, L, P, L, P, L, P, P, P, P, I, P, L, P],
     "icap_beam_reorder": [L, L, L, L, P, P, P, P, P, P, P],
     "icap_log_softmax_argmax": [L, L, P, L, P, L, P, P],
     "icap_log_softmax_bwd": [L, L, P, L, P, L, P, L, P],

@@ -22,10 +22,11 @@
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 64, UMMA_K = 16;
-constexpr int STAGES = 3;
 constexpr int A_TILE_BYTES = BM * BK * 2, B_TILE_BYTES = BN * BK * 2, STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
 constexpr int NTHREADS = 192;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 128 /*barriers*/ + BN * 4 /*bias*/ + 1024 /*align slack*/;
+// STAGES = 3: 98 KB, two CTAs per SM.  STAGES = 2: 66 KB, THREE CTAs per SM -- for launches of 2..3 x #SMs tiles (decode
+// FFN1: 320 tiles), which would otherwise leave a second, mostly empty wave (the SM's ingest is shared either way).
+constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 128 /*barriers*/ + BN * 4 /*bias*/ + 1024 /*align slack*/; }
 
 struct SmallArgs {
   int M, N, K;
@@ -40,7 +41,8 @@ __device__ __forceinline__ unsigned long long gtimer() {
   return t;
 }
 
-__global__ void __launch_bounds__(NTHREADS, 2)
+template <int STAGES>
+__global__ void __launch_bounds__(NTHREADS, STAGES == 2 ? 3 : 2)
 gemm_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, const SmallArgs g) {
   extern __shared__ uint8_t smem_raw[];
@@ -225,7 +227,7 @@ bool icap_gemm_small_eligible(int a_kmajor, int b_kmajor, int64_t M, int64_t N, 
   if (!(a_kmajor && b_kmajor) || c_dtype != ICAP_BF16 || (epi & 15) > 1 || accumulate || split_k > 1) return false;
   if (((uintptr_t)C & 15) || (ldc % 8)) return false;
   const int64_t tiles = ceil_div64(M, BM) * ceil_div64(N, BN);
-  return tiles <= (int64_t)icap_num_sms() * 9 / 4 || mode == 2;
+  return tiles <= (int64_t)icap_num_sms() * 3 || mode == 2;
 }
 
 int icap_gemm_small_launch(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
@@ -239,14 +241,22 @@ int icap_gemm_small_launch(int64_t M, int64_t N, int64_t K, const void* A, int64
   if ((rc = icap_make_tmap_2d(&tc, C, M, N, ldc, 32, ICAP_BF16))) return rc;
   static bool attr_done = false;
   if (!attr_done) {
-    ICAP_CUDA(cudaFuncSetAttribute(gemm_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    ICAP_CUDA(cudaFuncSetAttribute(gemm_small_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(3)));
+    ICAP_CUDA(cudaFuncSetAttribute(gemm_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(2)));
     attr_done = true;
   }
   SmallArgs g;
   g.M = (int)M; g.N = (int)N; g.K = (int)K;
   g.bias = bias; g.relu = relu; g.b_static = b_static; g.trace = icap_trace_slot();
-  ICAP_CUDA(icap_launch(gemm_small_kernel, dim3((unsigned)ceil_div64(N, BN), (unsigned)ceil_div64(M, BM)), dim3(NTHREADS),
-                        (size_t)SMEM_BYTES, st, ta, tb, tc, g));
+  const dim3 grid((unsigned)ceil_div64(N, BN), (unsigned)ceil_div64(M, BM));
+  const int64_t tiles = (int64_t)grid.x * grid.y;
+  static IcapEnv e_st;
+  const int force = e_st.geti("ICAP_GEMM_SMALL_STAGES", 0);
+  const bool two = force ? force == 2 : (tiles > 2 * (int64_t)icap_num_sms() && tiles <= 3 * (int64_t)icap_num_sms());
+  if (two)
+    ICAP_CUDA(icap_launch(gemm_small_kernel<2>, grid, dim3(NTHREADS), (size_t)smem_bytes(2), st, ta, tb, tc, g));
+  else
+    ICAP_CUDA(icap_launch(gemm_small_kernel<3>, grid, dim3(NTHREADS), (size_t)smem_bytes(3), st, ta, tb, tc, g));
   ICAP_LAUNCH_CHECK("icap_gemm(bf16, small)");
   return 0;
 }

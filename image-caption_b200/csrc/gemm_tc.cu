@@ -26,6 +26,12 @@
 
 namespace {
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
 constexpr int A_TILE_BYTES = BM * BK * 2;        // 16 KB per stage
 constexpr int NTHREADS = 320;
@@ -301,9 +307,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int nchunks = min((half + 1) * (BN / 64), (N - n0 + 31) / 32);      // this warp: chunks [c_begin, nchunks)
       AuxRow<TO> a_cur, a_nxt;
       const bool aux_vec = g.vec_ok != 0;
+      // epi == 3 (classifier -> beam select): running (largest, second largest, sum of exp(x - largest)) of this thread's
+      // row over this warp's columns of the tile, on the ROUNDED values that are stored
+      float st_m1 = -INFINITY, st_m2 = -INFINITY, st_s = 0.f;
       if (g.epi == 2 && row < M && c_begin < nchunks)
         aux_load(a_cur, aux + (int64_t)row * g.ldaux + n0 + c_begin * 32, aux_vec && n0 + c_begin * 32 + 32 <= N,
                  N - n0 - c_begin * 32);
+      // lane j's bias of every chunk of this warp, requested before the accumulator wait (a load per chunk inside the
+      // loop left its whole latency exposed in front of the shared-memory broadcast: ncu source page, round 2)
+      float bias_c[BN / 64];
+#pragma unroll
+      for (int u = 0; u < BN / 64; ++u) {
+        const int cc = n0 + (c_begin + u) * 32 + lane;
+        bias_c[u] = (add_bias && cc < N) ? __ldg(g.bias + cc) : 0.f;
+      }
       mbar_wait_t<TWO>(tfull_bar + 8 * as, aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (tr && it == 0 && ew == 0 && lane == 0) tr[6] = gtimer();
@@ -319,8 +336,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int col0 = n0 + c * 32;
         if (g.epi == 2 && row < M && c + 1 < nchunks)
           aux_load(a_nxt, aux + (int64_t)row * g.ldaux + col0 + 32, aux_vec && col0 + 64 <= N, N - col0 - 32);
-        float bias_l = 0.f;                     // lane j holds bias[col0 + j]; broadcast through smem below
-        if (add_bias && col0 + lane < N) bias_l = __ldg(g.bias + col0 + lane);
+        float bias_l = bias_c[0];               // lane j holds bias[col0 + j]; broadcast through smem below
+#pragma unroll
+        for (int u = 1; u < BN / 64; ++u) if (c - c_begin == u) bias_l = bias_c[u];
         uint32_t r[32];
         tmem_ld32(tacc + (uint32_t)(c * 32), r);
         if (c == nchunks - 1) {                 // accumulator fully read: hand the TMEM stage back to the MMA warp
@@ -352,6 +370,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else if (g.epi == 2) {
           if (row < M) aux_mask<TO>(a_cur, v);
           a_cur = a_nxt;
+        } else if (g.epi == 3) {
+          if constexpr (ESZ == 2) {
+            // The epilogue warps have two warps per scheduler: dependent chains cost their full latency.  So: top-2 on
+            // PACKED bf16 pairs in two independent chains (3 instructions per two logits), the exp-sum in four
+            // accumulators, the bf16 rounding shared with the store below (same cvt, merged by the compiler).
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+              pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            if (col0 + 32 > N) {                       // ragged last chunk of the row: columns >= N count as -inf
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (col0 + 2 * j >= N) pk[j] = (pk[j] & 0xffff0000u) | 0xff80u;
+                if (col0 + 2 * j + 1 >= N) pk[j] = (pk[j] & 0xffffu) | 0xff800000u;
+              }
+            }
+            const uint32_t ninf2 = 0xff80ff80u;
+            __nv_bfloat162 a1 = *reinterpret_cast<const __nv_bfloat162*>(&ninf2), a2 = a1, b1 = a1, b2 = a1;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const __nv_bfloat162 wa = *reinterpret_cast<const __nv_bfloat162*>(&pk[j]);
+              const __nv_bfloat162 wb = *reinterpret_cast<const __nv_bfloat162*>(&pk[8 + j]);
+              a2 = __hmax2(a2, __hmin2(a1, wa)); a1 = __hmax2(a1, wa);
+              b2 = __hmax2(b2, __hmin2(b1, wb)); b1 = __hmax2(b1, wb);
+            }
+            const __nv_bfloat162 p1 = __hmax2(a1, b1), p2 = __hmax2(__hmin2(a1, b1), __hmax2(a2, b2));
+            const float l1 = __low2float(p1), h1 = __high2float(p1), l2 = __low2float(p2), h2 = __high2float(p2);
+            const float cm1 = fmaxf(l1, h1), cm2 = fmaxf(fminf(l1, h1), fmaxf(l2, h2));
+            const float mn = fmaxf(st_m1, cm1);
+            if (mn > -INFINITY) {
+              constexpr float LOG2E = 1.4426950408889634f;
+              const float nb = -mn * LOG2E;
+              float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                s4[(2 * j) & 3] += ex2_approx(fmaf(__uint_as_float(pk[j] << 16), LOG2E, nb));
+                s4[(2 * j + 1) & 3] += ex2_approx(fmaf(__uint_as_float(pk[j] & 0xffff0000u), LOG2E, nb));
+              }
+              st_s = st_s * ex2_approx((st_m1 - mn) * LOG2E) + ((s4[0] + s4[1]) + (s4[2] + s4[3]));
+            }
+            st_m2 = fmaxf(fmaxf(st_m2, cm2), fminf(st_m1, cm1));
+            st_m1 = mn;
+          }
         }
         if ((g.debug & 7) == 3) {                     // timing experiment: no stores at all (keep the math alive)
           float acc = 0.f;
@@ -425,6 +488,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         }
+      }
+      if (g.epi == 3 && row < M) {
+        float* sp = const_cast<float*>(reinterpret_cast<const float*>(g.aux)) + (int64_t)row * g.ldaux +
+                    (int64_t)((tile % g.tiles_n) * 2 + half) * 4;
+        *reinterpret_cast<float4*>(sp) = make_float4(st_m1, st_m2, st_s, 0.f);
       }
     }
     if (g.store_mode != 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -589,11 +657,12 @@ int icap_gemm_bf16_launch(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int6
   const bool no_pair = e_nopair.get("ICAP_GEMM_NO_PAIR") != nullptr;
   const bool direct_epi = e_direct.get("ICAP_GEMM_DIRECT_EPILOGUE") != nullptr;
   for (int c = 2; c >= 0; --c) {
-    if (force_bn) {
+    if (force_bn && epi != 3) {
       const int want = force_bn[0] == 'p' ? 2 : (atoi(force_bn) == 256 ? 1 : 0);
       if (want != c) continue;
     }
     const int bn = c == 0 ? 128 : 256, bm = c == 2 ? 256 : 128;
+    if (epi == 3 && c != 1) continue;          // row statistics: one partial per 128 columns = per column half of a 128x256 tile
     if (c >= 1 && N <= 128 && !force_bn) continue;
     if (c == 2 && !force_bn && (M <= 128 || no_pair)) continue;
     const int64_t tiles = ceil_div64(M, bm) * ceil_div64(N, bn);
@@ -622,6 +691,12 @@ int icap_gemm_bf16_launch(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int6
       cost = 0.0;                            // eligible: take it
     }
     if (cost < best_cost) { best_cost = cost; best_cfg = c; best_split = split; }
+  }
+  if (epi == 3) {
+    ICAP_ARG(c_dtype == ICAP_BF16 && !accumulate && split_k <= 1 && aux && ((uintptr_t)aux & 15) == 0 &&
+             ldaux >= 8 * ceil_div64(N, 256) && ldaux % 4 == 0 && best_cfg == 1,
+             "icap_gemm(bf16): the row-statistics epilogue needs bf16 C, no accumulation and a 16-byte aligned stats buffer "
+             "of >= 8 * ceil(N / 256) floats per row");
   }
   if (split_k > 1)
     ICAP_ARG(can_split, "icap_gemm(bf16): split_k>1 needs fp32 C, accumulate!=0, no bias and no activation epilogue");

@@ -179,6 +179,101 @@ constexpr int KMAX = 8;   // beam width limit; lists hold KMAX+1 entries so the 
 struct Cand { float s; int i; };
 __device__ __forceinline__ bool better(float s, int i, float s2, int i2) { return s > s2 || (s == s2 && i < i2); }
 
+// Exact selection without a candidate bound: every thread keeps the sorted best L of the candidates it scans, the block
+// merges the lists.  The fall-back of both beam_select kernels when more than CAND_CAP candidates tie with the bound
+// (degenerate logits); needs the softmax maximum / denominator of every row in s_mx / s_den.  Whole block, convergent.
+template <typename T>
+__device__ __forceinline__ void beam_select_exact(int b, int kin, int V, const T* __restrict__ logits, int64_t ldl,
+                                               const float* __restrict__ prev, int kout, float* __restrict__ out_score,
+                                               int* __restrict__ out_parent, int* __restrict__ out_token,
+                                               float* __restrict__ gap, int log_domain, const float* s_mx,
+                                               const float* s_den, float* h_s, int* h_i, int* h_t) {
+  const bool vec = ((uintptr_t)logits % 16 == 0) && (ldl * sizeof(T)) % 16 == 0;
+  const int L = kout + 1;
+  Cand lst[KMAX + 1];                      // sorted, best first; only static indices (stays in registers)
+#pragma unroll
+  for (int t = 0; t <= KMAX; ++t) { lst[t].s = -INFINITY; lst[t].i = 0x7fffffff; }
+  float worst_s = -INFINITY;               // == lst[L-1]: the entry a candidate has to beat
+  int worst_i = 0x7fffffff;
+  for (int r = 0; r < kin; ++r) {
+    const T* x = logits + ((int64_t)b * kin + r) * ldl;
+    const float mx = s_mx[r], den = s_den[r], pv = prev ? prev[b * kin + r] : 0.f;
+    // Cheap pre-filter in the logit domain: the score is monotonic in the logit, so only logits above
+    //   tl = logit whose score equals the current worst list entry (minus a 1e-3 safety margin)
+    // can enter the list; everything else costs one compare instead of expf + divide.
+    float tl;
+    auto refresh_tl = [&]() {
+      if (log_domain) tl = worst_s - pv + mx + den;
+      else { const float need = worst_s - pv; tl = need > 0.f ? mx + logf(need * den) : -INFINITY; }
+      tl -= 1e-3f;
+    };
+    refresh_tl();
+    for (int j0 = threadIdx.x * 8; j0 < V; j0 += NT * 8) {
+      float v[8];
+      const int n = load_chunk8(x, j0, V, vec, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (i >= n) break;
+        const float xv = v[i];
+        if (!(xv > tl)) continue;
+        const float sc = (log_domain ? (xv - mx - den) : (expf(xv - mx) / den)) + pv;
+        const int idx = r * V + j0 + i;
+        if (better(sc, idx, worst_s, worst_i)) {
+#pragma unroll
+          for (int t = 0; t <= KMAX; ++t) if (t == L - 1) { lst[t].s = sc; lst[t].i = idx; }
+#pragma unroll
+          for (int t = KMAX; t > 0; --t) {
+            if (t < L && better(lst[t].s, lst[t].i, lst[t - 1].s, lst[t - 1].i)) {
+              Cand c = lst[t]; lst[t] = lst[t - 1]; lst[t - 1] = c;
+            }
+          }
+#pragma unroll
+          for (int t = 0; t <= KMAX; ++t) if (t == L - 1) { worst_s = lst[t].s; worst_i = lst[t].i; }
+          refresh_tl();
+        }
+      }
+    }
+  }
+  // block merge: L rounds of "best remaining head"
+  int head = 0;
+  float kth = 0.f;
+  for (int round = 0; round < L; ++round) {
+    float hs = -INFINITY;
+    int hi = 0x7fffffff;
+#pragma unroll
+    for (int t = 0; t <= KMAX; ++t) if (t == head && t < L) { hs = lst[t].s; hi = lst[t].i; }
+    h_s[threadIdx.x] = hs;
+    h_i[threadIdx.x] = hi;
+    h_t[threadIdx.x] = threadIdx.x;
+    __syncthreads();
+    for (int s = NT / 2; s > 0; s >>= 1) {
+      if (threadIdx.x < s) {
+        if (better(h_s[threadIdx.x + s], h_i[threadIdx.x + s], h_s[threadIdx.x], h_i[threadIdx.x])) {
+          h_s[threadIdx.x] = h_s[threadIdx.x + s];
+          h_i[threadIdx.x] = h_i[threadIdx.x + s];
+          h_t[threadIdx.x] = h_t[threadIdx.x + s];
+        }
+      }
+      __syncthreads();
+    }
+    const int winner = h_t[0];
+    const float ws = h_s[0];
+    const int wi = h_i[0];
+    if (threadIdx.x == winner) ++head;
+    if (threadIdx.x == 0) {
+      if (round < kout) {
+        out_score[b * kout + round] = ws;
+        out_parent[b * kout + round] = wi / V;
+        out_token[b * kout + round] = wi % V;
+        kth = ws;
+      } else if (gap) {
+        gap[b] = kth - ws;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(NT)
 beam_select_kernel(int kin, int V, const T* __restrict__ logits, int64_t ldl, const float* __restrict__ prev,
@@ -348,88 +443,175 @@ beam_select_kernel(int kin, int V, const T* __restrict__ logits, int64_t ldl, co
     }
     // more than CAND_CAP candidates tie with tau (degenerate logits): exact but slow path below
   }
-  Cand lst[KMAX + 1];                      // sorted, best first; only static indices (stays in registers)
+  beam_select_exact<T>(b, kin, V, logits, ldl, prev, kout, out_score, out_parent, out_token, gap, log_domain, s_mx, s_den,
+                       h_s, h_i, h_t);
+}
+
+// The same selection fed with the classifier GEMM's ICAP_EPI_ROWSTATS buffer: (largest, second largest, sum exp(x -
+// largest)) per row and 128 logits.  No pass over the logits at all: the row statistics and the candidate bound come from
+// the V / 128 partials per row, and only the ~L segments whose maximum can beat the bound are read.  Built for latency
+// (the kernel sits on the decode step's critical path between the classifier and the next step's embedding): all rows'
+// partials are requested at once, the bound and the final order are rank counts instead of L rounds of warp reductions.
+constexpr int HIT_CAP = 256;
+
+// (largest, second largest, sum exp(x - largest)) of two disjoint sets -> of their union
+__device__ __forceinline__ void top2sum_merge(float& t1, float& t2, float& es, float o1, float o2, float oe) {
+  const float n1 = fmaxf(t1, o1);
+  // a side whose maximum IS the new maximum keeps its sum as it is (also keeps -inf - -inf out of the exponent)
+  const float a = t1 == n1 ? 1.f : __expf(t1 - n1), c = o1 == n1 ? 1.f : __expf(o1 - n1);
+  es = es * a + oe * c;
+  t2 = fmaxf(fminf(t1, o1), fmaxf(t2, o2));
+  t1 = n1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NT)
+beam_select_stats_kernel(int kin, int V, const T* __restrict__ logits, int64_t ldl, const float* __restrict__ prev,
+                         int kout, float* __restrict__ out_score, int* __restrict__ out_parent,
+                         int* __restrict__ out_token, float* __restrict__ gap, int log_domain,
+                         const float* __restrict__ stats, int64_t stats_ld) {
+  pdl_prologue();
+  constexpr int NW = NT / 32, PER = 2 * NW;
+  __shared__ float s_mx[KMAX], s_den[KMAX], s_pv[KMAX], s_tl[KMAX];
+  __shared__ float s_w1[KMAX][NW], s_w2[KMAX][NW];     // two largest logits of every (row, lane group)
+  __shared__ float b_s[KMAX * PER];
+  __shared__ float s_tau;
+  __shared__ int h_n, c_n;
+  __shared__ int h_seg[HIT_CAP];
+  __shared__ float c_s[CAND_CAP];
+  __shared__ int c_i[CAND_CAP];
+  __shared__ float r_s[KMAX + 1];
+  __shared__ float h_s[NT];
+  __shared__ int h_i[NT], h_t[NT];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int L = kout + 1, np = (V + 127) / 128;
+  const float4* sp0 = reinterpret_cast<const float4*>(stats + (int64_t)b * kin * stats_ld);
+  const int64_t sld4 = stats_ld >> 2;
+  static_assert(KMAX <= NW, "one warp per beam row");
+  if (tid == 0) { h_n = 0; c_n = 0; }
+  if (tid <= KMAX) r_s[tid] = -INFINITY;
+  // ---- warp r owns row r: softmax maximum / sum of the row and, as candidates for the bound, the two largest logits of each
+  // of 8 lane groups (partials pi with pi % 32 in [4g, 4g + 4)).  A loop and five shuffle rounds: small code -- the first
+  // version, unrolled over the rows, spent 40 % of its samples waiting for instruction fetches.
+  if (warp < kin) {
+    const int r = warp;
+    const float4* sp = sp0 + r * sld4;
+    float t1 = -INFINITY, t2 = -INFINITY, es = 0.f;
+#pragma unroll 2
+    for (int pi = lane; pi < np; pi += 32) {
+      const float4 q = __ldg(sp + pi);
+      top2sum_merge(t1, t2, es, q.x, q.y, q.z);
+    }
 #pragma unroll
-  for (int t = 0; t <= KMAX; ++t) { lst[t].s = -INFINITY; lst[t].i = 0x7fffffff; }
-  float worst_s = -INFINITY;               // == lst[L-1]: the entry a candidate has to beat
-  int worst_i = 0x7fffffff;
-  for (int r = 0; r < kin; ++r) {
-    const T* x = logits + ((int64_t)b * kin + r) * ldl;
-    const float mx = s_mx[r], den = s_den[r], pv = prev ? prev[b * kin + r] : 0.f;
-    // Cheap pre-filter in the logit domain: the score is monotonic in the logit, so only logits above
-    //   tl = logit whose score equals the current worst list entry (minus a 1e-3 safety margin)
-    // can enter the list; everything else costs one compare instead of expf + divide.
+    for (int o = 1; o < 32; o <<= 1) {
+      if (o == 4 && (lane & 3) == 0) { s_w1[r][lane >> 2] = t1; s_w2[r][lane >> 2] = t2; }
+      const float o1 = __shfl_xor_sync(0xffffffffu, t1, o), o2 = __shfl_xor_sync(0xffffffffu, t2, o);
+      const float oe = __shfl_xor_sync(0xffffffffu, es, o);
+      top2sum_merge(t1, t2, es, o1, o2, oe);
+    }
+    if (lane == 0) {
+      s_mx[r] = t1; s_den[r] = log_domain ? logf(es) : es;
+      s_pv[r] = prev ? prev[b * kin + r] : 0.f;
+    }
+  }
+  __syncthreads();
+  // ---- bound: the L-th largest score among the two largest logits of every (row, warp) -- real candidates, so at least L
+  // candidates reach it.  One rank count per bound candidate instead of L rounds of warp reductions.
+  const int total = kin * PER;
+  if (tid < total) {
+    const int r = tid / PER, w = (tid % PER) >> 1;
+    const float lg = (tid & 1) ? s_w2[r][w] : s_w1[r][w];
+    float sc = -INFINITY;
+    if (lg > -INFINITY) sc = (log_domain ? (lg - s_mx[r] - s_den[r]) : (__expf(lg - s_mx[r]) / s_den[r])) + s_pv[r];
+    b_s[tid] = sc;
+  }
+  __syncthreads();
+  if (tid < total) {
+    const float sc = b_s[tid];
+    int rank = 0;
+#pragma unroll 4
+    for (int f = 0; f < total; ++f) {
+      const float o = b_s[f];
+      rank += (o > sc || (o == sc && f < tid)) ? 1 : 0;
+    }
+    if (rank == L - 1) s_tau = sc;                     // -inf (fewer than L real candidates): everything passes
+  }
+  __syncthreads();
+  const float tau = s_tau;
+  if (tid < kin) {                                     // logit whose score is tau, minus a safety margin
+    const int r = tid;
     float tl;
-    auto refresh_tl = [&]() {
-      if (log_domain) tl = worst_s - pv + mx + den;
-      else { const float need = worst_s - pv; tl = need > 0.f ? mx + logf(need * den) : -INFINITY; }
-      tl -= 1e-3f;
-    };
-    refresh_tl();
-    for (int j0 = threadIdx.x * 8; j0 < V; j0 += NT * 8) {
-      float v[8];
-      const int n = load_chunk8(x, j0, V, vec, v);
+    if (log_domain) tl = tau - s_pv[r] + s_mx[r] + s_den[r];
+    else { const float need = tau - s_pv[r]; tl = need > 0.f ? s_mx[r] + logf(need * s_den[r]) : -INFINITY; }
+    s_tl[r] = tl - 1e-3f;
+  }
+  __syncthreads();
+  // ---- the 128-logit segments whose maximum exceeds tl (about L of kin * V / 128) ...
+  if (warp < kin) {
+    const int r = warp;
+    const float tl = s_tl[r];
+    const float4* sp = sp0 + r * sld4;
+#pragma unroll 2
+    for (int pi = lane; pi < np; pi += 32) {
+      if (__ldg(&sp[pi].x) > tl) {                     // L1 hit: read a moment ago
+        const int pos = atomicAdd(&h_n, 1);
+        if (pos < HIT_CAP) h_seg[pos] = (r << 20) | pi;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- ... are read, one warp per segment, and their candidates (score >= tau) collected
+  const int nh = h_n;
+  if (nh <= HIT_CAP) {
+#pragma unroll 1
+    for (int h = warp; h < nh; h += NW) {
+      const int r = h_seg[h] >> 20, seg = h_seg[h] & 0xfffff;
+      const T* x = logits + ((int64_t)b * kin + r) * ldl;
+      const float mx = s_mx[r], den = s_den[r], pv = s_pv[r], tl = s_tl[r];
+      const int j0 = seg * 128 + lane * 4;
+      float v[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (i >= n) break;
-        const float xv = v[i];
-        if (!(xv > tl)) continue;
-        const float sc = (log_domain ? (xv - mx - den) : (expf(xv - mx) / den)) + pv;
-        const int idx = r * V + j0 + i;
-        if (better(sc, idx, worst_s, worst_i)) {
+      for (int i = 0; i < 4; ++i) v[i] = j0 + i < V ? to_f32(x[j0 + i]) : -INFINITY;
 #pragma unroll
-          for (int t = 0; t <= KMAX; ++t) if (t == L - 1) { lst[t].s = sc; lst[t].i = idx; }
-#pragma unroll
-          for (int t = KMAX; t > 0; --t) {
-            if (t < L && better(lst[t].s, lst[t].i, lst[t - 1].s, lst[t - 1].i)) {
-              Cand c = lst[t]; lst[t] = lst[t - 1]; lst[t - 1] = c;
-            }
-          }
-#pragma unroll
-          for (int t = 0; t <= KMAX; ++t) if (t == L - 1) { worst_s = lst[t].s; worst_i = lst[t].i; }
-          refresh_tl();
+      for (int i = 0; i < 4; ++i) {
+        if (!(v[i] > tl)) continue;
+        const float sc = (log_domain ? (v[i] - mx - den) : (__expf(v[i] - mx) / den)) + pv;
+        if (sc >= tau) {
+          const int pos = atomicAdd(&c_n, 1);
+          if (pos < CAND_CAP) { c_s[pos] = sc; c_i[pos] = r * V + j0 + i; }
         }
       }
     }
   }
-  // block merge: L rounds of "best remaining head"
-  int head = 0;
-  float kth = 0.f;
-  for (int round = 0; round < L; ++round) {
-    float hs = -INFINITY;
-    int hi = 0x7fffffff;
-#pragma unroll
-    for (int t = 0; t <= KMAX; ++t) if (t == head && t < L) { hs = lst[t].s; hi = lst[t].i; }
-    h_s[threadIdx.x] = hs;
-    h_i[threadIdx.x] = hi;
-    h_t[threadIdx.x] = threadIdx.x;
-    __syncthreads();
-    for (int s = NT / 2; s > 0; s >>= 1) {
-      if (threadIdx.x < s) {
-        if (better(h_s[threadIdx.x + s], h_i[threadIdx.x + s], h_s[threadIdx.x], h_i[threadIdx.x])) {
-          h_s[threadIdx.x] = h_s[threadIdx.x + s];
-          h_i[threadIdx.x] = h_i[threadIdx.x + s];
-          h_t[threadIdx.x] = h_t[threadIdx.x + s];
+  __syncthreads();
+  const int cn = c_n;
+  if (nh <= HIT_CAP && cn <= CAND_CAP) {
+    // ---- final order: every candidate counts the candidates that beat it
+#pragma unroll 1
+    for (int e = tid; e < cn; e += NT) {
+      const float sc = c_s[e];
+      const int ci = c_i[e];
+      int rank = 0;
+#pragma unroll 4
+      for (int f = 0; f < cn; ++f) rank += better(c_s[f], c_i[f], sc, ci) ? 1 : 0;
+      if (rank < L) {
+        r_s[rank] = sc;
+        if (rank < kout) {
+          out_score[b * kout + rank] = sc;
+          out_parent[b * kout + rank] = ci / V;
+          out_token[b * kout + rank] = ci % V;
         }
       }
+    }
+    if (gap) {
       __syncthreads();
+      if (tid == 0) gap[b] = r_s[kout - 1] - r_s[kout];
     }
-    const int winner = h_t[0];
-    const float ws = h_s[0];
-    const int wi = h_i[0];
-    if (threadIdx.x == winner) ++head;
-    if (threadIdx.x == 0) {
-      if (round < kout) {
-        out_score[b * kout + round] = ws;
-        out_parent[b * kout + round] = wi / V;
-        out_token[b * kout + round] = wi % V;
-        kth = ws;
-      } else if (gap) {
-        gap[b] = kth - ws;
-      }
-    }
-    __syncthreads();
+    return;
   }
+  // too many segments / candidates tie with the bound (degenerate logits): exact path over the logits
+  beam_select_exact<T>(b, kin, V, logits, ldl, prev, kout, out_score, out_parent, out_token, gap, log_domain, s_mx, s_den,
+                       h_s, h_i, h_t);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -552,17 +734,27 @@ extern "C" int icap_argmax(int dtype, int64_t M, int64_t V, const void* logits, 
 
 extern "C" int icap_beam_select(int dtype, int64_t B, int64_t kin, int64_t V, const void* logits, int64_t ldl,
                                 const float* prev_score, int64_t kout, float* out_score, int* out_parent,
-                                int* out_token, float* gap, int log_domain, void* stream) {
+                                int* out_token, float* gap, int log_domain, const float* stats, int64_t stats_ld,
+                                void* stream) {
+  ICAP_ARG(stats == nullptr || (((uintptr_t)stats & 15) == 0 && stats_ld % 4 == 0 && stats_ld >= 4 * ((V + 127) / 128)),
+           "icap_beam_select: the statistics buffer needs 16-byte alignment and >= 4 * ceil(V / 128) floats per row");
   ICAP_ARG(B > 0 && V > 0 && logits && out_score && out_parent && out_token, "icap_beam_select: null/empty argument");
   ICAP_ARG(kin >= 1 && kin <= KMAX && kout >= 1 && kout <= KMAX, "icap_beam_select: beam width must be in [1, %d]", KMAX);
   ICAP_ARG(kin * V > kout, "icap_beam_select: fewer candidates than beams");
+  ICAP_ARG(stats == nullptr || V < (1 << 27), "icap_beam_select: V too large for the statistics path");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == ICAP_F32)
-    icap_launch(beam_select_kernel<float>, (unsigned)B, NT, 0, st, (int)kin, (int)V, (const float*)logits, ldl, prev_score,
-                                                          (int)kout, out_score, out_parent, out_token, gap, log_domain);
-  else
-    icap_launch(beam_select_kernel<bf16>, (unsigned)B, NT, 0, st, (int)kin, (int)V, (const bf16*)logits, ldl, prev_score,
-                                                         (int)kout, out_score, out_parent, out_token, gap, log_domain);
+#define GO_SELECT(T)                                                                                                  \
+  do {                                                                                                                \
+    if (stats)                                                                                                        \
+      icap_launch(beam_select_stats_kernel<T>, (unsigned)B, NT, 0, st, (int)kin, (int)V, (const T*)logits, ldl, prev_score,  \
+                  (int)kout, out_score, out_parent, out_token, gap, log_domain, stats, stats_ld);                    \
+    else                                                                                                              \
+      icap_launch(beam_select_kernel<T>, (unsigned)B, NT, 0, st, (int)kin, (int)V, (const T*)logits, ldl, prev_score,        \
+                  (int)kout, out_score, out_parent, out_token, gap, log_domain);                                     \
+  } while (0)
+  if (dtype == ICAP_F32) GO_SELECT(float);
+  else GO_SELECT(bf16);
+#undef GO_SELECT
   ICAP_LAUNCH_CHECK("icap_beam_select");
   return 0;
 }

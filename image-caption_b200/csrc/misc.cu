@@ -530,8 +530,9 @@ extern "C" int icap_gemm(int ab_dtype, int a_kmajor, int b_kmajor, int64_t M, in
                          int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int c_dtype, const float* bias,
                          int epilogue, const void* aux, int64_t ldaux, int accumulate, int split_k, void* stream) {
   ICAP_ARG(M > 0 && N > 0 && K > 0 && A && B && C, "icap_gemm: null/empty argument");
-  ICAP_ARG(epilogue >= 0 && (epilogue & 15) <= 2 && (epilogue & ~31) == 0 && ((epilogue & 15) != 2 || aux),
+  ICAP_ARG(epilogue >= 0 && (epilogue & 15) <= 3 && (epilogue & ~31) == 0 && ((epilogue & 15) < 2 || aux),
            "icap_gemm: bad epilogue %d", epilogue);
+  ICAP_ARG((epilogue & 15) != 3 || ab_dtype == ICAP_BF16, "icap_gemm: the row-statistics epilogue exists in bf16 mode only");
   ICAP_ARG(accumulate >= 0 && accumulate <= 1, "icap_gemm: accumulate must be 0 or 1");
   ICAP_ARG(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "icap_gemm: dimension too large");
   cudaStream_t st = (cudaStream_t)stream;

@@ -1050,8 +1050,14 @@ class CaptionEngine:
             if cfg.move_first_image_feature:
                 x = self._move_first_tail(x, enc, B, 1, R, rows_per_image=k)
             logits = self.new(rows, ldl)
+            # beam search in bf16: the classifier's epilogue leaves per-128-column (max, 2nd max, sum exp) statistics,
+            # so that beam_select does not make its own statistics pass over the k * V logits of every image
+            stats = None
+            if k > 1 and self.precision == "bf16":
+                stats = self.new(rows, 8 * ((V + 255) // 256), dtype=torch.float32)
             self.gemm(x, True, self.w("classifer.weight"), d, True, rows, V, d, logits, ldc=ldl,
-                      bias=self.p("classifer.bias"), b_static=True)
+                      bias=self.p("classifer.bias"), b_static=True, epi=N.EPI_ROWSTATS if stats is not None else 0,
+                      aux=stats)
             if k == 1:
                 call("icap_argmax", self.act, rows, V, logits.data_ptr(), ldl, tk.data_ptr() + 4 * (t + 1), Tmax,
                      gaps[t].data_ptr() if gaps is not None else None, s())
@@ -1059,7 +1065,8 @@ class CaptionEngine:
                 kin = 1 if t == 0 else k       # step 0: all beams hold <START>, only beam 0 competes (model.py:146-166)
                 call("icap_beam_select", self.act, B, kin, V, logits.data_ptr(), ldl * (k if t == 0 else 1),
                      score[cur].data_ptr() if t > 0 else None, k, score[cur ^ 1].data_ptr(), parent.data_ptr(),
-                     newtok.data_ptr(), gaps[t].data_ptr() if gaps is not None else None, int(log_domain), s())
+                     newtok.data_ptr(), gaps[t].data_ptr() if gaps is not None else None, int(log_domain),
+                     _ptr(stats), (stats.shape[1] * (k if t == 0 else 1)) if stats is not None else 0, s())
                 call("icap_beam_reorder", B, k, Tmax, t, parent.data_ptr(), newtok.data_ptr(), tk.data_ptr(),
                      tok[cur ^ 1].data_ptr(), slot[cur].data_ptr(), slot[cur ^ 1].data_ptr(), s())
                 cur ^= 1

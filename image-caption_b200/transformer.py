@@ -557,8 +557,28 @@ class DataParallel:
         eng.shadow_fresh = False
         self.eng = eng
         self.inv = torch.zeros(1, dtype=torch.float32, device=eng.dev)
+        # Exchange back-end.  ICAP_DP_PEER=1: libicap's own NVLink peer-memory kernels (PeerReduce); 0: NCCL; unset: the
+        # peer kernels when the fabric offers an NVSwitch multicast mapping of the gradient buffer (in-switch reduction),
+        # NCCL otherwise.  Measured on 8 x B200 (profiles/r2_scale8.log): 4.71 ms/step against NCCL's 5.02 (1 GPU 4.44);
+        # on 2 GPUs both take 4.73.
+        self.peer: Optional[PeerReduce] = None
+        mode = os.environ.get("ICAP_DP_PEER", "auto")
+        if mode != "0" and self.world <= 8 and eng.dev.type == "cuda" and dist.get_backend() == "nccl":
+            try:
+                peer = PeerReduce(dist, eng)
+            except Exception as e:                       # no symmetric memory on this fabric / torch build
+                if mode == "1":
+                    raise
+                peer = None
+                if dist.get_rank() == 0:
+                    print(f"[icap] peer-memory gradient exchange unavailable ({type(e).__name__}: {e}); using NCCL",
+                          flush=True)
+            # every rank takes the same branch: multicast_ptr is a property of the group's allocation
+            if peer is not None and (mode == "1" or peer.use_nvls):
+                self.peer = peer
+                eng.g32 = peer.g32                       # the engine's gradient buffer IS the exported one
         if bucket_mb is None:
-            bucket_mb = float(os.environ.get("ICAP_DP_BUCKET_MB", "48"))
+            bucket_mb = float(os.environ.get("ICAP_DP_BUCKET_MB", "16" if self.peer is not None else "48"))
         # SMs left to NCCL while the backward's persistent GEMMs run (0 = none reserved)
         reserve = int(os.environ.get("ICAP_DP_RESERVE_SMS", "0"))
         if reserve > 0:
@@ -567,17 +587,11 @@ class DataParallel:
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
         self.tail_elems = int(min(bucket_mb, float(os.environ.get("ICAP_DP_TAIL_MB", "8"))) * (1 << 20) / 4)
         self.overlap = overlap and os.environ.get("ICAP_DP_OVERLAP", "1") != "0"
-        # Gradient exchange dtype: fp32 (default) or, with ICAP_DP_GRAD_DTYPE=bf16, every bucket rounded to bf16 into a
-        # staging buffer, all-reduced there and widened back (half the NVLink bytes; the token count in the tail slot
-        # still travels in fp32).  Measured on 2 x B200: 4.736 vs 4.728 ms/step -- the exposed 0.29 ms is not volume
-        # (profiles/r2_summary.md), so the exact fp32 exchange stays the default.
-        want = os.environ.get("ICAP_DP_GRAD_DTYPE", "fp32")
-        # ICAP_DP_PEER=1: the gradient buckets are reduced by libicap's own NVLink peer-memory kernels (PeerReduce)
-        self.peer: Optional[PeerReduce] = None
-        if os.environ.get("ICAP_DP_PEER", "0") == "1" and self.world <= 8 and eng.dev.type == "cuda":
-            self.peer = PeerReduce(dist, eng)
-            eng.g32 = self.peer.g32                      # the engine's gradient buffer IS the exported one
-            want = "fp32"
+        # Gradient exchange dtype (NCCL back-end only): fp32 (default) or, with ICAP_DP_GRAD_DTYPE=bf16, every bucket
+        # rounded to bf16 into a staging buffer, all-reduced there and widened back (half the NVLink bytes; the token
+        # count in the tail slot still travels in fp32).  Measured on 2 x B200: 4.736 vs 4.728 ms/step -- the exposed
+        # 0.29 ms is not volume (profiles/r2_summary.md), so the exact fp32 exchange stays the default.
+        want = "fp32" if self.peer is not None else os.environ.get("ICAP_DP_GRAD_DTYPE", "fp32")
         self.comm_bf16 = want == "bf16"
         self.g16 = torch.empty(eng.n_flat, dtype=torch.bfloat16, device=eng.dev) if self.comm_bf16 else None
         self.comm: Optional[torch.cuda.Stream] = None

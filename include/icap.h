@@ -30,6 +30,11 @@ extern "C" {
 #define ICAP_EPI_NONE 0
 #define ICAP_EPI_RELU 1      /* C = relu(AB + bias)            FeedForward position_wise_1 + ReLU, modules.py:113-114 */
 #define ICAP_EPI_RELU_MASK 2 /* C = (AB) * (aux > 0)           backward of that ReLU                                   */
+/* C = AB + bias as usual (bf16 C), and aux = fp32 statistics OUT: per row and per 128 columns a float4 (largest value,
+ * second largest, sum of exp(x - largest), 0) of the ROUNDED values that were stored; ldaux >= 8 * ceil(N / 256) floats.
+ * The classifier of a beam-search step (model.py:176-186): icap_beam_select takes the buffer instead of making its own
+ * statistics pass over the V logits of every row. */
+#define ICAP_EPI_ROWSTATS 3
 /* flag, OR-ed into `epilogue`: B and bias are WEIGHTS that the kernel launched immediately before on this stream does
  * not write; the small-footprint kernel then fetches its first B stages before its grid dependency has resolved. */
 #define ICAP_EPI_B_STATIC 16
@@ -133,10 +138,12 @@ int icap_argmax(int dtype, int64_t M, int64_t V, const void* logits, int64_t ldl
 /* Beam step for B images: candidates (beam r, token j) score softmax(logits[b*kin+r])[j] + prev[b,r]
  * (log_domain=1: log-softmax, the PolicyNetwork variant); writes the kout best in DESCENDING order:
  * score, parent = r, token = j; gap[b] = score_k - score_{k+1} (nullable).
+ * stats (nullable): the ICAP_EPI_ROWSTATS buffer of the classifier GEMM that produced `logits` (row stride stats_ld
+ * floats): replaces the kernel's own statistics pass over the logits.
  * Replaces Softmax + cat + topk + // and % of model.py:160-166,181-198 (model_RL.py:157,182). */
 int icap_beam_select(int dtype, int64_t B, int64_t kin, int64_t V, const void* logits, int64_t ldl,
                      const float* prev_score, int64_t kout, float* out_score, int* out_parent, int* out_token,
-                     float* gap, int log_domain, void* stream);
+                     float* gap, int log_domain, const float* stats, int64_t stats_ld, void* stream);
 /* PolicyNetwork.sample (model_RL.py:93-97) on fp32 logits [M, V]: logp = log_softmax(x) per row, idx[row] (int64,
  * nullable) = arg-max (lowest index on ties, as torch.argmax on the CPU).  icap_log_softmax_bwd is its backward:
  * dx = dlogp - exp(logp) * rowsum(dlogp)  (the self-critical loss gathers log-probabilities, loss.py:90-103,145-158). */

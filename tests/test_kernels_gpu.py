@@ -652,7 +652,7 @@ def test_beam_select(log_domain, kin, kout, V):
     ot = torch.empty(B, kout, dtype=torch.int32, device=dev())
     gap = torch.empty(B, device=dev())
     N.call("icap_beam_select", F32, B, kin, V, logits.data_ptr(), V, prev.data_ptr(), kout, os_.data_ptr(), op.data_ptr(),
-           ot.data_ptr(), gap.data_ptr(), log_domain, S())
+           ot.data_ptr(), gap.data_ptr(), log_domain, None, 0, S())
     torch.cuda.synchronize()
     assert torch.equal(op.long() * V + ot.long(), ref_i[:, :kout])
     assert torch.allclose(os_, ref_s[:, :kout], rtol=1e-5, atol=1e-7)
@@ -704,7 +704,7 @@ def test_beam_select_degenerate_distributions(log_domain, case):
     ot = torch.empty(B, kout, dtype=torch.int32, device=dev())
     gap = torch.empty(B, device=dev())
     N.call("icap_beam_select", code, B, kin, V, logits.data_ptr(), ldl, prev.data_ptr(), kout, os_.data_ptr(), op.data_ptr(),
-           ot.data_ptr(), gap.data_ptr(), log_domain, S())
+           ot.data_ptr(), gap.data_ptr(), log_domain, None, 0, S())
     torch.cuda.synchronize()
     idx = op.long() * V + ot.long()
     ref_s = torch.topk(cand, kout + 1, dim=1).values
@@ -720,6 +720,54 @@ def test_beam_select_degenerate_distributions(log_domain, case):
         assert len({tuple(r) for r in idx.tolist()}) >= 1 and all(len(set(r)) == kout for r in idx.tolist())
         # log domain: scores are ~ -ln(V) = -9.2, one fp32 ulp there is 1e-6 -- the gap is a difference of two of them
         assert torch.allclose(gap, ref_s[:, kout - 1] - ref_s[:, kout], rtol=1e-2, atol=5e-6 if log_domain else 1e-7)
+
+
+@pytest.mark.parametrize("log_domain", [0, 1])
+@pytest.mark.parametrize("V,flat", [(10000, False), (9999, False), (300, False), (30000, False), (40000, False), (10000, True)])
+def test_classifier_rowstats_feed_beam_select(log_domain, V, flat):
+    """ICAP_EPI_ROWSTATS: the classifier GEMM's epilogue leaves (max, 2nd max, sum exp) per row and 128 columns of the
+    ROUNDED logits it stores; icap_beam_select with that buffer (no statistics pass of its own) picks exactly what it
+    picks without it, and the statistics equal torch's on the stored logits.  flat: all logits equal (zero weights) -- every
+    candidate ties with the bound and both kernels take their exact fall-back."""
+    B, k, d = 6, 5, 512
+    rows, ldl, P = B * k, (V + 7) // 8 * 8, 2 * ((V + 255) // 256)
+    g = torch.Generator(device="cuda").manual_seed(V)
+    X = torch.randn(rows, d, device=dev(), generator=g).bfloat16()
+    W = (torch.randn(V, d, device=dev(), generator=g) * (0.0 if flat else 0.05)).bfloat16()
+    bias = torch.randn(V, device=dev(), generator=g) * (0.0 if flat else 0.1)
+    logits = torch.zeros(rows, ldl, device=dev(), dtype=torch.bfloat16)
+    stats = torch.full((rows, 4 * P), float("nan"), device=dev())
+    N.call("icap_gemm", BF16, 1, 1, rows, V, d, X.data_ptr(), d, W.data_ptr(), d, logits.data_ptr(), ldl, BF16, bias.data_ptr(),
+           N.EPI_ROWSTATS | N.EPI_B_STATIC, stats.data_ptr(), 4 * P, 0, 1, S())
+    ref = X.double() @ W.double().t() + bias.double()
+    assert flat or rel_err(logits[:, :V], ref) < 6e-3
+    x = logits[:, :V].float()
+    st = stats.view(rows, P, 4)
+    npart = (V + 127) // 128
+    for pi in (0, npart // 2, npart - 1):
+        seg = x[:, pi * 128:min(V, (pi + 1) * 128)]
+        top = seg.topk(min(2, seg.shape[1]), dim=1).values
+        assert torch.equal(st[:, pi, 0], top[:, 0])
+        if seg.shape[1] > 1:
+            assert torch.equal(st[:, pi, 1], top[:, 1])
+        assert torch.allclose(st[:, pi, 2], (seg - top[:, :1]).exp().sum(1), rtol=1e-4)
+    prev = torch.rand(B, k, device=dev(), generator=g) * 1e-4
+    outs = []
+    for use in (False, True):
+        os_ = torch.empty(B, k, device=dev())
+        op = torch.empty(B, k, dtype=torch.int32, device=dev())
+        ot = torch.empty(B, k, dtype=torch.int32, device=dev())
+        gap = torch.empty(B, device=dev())
+        N.call("icap_beam_select", BF16, B, k, V, logits.data_ptr(), ldl, prev.data_ptr(), k, os_.data_ptr(), op.data_ptr(),
+               ot.data_ptr(), gap.data_ptr(), log_domain, stats.data_ptr() if use else None, 4 * P if use else 0, S())
+        torch.cuda.synchronize()
+        outs.append((os_, op, ot, gap))
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    assert torch.allclose(outs[0][0], outs[1][0], rtol=1e-5, atol=1e-8)
+    sm = torch.log_softmax(x, 1) if log_domain else torch.softmax(x, 1)
+    cand = (sm.view(B, k, V) + prev[:, :, None]).view(B, k * V)
+    ref_s = torch.topk(cand, k, dim=1).values
+    assert torch.allclose(outs[1][0], ref_s, rtol=1e-5, atol=1e-7)
 
 
 def test_beam_reorder():

@@ -23,7 +23,7 @@ opar = torch.empty(B, k, dtype=torch.int32, device=dev)
 otok = torch.empty(B, k, dtype=torch.int32, device=dev)
 for _ in range(3):
     N.call("icap_beam_select", BF16, B, k, V, logits.data_ptr(), V, prev.data_ptr(), k, osc.data_ptr(), opar.data_ptr(),
-           otok.data_ptr(), None, 0, S())
+           otok.data_ptr(), None, 0, None, 0, S())
 # cross attention G = 5
 q = torch.randn(rows, d, device=dev, generator=g).bfloat16()
 kv = torch.randn(B * R, 2 * d, device=dev, generator=g).bfloat16()

@@ -1,0 +1,17 @@
+#!/bin/bash
+# Data-parallel A/B on N GPUs (default 8): exchange back-ends and workloads through bench.py.
+N=${1:-8}
+run() {
+  echo "== $*"
+  env "${@:2}" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
+    bench.py --gpus $N --steps 40 --warmup 5 --no-cpu-baseline $1 2>&1 | grep "^{" | tee -a gpurun_out/r2_scale${N}_lines.jsonl | python -c "
+import sys,json
+for l in sys.stdin:
+    d=json.loads(l); e=d['extra']
+    print('  ms_per_step %.3f  samples/s %.0f  e2e %.0f  cache_e2e %s  dp_parity %s  beam5 %s' % (d['ms_per_step'], d['value'], d['e2e']['value'], e.get('train_region_cache_e2e_samples_per_s'), e.get('dp_parity_rel_err'), e.get('beam5_captions_per_s')))
+"
+}
+run "--no-decode" ICAP_DP_PEER=0
+run "--no-decode" ICAP_DP_PEER=1 ICAP_DP_BUCKET_MB=16
+run "--no-decode" ICAP_DP_PEER=1 ICAP_DP_BUCKET_MB=32
+run "--workload modelC" ICAP_DP_PEER=0
