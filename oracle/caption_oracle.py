@@ -28,7 +28,7 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass, asdict
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, Iterator, List, Optional, Tuple
 
 import numpy as np
 import torch
@@ -437,61 +437,65 @@ def synthetic_batch(batch: int, regions: int, dim_features: int, dim_positions: 
     return feats, pos, cap
 
 
+def _walk(prefix: str, children) -> Iterator[Tuple[str, Tuple[int, ...]]]:
+    """Flatten a (name, shape | children) tree the way nn.Module.state_dict() walks registered members."""
+    for name, node in children:
+        if isinstance(node, tuple):
+            yield prefix + name, node
+        else:
+            yield from _walk(prefix + name + ".", node)
+
+
+def _shape_linear(out_f: int, in_f: int, bias: bool = True):
+    return [("weight", (out_f, in_f))] + ([("bias", (out_f,))] if bias else [])
+
+
+def _shape_layer_norm(n: int):
+    return [("weight", (n,)), ("bias", (n,))]
+
+
+def _shape_multihead(d_in: int, dk: int, dv: int):
+    # modules.py MultiHeadAttention.__init__: three bias-free projections, the norm, then the bias-free output projection
+    return [("q_linear", _shape_linear(dk, d_in, False)), ("k_linear", _shape_linear(dk, d_in, False)),
+            ("v_linear", _shape_linear(dv, d_in, False)), ("layer_norm", _shape_layer_norm(d_in)),
+            ("joint_linear", _shape_linear(d_in, dv, False))]
+
+
+def _shape_feed_forward(d_in: int, hidden: int):
+    # modules.py PositionWiseFeedForward.__init__
+    return [("position_wise_1", _shape_linear(hidden, d_in)), ("position_wise_2", _shape_linear(d_in, hidden)),
+            ("layer_norm", _shape_layer_norm(d_in))]
+
+
 def param_shapes(cfg: OracleConfig) -> "Dict[str, Tuple[int, ...]]":
-    """state_dict layout in registration order (SURVEY.md §8a 'state_dict layout')."""
-    d, F_, E = cfg.encode_input_size, cfg.encode_hidden_size, cfg.dim_word_embedding
-    shapes: Dict[str, Tuple[int, ...]] = {}
-
-    def mha(p, d_in, dk, dv):
-        shapes[p + ".q_linear.weight"] = (dk, d_in)
-        shapes[p + ".k_linear.weight"] = (dk, d_in)
-        shapes[p + ".v_linear.weight"] = (dv, d_in)
-        shapes[p + ".layer_norm.weight"] = (d_in,)
-        shapes[p + ".layer_norm.bias"] = (d_in,)
-        shapes[p + ".joint_linear.weight"] = (d_in, dv)
-
-    def ffn(p, d_in, hid):
-        shapes[p + ".position_wise_1.weight"] = (hid, d_in)
-        shapes[p + ".position_wise_1.bias"] = (hid,)
-        shapes[p + ".position_wise_2.weight"] = (d_in, hid)
-        shapes[p + ".position_wise_2.bias"] = (d_in,)
-        shapes[p + ".layer_norm.weight"] = (d_in,)
-        shapes[p + ".layer_norm.bias"] = (d_in,)
-
+    """state_dict layout: the member tree of the reference's Transformer in the order its __init__ methods
+    register it (model.py Encoder / Decoder / Transformer, modules.py blocks), flattened like state_dict() does.  Pinned to
+    the reference's own key list and shapes by tests/test_oracle.py::test_state_dict_layout."""
+    d, dd = cfg.encode_input_size, cfg.decode_input_size
+    enc_block = [("multihead_attention", _shape_multihead(d, cfg.encode_q_k_dim, cfg.encode_v_dim)),
+                 ("feed_forward", _shape_feed_forward(d, cfg.encode_hidden_size))]
+    encoder = []
     if cfg.split_position:
-        shapes["encoder.object_embedding.weight"] = (d, cfg.encode_dim_positions - 4)
-        shapes["encoder.position_embedding.weight"] = (d, 4)
+        encoder.append(("object_embedding", _shape_linear(d, cfg.encode_dim_positions - 4, False)))
+        encoder.append(("position_embedding", _shape_linear(d, 4, False)))
     else:
-        shapes["encoder.position_embedding.weight"] = (d, cfg.encode_dim_positions)
+        encoder.append(("position_embedding", _shape_linear(d, cfg.encode_dim_positions, False)))
     if cfg.split_image_objects:
-        mha("encoder.image_encoder.multihead_attention", d, cfg.encode_q_k_dim, cfg.encode_v_dim)
-        ffn("encoder.image_encoder.feed_forward", d, F_)
-    shapes["encoder.feature_embedding.weight"] = (d, cfg.encode_dim_features)
-    shapes["encoder.norm.weight"] = (d,)
-    shapes["encoder.norm.bias"] = (d,)
-    for i in range(cfg.encode_num_blocks):
-        mha(f"encoder.encoder.{i}.multihead_attention", d, cfg.encode_q_k_dim, cfg.encode_v_dim)
-        ffn(f"encoder.encoder.{i}.feed_forward", d, F_)
-    dd, dF = cfg.decode_input_size, cfg.decode_hidden_size
-    shapes["decoder.word_embedding.weight"] = (cfg.num_vocab, E)
-    shapes["decoder.word_embedding_linear.weight"] = (dd, E)
-    shapes["decoder.position_embedding.pos_table"] = (1, cfg.max_length - 1, dd)
-    shapes["decoder.norm.weight"] = (dd,)
-    shapes["decoder.norm.bias"] = (dd,)
+        encoder.append(("image_encoder", enc_block))
+    encoder += [("feature_embedding", _shape_linear(d, cfg.encode_dim_features, False)), ("norm", _shape_layer_norm(d)),
+                ("encoder", [(str(i), enc_block) for i in range(cfg.encode_num_blocks)])]
+    dec_block = [("self_attention", _shape_multihead(dd, cfg.decode_q_k_dim, cfg.decode_v_dim)),
+                 ("encode_attention", _shape_multihead(dd, cfg.decode_q_k_dim, cfg.decode_v_dim)),
+                 ("feed_forward", _shape_feed_forward(dd, cfg.decode_hidden_size))]
+    decoder = [("word_embedding", [("weight", (cfg.num_vocab, cfg.dim_word_embedding))]),
+               ("word_embedding_linear", _shape_linear(dd, cfg.dim_word_embedding, False)),
+               ("position_embedding", [("pos_table", (1, cfg.max_length - 1, dd))]),          # registered buffer
+               ("norm", _shape_layer_norm(dd))]
     if cfg.move_first_image_feature:
-        shapes["decoder.position_wise_1.weight"] = (dF, dd)
-        shapes["decoder.position_wise_1.bias"] = (dF,)
-        shapes["decoder.position_wise_2.weight"] = (dd, dF)
-        shapes["decoder.position_wise_2.bias"] = (dd,)
-        shapes["decoder.layer_norm.weight"] = (dd,)
-        shapes["decoder.layer_norm.bias"] = (dd,)
-    for i in range(cfg.decode_num_blocks):
-        mha(f"decoder.decoder.{i}.self_attention", dd, cfg.decode_q_k_dim, cfg.decode_v_dim)
-        mha(f"decoder.decoder.{i}.encode_attention", dd, cfg.decode_q_k_dim, cfg.decode_v_dim)
-        ffn(f"decoder.decoder.{i}.feed_forward", dd, dF)
-    shapes["classifer.weight"] = (cfg.num_vocab, dd)
-    shapes["classifer.bias"] = (cfg.num_vocab,)
-    return shapes
+        decoder += _shape_feed_forward(dd, cfg.decode_hidden_size)      # the decoder's own FFN members, registered inline
+    decoder.append(("decoder", [(str(i), dec_block) for i in range(cfg.decode_num_blocks)]))
+    tree = [("encoder", encoder), ("decoder", decoder), ("classifer", _shape_linear(cfg.num_vocab, dd))]
+    return dict(_walk("", tree))
 
 
 def init_state_dict(cfg: OracleConfig, seed: int = 0) -> Dict[str, Tensor]:
