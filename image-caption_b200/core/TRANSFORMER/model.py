@@ -11,5 +11,6 @@ import icap_loader  # noqa: E402
 _pkg = icap_loader.load()
 Transformer = _pkg.Transformer
 GraphedTrainStep = _pkg.GraphedTrainStep
+PrefetchLoader = _pkg.PrefetchLoader
 
-__all__ = ["Transformer", "GraphedTrainStep"]
+__all__ = ["Transformer", "GraphedTrainStep", "PrefetchLoader"]

@@ -108,13 +108,19 @@ class PrefetchLoader:
     def _stage(self, slot: int, batch: Sequence[torch.Tensor]):
         batch = [torch.as_tensor(t) for t in batch]
         shapes = [(tuple(t.shape), t.dtype) for t in batch]
-        if self._host[slot] is None or [(tuple(t.shape), t.dtype) for t in self._host[slot]] != shapes:
-            self._host[slot] = [torch.empty(s, dtype=d).pin_memory() for s, d in shapes]
+        if self._devb[slot] is None or [(tuple(t.shape), t.dtype) for t in self._devb[slot]] != shapes:
             self._devb[slot] = [torch.empty(s, dtype=d, device=self.dev) for s, d in shapes]
+            self._host[slot] = None
         if self._free[slot] is not None:
             self._free[slot].synchronize()         # the previous user of this slot has consumed it
-        for h, t in zip(self._host[slot], batch):
-            h.copy_(t)
+        if all(t.is_pinned() for t in batch):      # already page-locked (a pin_memory=True DataLoader): no staging copy
+            self._host[slot] = batch               # keeps the source alive until the copy below has run
+        else:
+            if self._host[slot] is None or any(not h.is_pinned() or h.shape != t.shape or h.dtype != t.dtype
+                                               for h, t in zip(self._host[slot], batch)):
+                self._host[slot] = [torch.empty(sh, dtype=d).pin_memory() for sh, d in shapes]
+            for h, t in zip(self._host[slot], batch):
+                h.copy_(t)
         ev = torch.cuda.Event()
         with torch.cuda.stream(self.copy_stream):
             for d, h in zip(self._devb[slot], self._host[slot]):

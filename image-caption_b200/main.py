@@ -11,6 +11,7 @@ import torch
 from torch.utils.data import DataLoader
 
 from core.models import DEVICE, TRANSFORMER, SelfCriticNetwork
+from core.TRANSFORMER.model import PrefetchLoader
 from core.config import *          # noqa: F401,F403
 from core.dataset import IndexedCaptions, SyntheticCaptionDataset, TestDataset, TrainDataset
 from core.utils import save_pickle
@@ -124,10 +125,12 @@ def evaluation(split='test', epoch=90, beam_size=None, num_images=64, region_cac
                 captions_out[int(idx)] = captions[i]
         cache.check()
     else:
-        for features, positions, idxs in DataLoader(ds, batch_size=BATCH_SIZE, shuffle=False):
+        # host -> device copies of batch i + 1 run on a copy stream while batch i decodes
+        loader = DataLoader(ds, batch_size=BATCH_SIZE, shuffle=False, pin_memory=True)
+        for features, positions, idxs in PrefetchLoader(loader, DEVICE):
             captions, _ = model.generate_caption(object_features=features, position_features=positions,
                                                  beam_size=beam_size)
-            for i, idx in enumerate(idxs):
+            for i, idx in enumerate(idxs.tolist()):
                 captions_out[int(idx)] = captions[i]
     dt = time.time() - t0
     target_dir = os.path.join(DATA_PATH, f'{split}/{OUTPUT_NAME}/')
