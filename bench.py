@@ -185,6 +185,12 @@ def run_reference(args):
     wl = WORKLOADS[args.workload]
     kw = wl["kw"]
     bs = args.ref_batch or wl["ref_batch"]
+    if not args.ref_batch:
+        # bounded sample: the whole --steps + --warmup run stays near 3 minutes of CPU time (measured on the bench box's 16
+        # cores: ~115 samples/s for model A, ~13 for model C), so a large K shrinks the batch of each step instead
+        rate = 110.0 if wl["gflop_train"] < 20 else 12.0
+        fit = int(rate * 180.0 / (args.steps + max(1, args.warmup)))
+        bs = max(4, min(bs, fit // 4 * 4))
     ref = CpuReference(kw, train=True)
     f, p, c = O.synthetic_batch(bs, wl["regions"], 2048, 84, CAP_LEN, kw["num_vocab"], seed=1234)
     for _ in range(max(1, args.warmup)):

@@ -96,7 +96,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
   return t;
 }
 
-template <int BN, bool TWO, bool A_KMAJOR, bool B_KMAJOR, typename TO>
+template <int BN, bool TWO, bool A_KMAJOR, bool B_KMAJOR, typename TO, bool STATS = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const GemmArgs g) {
@@ -313,14 +313,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (g.epi == 2 && row < M && c_begin < nchunks)
         aux_load(a_cur, aux + (int64_t)row * g.ldaux + n0 + c_begin * 32, aux_vec && n0 + c_begin * 32 + 32 <= N,
                  N - n0 - c_begin * 32);
-      // lane j's bias of every chunk of this warp, requested before the accumulator wait (a load per chunk inside the
-      // loop left its whole latency exposed in front of the shared-memory broadcast: ncu source page, round 2)
-      float bias_c[BN / 64];
-#pragma unroll
-      for (int u = 0; u < BN / 64; ++u) {
-        const int cc = n0 + (c_begin + u) * 32 + lane;
-        bias_c[u] = (add_bias && cc < N) ? __ldg(g.bias + cc) : 0.f;
-      }
       mbar_wait_t<TWO>(tfull_bar + 8 * as, aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (tr && it == 0 && ew == 0 && lane == 0) tr[6] = gtimer();
@@ -336,9 +328,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int col0 = n0 + c * 32;
         if (g.epi == 2 && row < M && c + 1 < nchunks)
           aux_load(a_nxt, aux + (int64_t)row * g.ldaux + col0 + 32, aux_vec && col0 + 64 <= N, N - col0 - 32);
-        float bias_l = bias_c[0];               // lane j holds bias[col0 + j]; broadcast through smem below
-#pragma unroll
-        for (int u = 1; u < BN / 64; ++u) if (c - c_begin == u) bias_l = bias_c[u];
+        float bias_l = 0.f;                     // lane j holds bias[col0 + j]; broadcast through smem below
+        if (add_bias && col0 + lane < N) bias_l = __ldg(g.bias + col0 + lane);
         uint32_t r[32];
         tmem_ld32(tacc + (uint32_t)(c * 32), r);
         if (c == nchunks - 1) {                 // accumulator fully read: hand the TMEM stage back to the MMA warp
@@ -370,8 +361,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else if (g.epi == 2) {
           if (row < M) aux_mask<TO>(a_cur, v);
           a_cur = a_nxt;
-        } else if (g.epi == 3) {
-          if constexpr (ESZ == 2) {
+        }
+        if constexpr (STATS) {
+          {
             // The epilogue warps have two warps per scheduler: dependent chains cost their full latency.  So: top-2 on
             // PACKED bf16 pairs in two independent chains (3 instructions per two logits), the exp-sum in four
             // accumulators, the bf16 rounding shared with the store below (same cvt, merged by the compiler).
@@ -489,7 +481,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
-      if (g.epi == 3 && row < M) {
+      if (STATS && row < M) {
         float* sp = const_cast<float*>(reinterpret_cast<const float*>(g.aux)) + (int64_t)row * g.ldaux +
                     (int64_t)((tile % g.tiles_n) * 2 + half) * 4;
         *reinterpret_cast<float4*>(sp) = make_float4(st_m1, st_m2, st_s, 0.f);
@@ -571,10 +563,10 @@ int num_sms_all() {
   return g_num_sms;
 }
 
-template <int BN, bool TWO, bool AK, bool BKM, typename TO>
+template <int BN, bool TWO, bool AK, bool BKM, typename TO, bool STATS = false>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmArgs& g, cudaStream_t st) {
   static bool attr_done = false;
-  auto kern = gemm_tc_kernel<BN, TWO, AK, BKM, TO>;
+  auto kern = gemm_tc_kernel<BN, TWO, AK, BKM, TO, STATS>;
   using CF = Cfg<BN, TWO>;
   if (!attr_done) {
     ICAP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES));
@@ -694,9 +686,9 @@ int icap_gemm_bf16_launch(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int6
   }
   if (epi == 3) {
     ICAP_ARG(c_dtype == ICAP_BF16 && !accumulate && split_k <= 1 && aux && ((uintptr_t)aux & 15) == 0 &&
-             ldaux >= 8 * ceil_div64(N, 256) && ldaux % 4 == 0 && best_cfg == 1,
-             "icap_gemm(bf16): the row-statistics epilogue needs bf16 C, no accumulation and a 16-byte aligned stats buffer "
-             "of >= 8 * ceil(N / 256) floats per row");
+             ldaux >= 8 * ceil_div64(N, 256) && ldaux % 4 == 0 && best_cfg == 1 && a_kmajor && b_kmajor,
+             "icap_gemm(bf16): the row-statistics epilogue needs K-major A and B, bf16 C, no accumulation and a 16-byte "
+             "aligned stats buffer of >= 8 * ceil(N / 256) floats per row");
   }
   if (split_k > 1)
     ICAP_ARG(can_split, "icap_gemm(bf16): split_k>1 needs fp32 C, accumulate!=0, no bias and no activation epilogue");
@@ -734,6 +726,7 @@ int icap_gemm_bf16_launch(int a_kmajor, int b_kmajor, int64_t M, int64_t N, int6
   (c_dtype == ICAP_F32 ? launch<BNV, TW, AK, BKM, float>(ta, tb, tc, g, st)                              \
                        : launch<BNV, TW, AK, BKM, bf16>(ta, tb, tc, g, st))
 #define GO(AK, BKM) (two ? GO2(256, true, AK, BKM) : BN == 256 ? GO2(256, false, AK, BKM) : GO2(128, false, AK, BKM))
+  if (epi == 3) return launch<256, false, true, true, bf16, true>(ta, tb, tc, g, st);   // the one row-statistics build
   if (a_kmajor && b_kmajor) return GO(true, true);
   if (a_kmajor && !b_kmajor) return GO(true, false);
   return GO(false, false);

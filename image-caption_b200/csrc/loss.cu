@@ -64,25 +64,39 @@ xent_kernel(int V, T* __restrict__ logits, int64_t ldl, const int* __restrict__ 
     mx = fmaxf(mx, v);
   }
   mx = block_max(mx, red);
+  // bf16 logits carry 8 bits: the approximate exponential (2 ulp of fp32) is far below their rounding; fp32 mode keeps expf
+  constexpr bool kFastExp = sizeof(T) == 2;
+  const float x_tgt = valid ? to_f32(x[tgt]) : 0.f;            // read before the gradients overwrite the row
   float sum = 0.f;
-  for (int j = threadIdx.x; j < V; j += NT) sum += expf((cached ? xs[j] : to_f32(x[j])) - mx);
+  if (cached) {
+    // the row sits in shared memory: replace every logit by exp(x - max) once; the gradient pass only scales it
+    for (int j = threadIdx.x; j < V; j += NT) {
+      const float e = kFastExp ? __expf(xs[j] - mx) : expf(xs[j] - mx);
+      xs[j] = e;
+      sum += e;
+    }
+  } else {
+    for (int j = threadIdx.x; j < V; j += NT) sum += kFastExp ? __expf(to_f32(x[j]) - mx) : expf(to_f32(x[j]) - mx);
+  }
   sum = block_sum(sum, red);
   const float lse = mx + logf(sum);
-  if (threadIdx.x == 0) row_loss[row] = valid ? lse - (cached ? xs[tgt] : to_f32(x[tgt])) : 0.f;
+  if (threadIdx.x == 0) row_loss[row] = valid ? lse - x_tgt : 0.f;
   if (write_grad) {
     const float sc = valid ? *inv_count : 0.f;
+    const float inv_sum = 1.f / sum;
     for (int j = threadIdx.x * 4; j < V4; j += NT * 4) {
       float g[4];
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        const float xv = cached ? xs[j + t] : to_f32(x[j + t]);
-        g[t] = (expf(xv - lse) - ((j + t) == tgt ? 1.f : 0.f)) * sc;
+        const float pr = cached ? xs[j + t] * inv_sum
+                                : (kFastExp ? __expf(to_f32(x[j + t]) - lse) : expf(to_f32(x[j + t]) - lse));
+        g[t] = (pr - ((j + t) == tgt ? 1.f : 0.f)) * sc;
       }
       store4(x + j, g);
     }
     for (int j = V4 + threadIdx.x; j < V; j += NT) {
-      const float xv = cached ? xs[j] : to_f32(x[j]);
-      x[j] = from_f32<T>((expf(xv - lse) - (j == tgt ? 1.f : 0.f)) * sc);
+      const float pr = cached ? xs[j] * inv_sum : (kFastExp ? __expf(to_f32(x[j]) - lse) : expf(to_f32(x[j]) - lse));
+      x[j] = from_f32<T>((pr - (j == tgt ? 1.f : 0.f)) * sc);
     }
   }
 }
