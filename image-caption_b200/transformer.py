@@ -559,7 +559,7 @@ class DataParallel:
         self.inv = torch.zeros(1, dtype=torch.float32, device=eng.dev)
         # Exchange back-end.  ICAP_DP_PEER=1: libicap's own NVLink peer-memory kernels (PeerReduce); 0: NCCL; unset: the
         # peer kernels when the fabric offers an NVSwitch multicast mapping of the gradient buffer (in-switch reduction),
-        # NCCL otherwise.  Measured on 8 x B200 (profiles/r2_scale8.log): 4.71 ms/step against NCCL's 5.02 (1 GPU 4.44);
+        # NCCL otherwise.  Measured on 8 x B200 (profiles/r2_scale8_backends.log, r2_dp_ab_4gpu.log): 4.71 ms/step against NCCL's 5.02 (1 GPU 4.44);
         # on 2 GPUs both take 4.73.
         self.peer: Optional[PeerReduce] = None
         mode = os.environ.get("ICAP_DP_PEER", "auto")

@@ -1,6 +1,8 @@
 """Device timeline of ONE replay of the graphed training step (CUPTI through torch.profiler): per-kernel totals, the
 time during which NO kernel is running, and the busy time per stream -- what the 4.4 ms step is made of.
-    python tools/train_timeline.py [--batch 256] [--out gpurun_out/train_timeline.csv]"""
+    python tools/train_timeline.py [--batch 256] [--out gpurun_out/train_timeline.csv]
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/train_timeline.py   # the data-parallel
+        step: rank 0's timeline with the gradient exchange kernels on the communication stream"""
 import argparse
 import os
 import sys
@@ -18,14 +20,21 @@ def main():
     ap.add_argument("--out", default="gpurun_out/train_timeline.csv")
     args = ap.parse_args()
     pkg = icap_loader.load()
-    dev = torch.device("cuda:0")
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    dev = torch.device(f"cuda:{int(os.environ.get('LOCAL_RANK', '0'))}")
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
     kw = dict(num_vocab=10000, max_length=22, encode_dim_positions=84, encode_dim_features=2048, output_name="bench",
               dropout=0.2)
     model = pkg.Transformer(device=dev, **kw).to(dev).train()
-    f, p, c = O.synthetic_batch(args.batch, 36, 2048, 84, 22, 10000, seed=1234)
+    f, p, c = O.synthetic_batch(args.batch, 36, 2048, 84, 22, 10000, seed=1234 + rank)
     f, p, c = f.to(dev), p.to(dev), c.to(dev)
-    gs = pkg.GraphedTrainStep(model, args.batch, 36, 22, lr=5e-4)
+    dp = pkg.DataParallel(model, dist) if dist is not None else None
+    gs = pkg.GraphedTrainStep(model, args.batch, 36, 22, lr=5e-4, dp=dp)
     gs.load(f, p, c)
     for _ in range(5):
         gs.step()
@@ -36,20 +45,31 @@ def main():
         gs.step()
     e1.record()
     torch.cuda.synchronize()
-    print(f"un-profiled: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per step")
+    if rank == 0:
+        print(f"un-profiled: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per step ({world} rank(s))")
     from torch.profiler import profile, ProfilerActivity
+    if dist is not None:
+        dist.barrier()
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         gs.step()
+        gs.step()
         torch.cuda.synchronize()
+    if rank != 0:
+        torch.cuda.synchronize()
+        os._exit(0)
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range is not None]
     evs = [e for e in evs if "memcpy" not in e.name.lower()]
     evs.sort(key=lambda e: e.time_range.start)
+    # two replays were profiled (the second starts from a settled pipeline): keep the second
+    half = len(evs) // 2
+    evs = evs[half:]
     t0 = evs[0].time_range.start
     end = max(e.time_range.end for e in evs)
     with open(args.out, "w") as fh:
-        fh.write("idx,kernel,start_us,dur_us\n")
+        fh.write("idx,kernel,start_us,dur_us,stream\n")
         for i, e in enumerate(evs):
-            fh.write(f"{i},\"{e.name[:100]}\",{e.time_range.start - t0:.2f},{e.time_range.end - e.time_range.start:.2f}\n")
+            fh.write(f"{i},\"{e.name[:100]}\",{e.time_range.start - t0:.2f},{e.time_range.end - e.time_range.start:.2f},"
+                     f"{getattr(e, 'device_resource_id', getattr(e, 'device_index', ''))}\n")
     # union of busy intervals
     busy, cur_s, cur_e = 0.0, None, None
     for e in evs:
