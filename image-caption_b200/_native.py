@@ -36,6 +36,7 @@ SIGNATURES = {
     "icap_argmax": [I, L, L, P, L, P, L, P, P],
     "icap_beam_select": [I, L, L, L, P, L, P, L, P, P, P, P, I, P, L, P],
     "icap_beam_reorder": [L, L, L, L, P, P, P, P, P, P, P],
+    "icap_decode_embed_ln": [I, L, L, L, L, L, P, P, P, P, P, P, P, P, P, P, P, P, I, F, P],
     "icap_log_softmax_argmax": [L, L, P, L, P, L, P, P],
     "icap_log_softmax_bwd": [L, L, P, L, P, L, P, L, P],
     "icap_mha_decode": [I, L, L, L, L, L, P, L, P, L, P, L, L, P, L, P, L, P, L, I, P, L, P, P],

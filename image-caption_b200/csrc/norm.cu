@@ -485,6 +485,75 @@ add_ln_bwd_cols8_kernel(int M, int d, const T* __restrict__ dy1, const T* __rest
 
 inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
+// Start of a KV-cached decode step in ONE launch (was beam_reorder + embed_fwd + add_ln_fwd8: three dependent launches):
+// per row (one warp), (1) optionally the beam bookkeeping of the step before -- tokens_out[row, 0..t-1] =
+// tokens_in[parent row], tokens_out[row, t] = the chosen token, the same gather on the KV-cache slot table
+// (model.py:194-198) -- then (2) y[row] = LayerNorm(table[token] + pos_row) * gamma + beta with exactly the arithmetic of
+// embed_fwd_kernel followed by add_ln_fwd8_kernel (decoder input of position t, model.py:432-436), rowscale = token != pad.
+template <int NIT, typename T>
+__global__ void __launch_bounds__(256)
+decode_embed_ln_kernel(int M, int d, int k, int Tmax, int t, const int* __restrict__ parent,
+                       const int* __restrict__ token, const int* __restrict__ tok_in, int* __restrict__ tok_out,
+                       const int* __restrict__ slot_in, int* __restrict__ slot_out, const T* __restrict__ table,
+                       const T* __restrict__ pos_row, const float* __restrict__ gamma, const float* __restrict__ beta,
+                       T* __restrict__ y, float* __restrict__ rowscale, int pad, float eps) {
+  pdl_prologue();
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  int tk;
+  if (parent) {
+    const int src = (row / k) * k + parent[row];
+    tk = token[row];
+    for (int j = lane; j <= t && j < Tmax; j += 32) {
+      tok_out[(int64_t)row * Tmax + j] = (j == t) ? tk : tok_in[(int64_t)src * Tmax + j];
+      if (slot_in) slot_out[(int64_t)row * Tmax + j] = (j == t) ? row : slot_in[(int64_t)src * Tmax + j];
+    }
+  } else {
+    tk = tok_in[(int64_t)row * Tmax + t];
+  }
+  const int nvec = d >> 3;
+  float v[NIT][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int vi = it * 32 + lane;
+    if (vi < nvec) {
+      load8(table + (int64_t)tk * d + vi * 8, v[it]);
+      float rr[8];
+      load8(pos_row + vi * 8, rr);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[it][j] += rr[j];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[it][j];
+    }
+  }
+  const float mean = warp_sum(sum) / (float)d;
+  float sq = 0.f;
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int vi = it * 32 + lane;
+    if (vi < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float c = v[it][j] - mean; sq += c * c; }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)d + eps);
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int vi = it * 32 + lane;
+    if (vi < nvec) {
+      float g[8], b[8], o[8];
+      load8(gamma + vi * 8, g);
+      load8(beta + vi * 8, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = ((v[it][j] - mean) * rstd * g[j] + b[j]) * 1.f;
+      store8(y + (int64_t)row * d + vi * 8, o);
+    }
+  }
+  if (lane == 0 && rowscale) rowscale[row] = tk != pad ? 1.f : 0.f;
+}
+
 }  // namespace
 
 extern "C" int icap_add_ln_fwd(int a_dtype, int act_dtype, int64_t M, int64_t d, void* a, const void* res,
@@ -652,4 +721,36 @@ extern "C" int icap_add_ln_bwd_params(int act_dtype, int64_t M, int64_t d, const
   alignas(16) static const float dummy_gamma[4] = {0.f, 0.f, 0.f, 0.f};     // not read by the column kernel, only null-checked
   return add_ln_bwd_impl(2, act_dtype, M, d, dy1, dy2, s, mean, rstd, dummy_gamma, rowscale, const_cast<void*>(ds),
                          const_cast<void*>(da), dgamma, dbeta, dbias2, 0.f, 0, nullptr, stream);
+}
+
+extern "C" int icap_decode_embed_ln(int act_dtype, int64_t rows, int64_t d, int64_t k, int64_t Tmax, int64_t t,
+                                    const int* parent, const int* token, const int* tok_in, int* tok_out,
+                                    const int* slot_in, int* slot_out, const void* table, const void* pos_row,
+                                    const float* gamma, const float* beta, void* y, float* rowscale, int pad_idx,
+                                    float eps, void* stream) {
+  ICAP_ARG(rows > 0 && d > 0 && k >= 1 && rows % k == 0 && Tmax > 0 && t >= 0 && t < Tmax && tok_in && table && pos_row &&
+           gamma && beta && y, "icap_decode_embed_ln: null/empty argument");
+  ICAP_ARG(d % 8 == 0 && d <= 1024 && ((uintptr_t)table & 15) == 0 && ((uintptr_t)pos_row & 15) == 0 &&
+           ((uintptr_t)y & 15) == 0 && ((uintptr_t)gamma & 15) == 0 && ((uintptr_t)beta & 15) == 0,
+           "icap_decode_embed_ln: width must be a multiple of 8 (<= 1024) and every row pointer 16-byte aligned");
+  ICAP_ARG(parent == nullptr || (token && tok_out && tok_out != tok_in && (slot_in == nullptr || (slot_out && slot_out != slot_in))),
+           "icap_decode_embed_ln: the beam reorder is out of place and needs token / tok_out (and slot_out with slot_in)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)ceil_div64(rows, 8);
+#define GODE(NIT, T)                                                                                                   \
+  icap_launch(decode_embed_ln_kernel<NIT, T>, grid, 256, 0, st, (int)rows, (int)d, (int)k, (int)Tmax, (int)t, parent, token,  \
+              tok_in, tok_out, slot_in, slot_out, (const T*)table, (const T*)pos_row, gamma, beta, (T*)y, rowscale, pad_idx, \
+              eps)
+#define GODET(T)                                                                                                       \
+  do {                                                                                                                 \
+    if (d <= 256) GODE(1, T);                                                                                          \
+    else if (d <= 512) GODE(2, T);                                                                                     \
+    else GODE(4, T);                                                                                                   \
+  } while (0)
+  if (act_dtype == ICAP_F32) GODET(float);
+  else GODET(bf16);
+#undef GODET
+#undef GODE
+  ICAP_LAUNCH_CHECK("icap_decode_embed_ln");
+  return 0;
 }

@@ -1002,16 +1002,36 @@ class CaptionEngine:
         gaps = torch.zeros(T, B, dtype=torch.float32, device=self.dev) if want_gaps else None
         ldl = (V + 7) // 8 * 8
         cur = 0
-        for t in range(T):
-            tk = tok[cur]
-            x0 = self.new(rows, d)
+        fused_start = d % 8 == 0 and d <= 1024 and os.environ.get("ICAP_DECODE_FUSED_START", "1") != "0"
+
+        def step_input(t, tk, reorder=None):
+            """Decoder input of position t (model.py:432-436): folded embedding row + positional row -> decoder.norm;
+            with `reorder` = (parent, token, tok_out, slot_in, slot_out) the beam bookkeeping of step t - 1 runs in
+            the same launch (icap_decode_embed_ln)."""
+            x = self.new(rows, d)
             rowscale = self.new(rows, dtype=torch.float32)
+            pos_row = self.pos_table_act.data_ptr() + t * d * esz
+            if fused_start:
+                par, tokn, tko, sli, slo = reorder if reorder is not None else (None,) * 5
+                call("icap_decode_embed_ln", self.act, rows, d, k, Tmax, t, _ptr(par), _ptr(tokn), tk.data_ptr(), _ptr(tko),
+                     _ptr(sli), _ptr(slo), table.data_ptr(), pos_row, self.p("decoder.norm.weight"),
+                     self.p("decoder.norm.bias"), x.data_ptr(), rowscale.data_ptr(), cfg.pad_idx, LN_EPS, s())
+                return x, rowscale
+            if reorder is not None:
+                par, tokn, tko, sli, slo = reorder
+                call("icap_beam_reorder", B, k, Tmax, t - 1, par.data_ptr(), tokn.data_ptr(), tk.data_ptr(), tko.data_ptr(),
+                     _ptr(sli), _ptr(slo), s())
+                tk = tko
+            x0 = self.new(rows, d)
             call("icap_embed_fwd", self.act, self.act, tk.data_ptr() + 4 * t, Tmax, rows, d, table.data_ptr(),
                  x0.data_ptr(), rowscale.data_ptr(), cfg.pad_idx, s())
-            x = self.new(rows, d)
-            call("icap_add_ln_fwd", self.act, self.act, rows, d, x0.data_ptr(), self.pos_table_act.data_ptr() + t * d * esz,
-                 1, self.p("decoder.norm.weight"), self.p("decoder.norm.bias"), None, x.data_ptr(), None, None, 0, 0.0, 0,
-                 None, LN_EPS, s())
+            call("icap_add_ln_fwd", self.act, self.act, rows, d, x0.data_ptr(), pos_row, 1, self.p("decoder.norm.weight"),
+                 self.p("decoder.norm.bias"), None, x.data_ptr(), None, None, 0, 0.0, 0, None, LN_EPS, s())
+            return x, rowscale
+
+        x, rowscale = step_input(0, tok[cur])
+        for t in range(T):
+            tk = tok[cur]
             for i in range(cfg.decode_num_blocks):
                 pre = f"decoder.decoder.{i}"
                 last = i == cfg.decode_num_blocks - 1
@@ -1061,14 +1081,19 @@ class CaptionEngine:
             if k == 1:
                 call("icap_argmax", self.act, rows, V, logits.data_ptr(), ldl, tk.data_ptr() + 4 * (t + 1), Tmax,
                      gaps[t].data_ptr() if gaps is not None else None, s())
+                if t + 1 < T:
+                    x, rowscale = step_input(t + 1, tk)
             else:
                 kin = 1 if t == 0 else k       # step 0: all beams hold <START>, only beam 0 competes (model.py:146-166)
                 call("icap_beam_select", self.act, B, kin, V, logits.data_ptr(), ldl * (k if t == 0 else 1),
                      score[cur].data_ptr() if t > 0 else None, k, score[cur ^ 1].data_ptr(), parent.data_ptr(),
                      newtok.data_ptr(), gaps[t].data_ptr() if gaps is not None else None, int(log_domain),
                      _ptr(stats), (stats.shape[1] * (k if t == 0 else 1)) if stats is not None else 0, s())
-                call("icap_beam_reorder", B, k, Tmax, t, parent.data_ptr(), newtok.data_ptr(), tk.data_ptr(),
-                     tok[cur ^ 1].data_ptr(), slot[cur].data_ptr(), slot[cur ^ 1].data_ptr(), s())
+                if t + 1 < T:       # bookkeeping of this step + input of the next one in one launch
+                    x, rowscale = step_input(t + 1, tk, (parent, newtok, tok[cur ^ 1], slot[cur], slot[cur ^ 1]))
+                else:
+                    call("icap_beam_reorder", B, k, Tmax, t, parent.data_ptr(), newtok.data_ptr(), tk.data_ptr(),
+                         tok[cur ^ 1].data_ptr(), slot[cur].data_ptr(), slot[cur ^ 1].data_ptr(), s())
                 cur ^= 1
         ids = tok[cur].view(B, k, Tmax)[:, 0, :]
         if attn is not None:

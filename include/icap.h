@@ -152,6 +152,16 @@ int icap_log_softmax_argmax(int64_t M, int64_t V, const float* x, int64_t ldx, f
 int icap_log_softmax_bwd(int64_t M, int64_t V, const float* logp, int64_t ldp, const float* dlogp, int64_t ldd, float* dx,
                          int64_t ldx, void* stream);
 
+/* Start of a KV-cached decode step in one launch: (parent != NULL) the beam bookkeeping of the previous step exactly as
+ * icap_beam_reorder(B = rows / k, k, Tmax, t - 1, ...) does it -- position t receives `token` -- and then, for every row,
+ * y = LayerNorm(table[token of position t] + pos_row) * gamma + beta and rowscale = (token != pad_idx): the decoder
+ * input of position t (word embedding folded with word_embedding_linear, positional row, decoder.norm; model.py:432-436)
+ * with the arithmetic of icap_embed_fwd + icap_add_ln_fwd.  parent == NULL: tokens are read from tok_in[row, t].
+ * table / pos_row / y: act_dtype rows of width d (multiple of 8, <= 1024). */
+int icap_decode_embed_ln(int act_dtype, int64_t rows, int64_t d, int64_t k, int64_t Tmax, int64_t t, const int* parent,
+                         const int* token, const int* tok_in, int* tok_out, const int* slot_in, int* slot_out,
+                         const void* table, const void* pos_row, const float* gamma, const float* beta, void* y,
+                         float* rowscale, int pad_idx, float eps, void* stream);
 /* Reorder token buffer (and KV-cache slot table) by parent and append the new token: model.py:194-198. */
 int icap_beam_reorder(int64_t B, int64_t k, int64_t Tmax, int64_t t, const int* parent, const int* token,
                       const int* tok_in, int* tok_out, const int* slot_in, int* slot_out, void* stream);

@@ -770,6 +770,56 @@ def test_classifier_rowstats_feed_beam_select(log_domain, V, flat):
     assert torch.allclose(outs[1][0], ref_s, rtol=1e-5, atol=1e-7)
 
 
+@pytest.mark.parametrize("code,d,k", [(BF16, 512, 5), (BF16, 1024, 3), (F32, 256, 1), (BF16, 512, 1)])
+def test_decode_embed_ln_equals_reorder_embed_ln(code, d, k):
+    """icap_decode_embed_ln == icap_beam_reorder -> icap_embed_fwd -> icap_add_ln_fwd, bit for bit (same arithmetic order),
+    with and without the beam bookkeeping."""
+    dt = torch.float32 if code == F32 else torch.bfloat16
+    B, Tmax, t, V, pad = 7, 22, 6, 300, 0
+    rows = B * k
+    g = torch.Generator(device="cuda").manual_seed(d + k)
+    table = torch.randn(V, d, device=dev(), generator=g).to(dt)
+    pos = torch.randn(Tmax, d, device=dev(), generator=g).to(dt)
+    gamma = torch.rand(d, device=dev(), generator=g) + 0.5
+    beta = torch.randn(d, device=dev(), generator=g) * 0.1
+    tok_in = torch.randint(0, V, (rows, Tmax), device=dev(), generator=g, dtype=torch.int32)
+    slot_in = torch.randint(0, rows, (rows, Tmax), device=dev(), generator=g, dtype=torch.int32)
+    parent = torch.randint(0, k, (B, k), device=dev(), generator=g, dtype=torch.int32)
+    token = torch.randint(0, V, (B, k), device=dev(), generator=g, dtype=torch.int32)
+    token[0, 0] = pad
+    for reorder in ([True, False] if k > 1 else [False]):
+        # reference: the three separate launches
+        if reorder:
+            tok_ref, slot_ref = torch.zeros_like(tok_in), torch.zeros_like(slot_in)
+            N.call("icap_beam_reorder", B, k, Tmax, t - 1, parent.data_ptr(), token.data_ptr(), tok_in.data_ptr(),
+                   tok_ref.data_ptr(), slot_in.data_ptr(), slot_ref.data_ptr(), S())
+        else:
+            tok_ref, slot_ref = tok_in, slot_in
+        x0 = torch.empty(rows, d, device=dev(), dtype=dt)
+        rs_ref = torch.empty(rows, device=dev())
+        N.call("icap_embed_fwd", code, code, tok_ref.data_ptr() + 4 * t, Tmax, rows, d, table.data_ptr(), x0.data_ptr(),
+               rs_ref.data_ptr(), pad, S())
+        y_ref = torch.empty(rows, d, device=dev(), dtype=dt)
+        N.call("icap_add_ln_fwd", code, code, rows, d, x0.data_ptr(), pos[t].data_ptr(), 1, gamma.data_ptr(), beta.data_ptr(),
+               None, y_ref.data_ptr(), None, None, 0, 0.0, 0, None, 1e-6, S())
+        # fused
+        tok_out, slot_out = torch.zeros_like(tok_in), torch.zeros_like(slot_in)
+        y = torch.empty(rows, d, device=dev(), dtype=dt)
+        rs = torch.empty(rows, device=dev())
+        N.call("icap_decode_embed_ln", code, rows, d, k, Tmax, t, parent.data_ptr() if reorder else None,
+               token.data_ptr() if reorder else None, tok_in.data_ptr(), tok_out.data_ptr() if reorder else None,
+               slot_in.data_ptr() if reorder else None, slot_out.data_ptr() if reorder else None, table.data_ptr(),
+               pos[t].data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), rs.data_ptr(), pad, 1e-6, S())
+        torch.cuda.synchronize()
+        assert torch.equal(y, y_ref) and torch.equal(rs, rs_ref)
+        if reorder:
+            assert torch.equal(tok_out[:, :t + 1], tok_ref[:, :t + 1]) and torch.equal(slot_out[:, :t + 1], slot_ref[:, :t + 1])
+            assert float(rs[0]) == 0.0
+    with pytest.raises(N.IcapError):
+        N.call("icap_decode_embed_ln", code, rows, 30, k, Tmax, t, None, None, tok_in.data_ptr(), None, None, None,
+               table.data_ptr(), pos[t].data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), None, pad, 1e-6, S())
+
+
 def test_beam_reorder():
     B, k, Tmax, t = 4, 3, 8, 2
     g = torch.Generator(device="cuda").manual_seed(2)

@@ -53,10 +53,12 @@ def main():
         for i, (n, s, d, g) in enumerate(rows):
             fh.write(f"{i},\"{n[:90]}\",{s:.2f},{d:.2f},{g:.2f}\n")
     print(f"{len(rows)} kernels, {total:.1f} us from first start to last end (profiled replay)")
-    # one decode step: between two beam_reorder (or argmax) kernels
-    marks = [i for i, r in enumerate(rows) if "beam_reorder" in r[0] or "argmax" in r[0]]
+    # one decode step: from one step-start kernel (decode_embed_ln; embed_fwd in the unfused build) to the next
+    marks = [i for i, r in enumerate(rows) if "decode_embed_ln" in r[0]]
+    if not marks:
+        marks = [i for i, r in enumerate(rows) if "embed_fwd" in r[0]]
     if len(marks) > args.step + 1:
-        a, b = marks[args.step] + 1, marks[args.step + 1] + 1
+        a, b = marks[args.step], marks[args.step + 1]
         seg = rows[a:b]
         print(f"-- step {args.step + 1}: {len(seg)} kernels, {seg[-1][1] + seg[-1][2] - seg[0][1]:.1f} us; "
               f"sum of durations {sum(r[2] for r in seg):.1f} us, sum of positive gaps {sum(max(0, r[3]) for r in seg):.1f} us")
