@@ -353,8 +353,13 @@ def test_full_size_decode_properties_bf16(monkeypatch):
         assert bool((ids[:, 0] == 1).all()) and int(ids.min()) >= 0 and int(ids.max()) < 10000
         monkeypatch.setenv("ICAP_DECODE_GRAPH", "0")
         eager = m.beam_search(f, p, beam_size=k) if k > 1 else m.generate_caption_vector(f, p)[0][:, :22]
-        monkeypatch.delenv("ICAP_DECODE_GRAPH")
         assert torch.equal(ids, eager)
+        # the step start as three launches (beam reorder, embedding, LayerNorm) instead of icap_decode_embed_ln
+        monkeypatch.setenv("ICAP_DECODE_FUSED_START", "0")
+        unfused = m.beam_search(f, p, beam_size=k) if k > 1 else m.generate_caption_vector(f, p)[0][:, :22]
+        monkeypatch.delenv("ICAP_DECODE_FUSED_START")
+        monkeypatch.delenv("ICAP_DECODE_GRAPH")
+        assert torch.equal(ids, unfused)
         part = m.beam_search(f[128:256], p[128:256], beam_size=k) if k > 1 else \
             m.generate_caption_vector(f[128:256], p[128:256])[0][:, :22]
         same = (part == ids[128:256]).all(dim=1).float().mean()
