@@ -14,6 +14,23 @@ from core.config import *          # noqa: F401,F403  (the reference does the sa
 from core.utils import decode_captions
 
 
+# keyword of the model constructors -> the core/config.py constant of the same name in upper case
+_CONFIG_KEYWORDS = ("encode_dim_positions", "encode_dim_features", "encode_input_size", "encode_q_k_dim", "encode_v_dim",
+                    "encode_hidden_size", "encode_num_blocks", "encode_num_heads", "dim_word_embedding",
+                    "decode_input_size", "decode_q_k_dim", "decode_v_dim", "decode_hidden_size", "decode_num_blocks",
+                    "decode_num_heads", "dropout", "encode_mask", "pad_idx", "split_position", "split_image_objects")
+
+
+def _model_kwargs(num_vocab):
+    """Constructor arguments of Transformer / PolicyNetwork taken from core/config.py (the reference spells the same 24
+    keywords out at both call sites, models.py:68-94 and :141-166)."""
+    cfg = globals()
+    kw = {name: cfg[name.upper()] for name in _CONFIG_KEYWORDS}
+    kw.update(num_vocab=num_vocab, max_length=MAX_LENGTH + 2, device=DEVICE,
+              move_first_image_feature=MOVE_FIRST_IMAGE_FAETURE)        # (sic) the constant's spelling in config.py
+    return kw
+
+
 class MODEL_init:
 
     def __init__(self):
@@ -74,31 +91,7 @@ class TRANSFORMER(MODEL_init):
 
     def __init__(self):
         super(TRANSFORMER, self).__init__()
-        self.model = Transformer(num_vocab=self.num_vocab,
-                                 max_length=MAX_LENGTH + 2,
-                                 encode_dim_positions=ENCODE_DIM_POSITIONS,
-                                 encode_dim_features=ENCODE_DIM_FEATURES,
-                                 encode_input_size=ENCODE_INPUT_SIZE,
-                                 encode_q_k_dim=ENCODE_Q_K_DIM,
-                                 encode_v_dim=ENCODE_V_DIM,
-                                 encode_hidden_size=ENCODE_HIDDEN_SIZE,
-                                 encode_num_blocks=ENCODE_NUM_BLOCKS,
-                                 encode_num_heads=ENCODE_NUM_HEADS,
-                                 dim_word_embedding=DIM_WORD_EMBEDDING,
-                                 decode_input_size=DECODE_INPUT_SIZE,
-                                 decode_q_k_dim=DECODE_Q_K_DIM,
-                                 decode_v_dim=DECODE_V_DIM,
-                                 decode_hidden_size=DECODE_HIDDEN_SIZE,
-                                 decode_num_blocks=DECODE_NUM_BLOCKS,
-                                 decode_num_heads=DECODE_NUM_HEADS,
-                                 dropout=DROPOUT,
-                                 device=DEVICE,
-                                 output_name=OUTPUT_NAME,
-                                 encode_mask=ENCODE_MASK,
-                                 pad_idx=PAD_IDX,
-                                 move_first_image_feature=MOVE_FIRST_IMAGE_FAETURE,
-                                 split_position=SPLIT_POSITION,
-                                 split_image_objects=SPLIT_IMAGE_OBJECTS).to(DEVICE)
+        self.model = Transformer(output_name=OUTPUT_NAME, **_model_kwargs(self.num_vocab)).to(DEVICE)
         # Adam(lr=LEARNING_RATE) state lives in the engine's flat buffers (models.py:111-113)
         self.last_loss = None
 
@@ -144,30 +137,7 @@ class SelfCriticNetwork(MODEL_init):
 
     def __init__(self, reward_fn=None):
         super(SelfCriticNetwork, self).__init__()
-        self.model = PolicyNetwork(num_vocab=self.num_vocab,
-                                   max_length=MAX_LENGTH + 2,
-                                   encode_dim_positions=ENCODE_DIM_POSITIONS,
-                                   encode_dim_features=ENCODE_DIM_FEATURES,
-                                   encode_input_size=ENCODE_INPUT_SIZE,
-                                   encode_q_k_dim=ENCODE_Q_K_DIM,
-                                   encode_v_dim=ENCODE_V_DIM,
-                                   encode_hidden_size=ENCODE_HIDDEN_SIZE,
-                                   encode_num_blocks=ENCODE_NUM_BLOCKS,
-                                   encode_num_heads=ENCODE_NUM_HEADS,
-                                   dim_word_embedding=DIM_WORD_EMBEDDING,
-                                   decode_input_size=DECODE_INPUT_SIZE,
-                                   decode_q_k_dim=DECODE_Q_K_DIM,
-                                   decode_v_dim=DECODE_V_DIM,
-                                   decode_hidden_size=DECODE_HIDDEN_SIZE,
-                                   decode_num_blocks=DECODE_NUM_BLOCKS,
-                                   decode_num_heads=DECODE_NUM_HEADS,
-                                   dropout=DROPOUT,
-                                   device=DEVICE,
-                                   move_first_image_feature=MOVE_FIRST_IMAGE_FAETURE,
-                                   split_position=SPLIT_POSITION,
-                                   split_image_objects=SPLIT_IMAGE_OBJECTS,
-                                   encode_mask=ENCODE_MASK,
-                                   pad_idx=PAD_IDX).to(DEVICE)
+        self.model = PolicyNetwork(**_model_kwargs(self.num_vocab)).to(DEVICE)
         g = globals()
         self.loss = ReinforcementLearningLoss(word_to_idx_path=WORD_TO_IDX_PATH,
                                               pad_idx=PAD_IDX,
