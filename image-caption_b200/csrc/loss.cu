@@ -101,6 +101,71 @@ xent_kernel(int V, T* __restrict__ logits, int64_t ldl, const int* __restrict__ 
   }
 }
 
+// The same loss / gradient with the whole row in REGISTERS (bf16 logits, V <= NV * 2048, V % 8 == 0, 16-byte aligned rows):
+// one 16-byte load and one 16-byte store per 8 logits and no shared-memory round trips -- the shared-memory version above
+// spends 72 % of its issue slots on 155 MB of traffic (profiles/r2_summary.md section 3).
+template <int NV>
+__global__ void __launch_bounds__(NT)
+xent_reg_kernel(int V, bf16* __restrict__ logits, int64_t ldl, const int* __restrict__ targets, int ignore_index,
+                const float* __restrict__ inv_count, float* __restrict__ row_loss, int write_grad) {
+  pdl_prologue();
+  __shared__ float red[NT / 32];
+  const int row = blockIdx.x;
+  bf16* x = logits + (int64_t)row * ldl;
+  const int tgt = targets[row];
+  const bool valid = tgt != ignore_index;
+  if (!valid && !write_grad) {
+    if (threadIdx.x == 0) row_loss[row] = 0.f;
+    return;
+  }
+  float v[NV][8];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int j = (i * NT + threadIdx.x) * 8;
+    if (j < V) {
+      const uint4 t = *reinterpret_cast<const uint4*>(x + j);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { v[i][2 * e] = __low2float(h[e]); v[i][2 * e + 1] = __high2float(h[e]); }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) mx = fmaxf(mx, v[i][e]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[i][e] = -INFINITY;
+    }
+  }
+  const float x_tgt = valid ? to_f32(x[tgt]) : 0.f;             // read before any thread overwrites the row (barriers below)
+  mx = block_max(mx, red);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { v[i][e] = __expf(v[i][e] - mx); sum += v[i][e]; }
+  }
+  sum = block_sum(sum, red);
+  if (threadIdx.x == 0) row_loss[row] = valid ? mx + logf(sum) - x_tgt : 0.f;
+  if (write_grad) {
+    const float sc = valid ? *inv_count : 0.f, inv_sum = 1.f / sum;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int j = (i * NT + threadIdx.x) * 8;
+      if (j < V) {
+        uint4 t;
+        uint32_t* w = reinterpret_cast<uint32_t*>(&t);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float g0 = (v[i][2 * e] * inv_sum - (j + 2 * e == tgt ? 1.f : 0.f)) * sc;
+          const float g1 = (v[i][2 * e + 1] * inv_sum - (j + 2 * e + 1 == tgt ? 1.f : 0.f)) * sc;
+          const __nv_bfloat162 hh = __floats2bfloat162_rn(g0, g1);
+          w[e] = *reinterpret_cast<const uint32_t*>(&hh);
+        }
+        *reinterpret_cast<uint4*>(x + j) = t;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(NT)
 xent_finalize_kernel(int M, const float* __restrict__ row_loss, const float* __restrict__ inv_count, int focal,
                      float* __restrict__ out) {
@@ -708,6 +773,13 @@ extern "C" int icap_xent(int dtype, int64_t M, int64_t V, void* logits, int64_t 
   int cached = smem <= 200 * 1024;
   if (!cached) smem = 0;
   cudaStream_t st = (cudaStream_t)stream;
+  static IcapEnv e_reg;
+  if (dtype == ICAP_BF16 && vec && V % 8 == 0 && V <= 5 * NT * 8 && e_reg.geti("ICAP_XENT_REG", 1) != 0) {
+    icap_launch(xent_reg_kernel<5>, (unsigned)M, NT, 0, st, (int)V, (bf16*)logits, ldl, targets, ignore_index, inv_count,
+                row_loss, write_grad);
+    ICAP_LAUNCH_CHECK("icap_xent");
+    return 0;
+  }
   static size_t cur_f = 48 * 1024, cur_b = 48 * 1024;
   if (dtype == ICAP_F32) {
     if (smem > cur_f) {
