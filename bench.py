@@ -87,7 +87,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
             self.t.start()
         except Exception:
@@ -205,6 +205,7 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["text"], "dropout": "on (0.2 / attention 0.1)" if ref.kind == "reference" else "off",
+                       "global_batch": bs, "batch_per_gpu": None, "parallelism": f"cpu, {torch.get_num_threads()} host threads",
                        "sample": f"each step = one train step on batch {bs}"},
             "cpu_baseline": {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": ref.kind,
                              "sample": sample},
@@ -577,7 +578,7 @@ def run_ours(args):
                 "step_model_flops_frac_of_sustained": step_tf / pk["tflops_sustained"]}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:       # CPU baselines: rank 0 at N = 1 only (the reference arm covers N > 1)
         cpu = cpu_baseline_sample(wl)
         if args.workload == "modelA" and not args.no_decode:
             # configs[0]: model B greedy B=8 on the CPU (reference) and on the GPU (bf16 timing + fp32 id parity)
