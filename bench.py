@@ -555,7 +555,8 @@ def run_ours(args):
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
-    if os.path.exists(tpath) and args.workload in ("modelA", "global2048"):   # the capture is of the model-A step only
+    if os.path.exists(tpath) and args.workload in ("modelA", "global2048") and BATCH == 256:   # the capture is of the
+        # model-A step at batch 256 only (bytes per launch grow with the batch: no figure for other per-GPU batches)
         tj = json.load(open(tpath))
         traffic = tj.get("dram_bytes_per_launch")
         traffic_src = ("static, NOT measured by this run: dram__bytes_read+write per launch from the ncu capture "
