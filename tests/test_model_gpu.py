@@ -446,8 +446,10 @@ def test_train_step_fused_auto_graph_equals_eager(monkeypatch):
         losses = [float(m.train_step_fused(f, p, c, lr=5e-4, train_mode=False)) for f, p, c in batches]
         out[graph] = (losses, {n: q.detach().clone() for n, q in m.state_dict().items()}, m.optimizer_state_dict())
         assert len(m._train_graphs) == (3 if graph == "1" else 0)
+    # the two trajectories of the note below differ by up to 9e-6 in the loss of step 5 (profiles/r2_fp32_bimodal_trajectory.log);
+    # a leaked warm-up step (one extra Adam update at lr 5e-4) moves the next losses by ~1e-2
     for a, b in zip(out["0"][0], out["1"][0]):
-        assert abs(a - b) <= 1e-5 * abs(a), (out["0"][0], out["1"][0])
+        assert abs(a - b) <= 1e-4 * abs(a), (out["0"][0], out["1"][0])
     # Whole tensors in norm: Adam's first steps move every weight by ~lr * sign(g), so an element whose gradient is at
     # the rounding-noise level of the fp32 atomics (embedding scatter-add, column sums) may flip between two runs.
     # A leaked warm-up step would move EVERY element by ~lr: ~2e-2 of the norm.
