@@ -198,6 +198,41 @@ def test_config1_shapes_bf16_and_fp32_vs_oracle():
     assert rel(mb.logits(f, p, c), ref_logits) < 2e-2
 
 
+@pytest.mark.parametrize("name", ["modelA", "modelB"])
+def test_full_width_reference_golden(name):
+    """The CUDA path against outputs of the UNMODIFIED reference at the benchmarked widths (tests/golden/full_width.pt,
+    made by tests/golden/make_golden_full.py): model A = ctor defaults (BASELINE configs[1-3]), model B = core/config.py
+    defaults (configs[0]); vocab 10k, 36 x 2048 regions.  fp32 mode: logits / loss within 1e-4, greedy and beam ids
+    identical except at reported near-ties; bf16 mode: logits / loss within 2e-2."""
+    import sys
+    sys.path.insert(0, GOLD)
+    try:
+        import make_golden_full as G
+    finally:
+        sys.path.remove(GOLD)
+    case = torch.load(os.path.join(GOLD, "full_width.pt"), weights_only=False)[name]
+    cfg, sd, f, p, c, sha = G.regenerate(name)
+    if sha != case["sha256"]:
+        pytest.skip("this torch build draws a different CPU random stream than the one the golden was made with")
+    kw = case["ctor"]
+    for precision, tol in (("fp32", 1e-4), ("bf16", 2e-2)):
+        m = build(kw, sd, precision)
+        lg = m.logits(f, p, c)
+        assert rel(lg[:, :, :64], case["logits_slice"]) < tol, precision
+        assert rel(lg.max(dim=-1).values, case["logits_row_max"]) < tol, precision
+        with torch.no_grad():
+            loss = float(m(f, p, c)["loss"])
+        assert abs(loss - float(case["loss"])) / float(case["loss"]) < tol, (precision, loss)
+        if precision == "fp32":
+            ids, att = m.generate_caption_vector(f, p)
+            assert ids.shape == case["greedy_ids"].shape and len(att) == cfg.max_length - 1
+            assert not ids_match_except_near_ties(ids, case["greedy_ids"], case["greedy_gaps"], what=name + " greedy")
+            for k in ((3, 5) if name == "modelA" else (3,)):
+                out = m.beam_search(f[:2], p[:2], beam_size=k)
+                assert not ids_match_except_near_ties(out, case[f"beam{k}_ids"], case[f"beam{k}_gaps"], tol=1e-6,
+                                                      what=f"{name} beam-{k}")
+
+
 # ------------------------------------------------------------------------------------------ oracle, model A shapes
 def model_a_cfg(**over):
     kw = dict(num_vocab=10000, max_length=22, encode_dim_positions=84, encode_dim_features=2048, output_name="x",

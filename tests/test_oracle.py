@@ -85,6 +85,42 @@ def test_policy_beam(name):
     assert torch.equal(ids, g["policy_beam3_ids"])
 
 
+def _full_case(name):
+    """tests/golden/full_width.pt: outputs of the unmodified reference at the benchmarked widths; weights / inputs are
+    regenerated from their seeds and must hash to what the reference was run on."""
+    sys.path.insert(0, GOLD)
+    try:
+        import make_golden_full as G
+    finally:
+        sys.path.remove(GOLD)
+    case = torch.load(os.path.join(GOLD, "full_width.pt"), weights_only=False)[name]
+    cfg, sd, f, p, c, sha = G.regenerate(name)
+    if sha != case["sha256"]:
+        pytest.skip("this torch build draws a different CPU random stream than the one the golden was made with")
+    return case, cfg, sd, f, p, c
+
+
+@pytest.mark.parametrize("name", ["modelA", "modelB"])
+def test_full_width_reference_outputs(name):
+    """The oracle against the reference at the BENCHMARKED widths (model A: ctor defaults, model B: core/config.py
+    defaults, vocab 10k, 36 x 2048 regions): logits, loss, greedy ids and decision gaps, beam ids."""
+    case, cfg, sd, f, p, c = _full_case(name)
+    B, T, V = case["batch"], cfg.max_length - 1, cfg.num_vocab
+    logits = O.logits_forward(sd, cfg, f, p, c).reshape(B, T, V)
+    torch.testing.assert_close(logits[:, :, :64], case["logits_slice"], rtol=1e-5, atol=2e-6)
+    torch.testing.assert_close(logits.max(dim=-1).values, case["logits_row_max"], rtol=1e-5, atol=2e-6)
+    assert torch.equal(logits.argmax(dim=-1), case["logits_row_argmax"])
+    assert abs(float(logits.double().abs().sum()) - float(case["logits_abs_sum"])) < 1e-6 * float(case["logits_abs_sum"])
+    torch.testing.assert_close(O.loss_from_logits(cfg, logits, c), case["loss"], rtol=1e-6, atol=1e-6)
+    ids, _, gaps = O.generate_caption_vector(sd, cfg, f, p, return_gaps=True)
+    assert torch.equal(ids, case["greedy_ids"])
+    torch.testing.assert_close(gaps, case["greedy_gaps"], rtol=1e-3, atol=2e-6)
+    k = 3                                               # beam 5 of model A was checked when the golden was generated
+    out, trace = O.beam_search(sd, cfg, f[:2], p[:2], beam_size=k, return_trace=True)
+    assert torch.equal(out, case[f"beam{k}_ids"])
+    torch.testing.assert_close(trace, case[f"beam{k}_gaps"], rtol=1e-3, atol=1e-9)
+
+
 def test_decode_captions():
     vocab = {0: "<NULL>", 1: "<START>", 2: "<END>", 3: "<UNK>", 4: "a", 5: "dog"}
     out = O.decode_captions(np.array([[1, 4, 5, 2, 0, 0], [1, 5, 0, 4, 0, 0]]), vocab)
