@@ -2,7 +2,7 @@
 configs[1-3]; model B = core/config.py defaults, configs[0]).  The 223 MB / 30 MB state_dicts are not stored: weights and
 inputs are regenerated from seeds with the torch CPU generator (oracle.init_state_dict / synthetic_batch; serial, so
 independent of the thread count) and pinned by a SHA-256 in the file; what IS stored are the reference's outputs on
-them -- loss, a logits slice + whole-tensor sums, greedy ids and top-2 gaps of every decision, beam-3 / beam-5 ids (first two
+them -- loss, a logits slice + whole-tensor sums, per-parameter gradient norms / sums / leading elements, greedy ids and top-2 gaps of every decision, beam-3 / beam-5 ids (first two
 images) with the candidate gaps of every beam step.  Seeds were picked so that no greedy decision is a near-tie
 (smallest top-2 gap: model A 0.13, model B 3.7e-4).
 
@@ -71,6 +71,13 @@ def main():
                 "loss": loss.detach().clone(), "logits_slice": lg[:, :, :64].clone(),
                 "logits_sum": lg.double().sum(), "logits_abs_sum": lg.double().abs().sum(),
                 "logits_row_max": lg.max(dim=-1).values.clone(), "logits_row_argmax": lg.argmax(dim=-1).clone()}
+        # every gradient of the teacher-forced loss, as (Frobenius norm, sum, first 32 elements) per parameter
+        model.zero_grad()
+        model(f, p, c)["loss"].backward()
+        case["grad_stats"] = {k: (float(q.grad.double().norm()), float(q.grad.double().sum()),
+                                  q.grad.reshape(-1)[:32].detach().clone())
+                              for k, q in model.named_parameters() if q.grad is not None}
+        model.zero_grad()
         # greedy: ids + the top-2 gap of every decision, from the reference's own per-step logits (classifer hook)
         steps = []
         h = model.classifer.register_forward_hook(lambda m, i, o: steps.append(o.detach().clone()))      # [B, V] per decision

@@ -121,6 +121,21 @@ def test_full_width_reference_outputs(name):
     torch.testing.assert_close(trace, case[f"beam{k}_gaps"], rtol=1e-3, atol=1e-9)
 
 
+@pytest.mark.parametrize("name", ["modelA", "modelB"])
+def test_full_width_reference_grads(name):
+    """Backward of the oracle against the reference at the benchmarked widths: Frobenius norm, sum and the leading 32
+    elements of every parameter gradient."""
+    case, cfg, sd, f, p, c = _full_case(name)
+    _, grads = O.loss_and_grads(sd, cfg, f, p, c)
+    assert set(case["grad_stats"]) <= set(grads)
+    for k, (norm, total, head) in case["grad_stats"].items():
+        g = grads[k]
+        assert abs(float(g.double().norm()) - norm) <= 1e-5 * norm + 1e-12, k
+        assert abs(float(g.double().sum()) - total) <= 1e-4 * norm + 1e-9, k
+        torch.testing.assert_close(g.reshape(-1)[:32], head, rtol=1e-4, atol=1e-6 * max(norm, 1e-30) + 1e-9,
+                                   msg=lambda m, k=k: f"{k}: {m}")
+
+
 def test_decode_captions():
     vocab = {0: "<NULL>", 1: "<START>", 2: "<END>", 3: "<UNK>", 4: "a", 5: "dog"}
     out = O.decode_captions(np.array([[1, 4, 5, 2, 0, 0], [1, 5, 0, 4, 0, 0]]), vocab)
